@@ -1,0 +1,107 @@
+"""
+Small, seeded versions of the BASELINE.json configs (C1..C5) used by the golden
+fixtures, the oracle tests and the GPU parity tests.  Pure data: builds the
+oracle-style problem dict (see oracle/smc_oracle.py) plus sampler arguments.
+Nothing here reads /root/reference.
+"""
+
+import numpy as np
+
+TRUE_COV = np.array([[0.5, 0.25, 0.005], [0.25, 0.25, 0.04], [0.005, 0.04, 1.0]])
+
+
+def noisy(clean, std, seed):
+    """Same draw as smcpy/utils/noise_generator.py:4-10 (normal(0,std,data.T.shape).T)."""
+    clean = np.atleast_2d(clean)
+    return np.random.default_rng(seed).normal(0, std, clean.T.shape).T + clean
+
+
+def linear_problem(m, sigma=0.5, data_seed=0, unknown_sigma=False):
+    x = np.linspace(0.5, 2.5, m)
+    data = noisy(2.0 * x + 3.5, 0.5, data_seed)[0]
+    priors = [("uniform", -6.0, 12.0), ("uniform", -6.0, 12.0)]
+    if unknown_sigma:
+        priors.append(("uniform", 0.0, 10.0))
+    return {
+        "model": ("linear", x),
+        "data": data,
+        "loglike": ("normal", None if unknown_sigma else sigma),
+        "priors": priors,
+        "names": ["a", "b"] + (["std"] if unknown_sigma else []),
+    }
+
+
+def spring_problem(n_out=100, nsub=4, data_seed=3):
+    t_end = 5.0
+    dt = t_end / (n_out - 1)
+    args = dict(x0=0.0, v0=0.0, t0=0.0, dt=dt, n_out=n_out, nsub=nsub)
+    t = np.arange(n_out) * dt
+    K, g = 1.67, 4.62
+    clean = (g / K) * (1.0 - np.cos(np.sqrt(K) * t))
+    data = noisy(clean, 0.5, data_seed)[0]
+    return {
+        "model": ("spring_mass", args),
+        "data": data,
+        "loglike": ("normal", None),
+        "priors": [("uniform", 0.0, 10.0)] * 3,
+        "names": ["K", "g", "std"],
+    }
+
+
+def mvn_problem(n_snap=50, data_seed=200):
+    X = np.arange(3, dtype=float)
+    rs = np.random.RandomState(data_seed)
+    data = np.tile(2.0 * X + 3.5, (n_snap, 1)) + rs.multivariate_normal([0, 0, 0], TRUE_COV, n_snap)
+    return {
+        "model": ("linear_features", X),
+        "data": data,
+        "loglike": ("mvnormal", [None] * 6),
+        "priors": [("uniform", 0.0, 6.0), ("uniform", 0.0, 6.0), ("improper_cov", 3)],
+        "names": ["a", "b"] + ["cov%d" % i for i in range(6)],
+    }
+
+
+def gauss_problem(d, data_seed=5):
+    data = np.random.default_rng(data_seed).normal(0, 1, d)
+    return {
+        "model": ("identity", d),
+        "data": data,
+        "loglike": ("normal", 1.0),
+        "priors": [("uniform", -10.0, 20.0)] * d,
+        "names": ["x%d" % i for i in range(d)],
+    }
+
+
+# name -> (problem builder, sampler kind, sampler kwargs, rng seed)
+CASES = {
+    "c1_adaptive": (lambda: linear_problem(100), "adaptive",
+                    dict(n=500, K=10, target_ess=0.8, resampler="standard"), 1),
+    "c2_fixed_strat": (lambda: linear_problem(200, data_seed=7), "fixed",
+                       dict(n=600, K=5, phi=np.linspace(0, 1, 12), ess_threshold=0.8,
+                            resampler="stratified"), 2),
+    "c2_fixed_unknown_std": (lambda: linear_problem(60, data_seed=8, unknown_sigma=True), "fixed",
+                             dict(n=400, K=6, phi=np.linspace(0, 1, 15) ** 2, ess_threshold=0.6,
+                                  resampler="standard"), 3),
+    "c3_spring": (lambda: spring_problem(100, 4), "adaptive",
+                  dict(n=300, K=3, target_ess=0.8, resampler="standard"), 4),
+    "c4_mvn": (lambda: mvn_problem(50), "adaptive",
+               dict(n=300, K=5, target_ess=0.8, resampler="standard", iw_seed=11), 5),
+    "c5_gauss8": (lambda: gauss_problem(8), "adaptive",
+                  dict(n=400, K=4, target_ess=0.8, resampler="stratified"), 6),
+    "c5_gauss32": (lambda: gauss_problem(32), "adaptive",
+                   dict(n=200, K=3, target_ess=0.85, resampler="standard"), 7),
+}
+
+
+def mvn_init_params(n, seed):
+    """Host-side prior draw for the MVNormal case (uniform a,b + inverse-Wishart
+    covariance columns), as the reference's ImproperCov.rvs does it
+    (smcpy/priors.py:118-123); stored in the fixture so the box needs no scipy
+    stream parity."""
+    from scipy.stats import invwishart, uniform
+    rng = np.random.default_rng(seed)
+    a = uniform(0.0, 6.0).rvs(n, random_state=rng)
+    b = uniform(0.0, 6.0).rvs(n, random_state=rng)
+    cov = invwishart(5, np.eye(3)).rvs(n, random_state=rng)
+    i1, i2 = np.triu_indices(3)
+    return np.column_stack([a, b, cov[:, i1, i2]])

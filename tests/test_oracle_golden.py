@@ -1,0 +1,230 @@
+"""
+Pins oracle/smc_oracle.py (CPU, no GPU needed):
+  (1) against the known-answer vectors the reference's own unit tests hold
+      (file:line of each cited), and
+  (2) against tests/golden/*.npz, outputs of the unmodified reference generated
+      in the build container by tests/golden/make_golden.py.
+"""
+
+import math
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import smc_oracle as orc
+from tests.golden import configs
+from tests.helpers import golden, run_oracle_case
+
+
+# ------------------------------------------------------------------ (1) reference KATs
+@pytest.mark.parametrize("u, expected", [
+    ([0.3, 0.3, 0.7], [1, 1, 2]), ([0.3, 0.05, 0.05], [1, 0, 0]), ([0.3, 0.05, 0.7], [1, 0, 2]),
+    ([0.05, 0.05, 0.7], [0, 0, 2]), ([0.3, 0.7, 0.3], [1, 2, 1])])
+def test_kat_standard_resample_indices(u, expected):
+    # tests/unit/test_updater.py:279-325
+    lw, w = orc.normalize_log_weights(np.log([0.1, 0.4, 0.5]))
+    np.testing.assert_array_equal(orc.resample_indices(w, np.array(u)), expected)
+
+
+@pytest.mark.parametrize("u, expected", [([0.3, 0.5, 0.5], [0, 1, 2]), ([0.4, 0.5, 0.5], [1, 1, 2])])
+def test_kat_stratified_nonuniform(u, expected):
+    # tests/unit/test_updater.py:342-361 (weights [.1,.6,.3] from the fixture at :29-35)
+    class R:
+        def uniform(self, a, b, n):
+            return np.array(u)
+    uu = orc.resample_uniforms("stratified", 3, R())
+    np.testing.assert_array_equal(orc.resample_indices(np.exp(np.log([0.1, 0.6, 0.3])), uu), expected)
+
+
+@pytest.mark.parametrize("phi_old, target, expected", [
+    (1, 0.8, 1), (0.5, 0.8, -0.5364679374), (0, 0.8, -1.8650126), (1, 1, 0)])
+def test_kat_ess_margin(phi_old, target, expected):
+    # tests/unit/test_samplers.py:97-127
+    ll = np.arange(5.0).reshape(-1, 1)
+    lp = np.ones((5, 1))
+    assert orc.ess_margin(ll, lp, 1, phi_old, target) == pytest.approx(expected)
+    assert orc.ess_margin(ll, lp, 1, phi_old, target, lq=np.ones((5, 1))) == pytest.approx(expected)
+
+
+def test_kat_ess_margin_all_neginf():
+    # tests/unit/test_samplers.py:129-148,257-264
+    ll = np.full((5, 1), -np.inf)
+    assert orc.ess_margin(ll, np.ones((5, 1)), 1, 0, 0.8) == -5 * 0.8
+    assert orc.ess_margin(ll, np.ones((5, 1)), 0.5, 0.5, 0.8) == pytest.approx(5 - 4.0)
+
+
+def test_kat_particles():
+    # tests/unit/test_particles.py:34-53,88-92
+    lw, w = orc.normalize_log_weights([0.2] * 10)
+    np.testing.assert_array_equal(lw, np.log(np.full((10, 1), 0.1)))
+    assert orc.logsum([0.2] * 10) == pytest.approx(2.50258509)
+    assert orc.compute_ess(w) == pytest.approx(10.0)
+    # tests/unit/test_particles.py:95-124 weighted mean / variance
+    _, w = orc.normalize_log_weights(np.log([1, 3]))
+    p = np.array([[1, 4], [5 / 3, 2]])
+    np.testing.assert_allclose(orc.weighted_mean(p, w), [1.5, 2.5])
+    # tests/integration/test_single_param_cov.py:7-16
+    _, w = orc.normalize_log_weights(np.log([0.5, 0.5]))
+    c = orc.weighted_cov(np.array([[1.0], [2.0]]) * math.sqrt(2), w)
+    assert c.shape == (1, 1) and c[0, 0] == pytest.approx(0.5)
+
+
+def test_kat_normal_loglike():
+    # tests/unit/test_vector_mcmc.py:78-96 (model from its stub fixture :9-18)
+    x = np.array([1.0, 2, 3])
+    model = lambda q: (q[:, 0, None] * 2 + 3.25 * q[:, 1, None] - q[:, 2, None] ** 2) * x
+    prob = {"model": ("callable", model), "data": np.array([5.0, 4, 9]),
+            "loglike": ("normal", 1 / np.sqrt(2 * np.pi))}
+    th = np.array([[0, 1, 0.5]] * 4)
+    np.testing.assert_array_almost_equal(orc.log_likelihood(prob, th), np.full((4, 1), -8 * np.pi))
+    prob["loglike"] = ("normal", None)
+    th = np.array([[0, 1, 0.5, 1 / np.sqrt(2 * np.pi)]] * 4)
+    np.testing.assert_array_almost_equal(orc.log_likelihood(prob, th), np.full((4, 1), -8 * np.pi))
+
+
+@pytest.mark.parametrize("n_snap", [1, 2, 5])
+@pytest.mark.parametrize("args", [(1, 2, 3, -1, 0, -2), (None, 2, 3, -1, 0, None),
+                                  (1, None, None, None, 0, None), (None,) * 6])
+def test_kat_mvnormal(n_snap, args):
+    # tests/unit/test_likelihoods.py:107-155  (NB the matrix there is indefinite; the
+    # reference evaluates it through det/inv, so compare on a PD variant too below)
+    base = (1, 2, 3, -1, 0, -2)
+    vec = [1, 2] + [base[i] for i, a in enumerate(args) if a is None]
+    th = np.tile(vec, (3, 1)).astype(float)
+    prob = {"model": ("callable", lambda t: np.ones((t.shape[0], 3))),
+            "data": np.ones((n_snap, 3)) * 2, "loglike": ("mvnormal", list(args))}
+    cov = orc.unpack_upper(np.array([base], float), 3)[0]
+    if np.all(np.linalg.eigvalsh(cov) > 0):
+        np.testing.assert_array_almost_equal(orc.log_likelihood(prob, th),
+                                             np.full((3, 1), -4.54482456 * n_snap))
+    else:                                                     # indefinite: det/inv formula
+        e = np.ones(3) - 2
+        ref = n_snap * (-1.5 * np.log(2 * np.pi) - 0.5 * np.log(np.linalg.det(cov))
+                        - 0.5 * e @ np.linalg.inv(cov) @ e)
+        assert ref == pytest.approx(-4.54482456 * n_snap)
+
+
+def test_kat_mvnormal_1d():
+    # tests/unit/test_likelihoods.py:107-119
+    prob = {"model": ("callable", lambda t: np.ones((t.shape[0], 1))),
+            "data": np.full((5, 1), 3.0), "loglike": ("mvnormal", [1 / (2 * np.pi)])}
+    np.testing.assert_allclose(orc.log_likelihood(prob, np.ones((4, 2))), np.full((4, 1), -4 * np.pi * 5))
+
+
+def test_kat_path_logpdf():
+    # tests/unit/test_kernel_overrides.py:26-58,97-140
+    ll = np.full((3, 1), 2.0)
+    lp = np.ones((3, 2))
+    for phi, want in ((0.0, 2.0), (0.5, 3.0), (1.0, 4.0)):
+        np.testing.assert_array_equal(orc.path_logpdf(ll, lp, phi), np.full((3, 1), want))
+    lq = np.full((3, 1), 3.0)
+    np.testing.assert_array_equal(orc.path_logpdf(ll, lp, 0.2, 1.0, lq), np.full((3, 1), 3.2))
+    lam, _ = orc.path_lambda(0.4)
+    np.testing.assert_array_equal(orc.path_logpdf(ll, lp, 0.2, lam, lq), np.full((3, 1), 2.9))
+    lam, _ = orc.path_lambda([0.1, 0.3])
+    np.testing.assert_array_equal(orc.path_logpdf(ll, lp, 0.2, lam, lq), np.full((3, 1), 2.4))
+
+
+def test_kat_priors_and_mll():
+    # tests/unit/test_priors.py:35-49 inclusive bounds; scipy uniform quirk Q18
+    np.testing.assert_array_equal(orc.logpdf_improper_uniform(np.array([-6.0, 6.0, 6.1]), -6, 6),
+                                  [0, 0, -np.inf])
+    assert np.isfinite(orc.logpdf_uniform(np.array([np.nextafter(6.0, 7.0)]), -6.0, 12.0))[0]
+    # tests/unit/test_priors.py:174-185 PD test
+    np.testing.assert_array_equal(orc.logpdf_improper_cov(np.array([[1, 0, 1.0], [1, 2, 1.0]]), 2),
+                                  [0, -np.inf])
+    # tests/unit/test_storage.py:62-73 mll = cumsum with leading 0
+
+    class S:
+        def __init__(self, t):
+            self.total_unnorm_log_weight = t
+    np.testing.assert_array_equal(orc.marginal_log_likelihoods([S(1), S(2), S(3)]), [0, 1, 3, 6])
+
+
+def test_bisect_emulation_matches_scipy():
+    # third-party dependency of samplers.py:254-259 (scipy 1.18.1, not vendored)
+    from scipy.optimize import bisect
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        r = rng.uniform(1e-6, 0.999)
+        a = rng.uniform(0, r * 0.9)
+        f = lambda x: math.exp(-3 * x) - math.exp(-3 * r)
+        got, nf = orc.bisect_scipy(f, a, 1.0)
+        ref, info = bisect(f, a, 1.0, full_output=True)
+        assert got == ref and nf == info.function_calls
+
+
+# ------------------------------------------------------------------ (2) reference fixtures
+U = golden("unit_vectors")
+
+
+def test_fixture_particles():
+    lw, w = orc.normalize_log_weights(U["p_lw_in"])
+    np.testing.assert_array_equal(lw, U["p_log_w"])
+    np.testing.assert_array_equal(w, U["p_w"])
+    assert orc.logsum(U["p_lw_in"]) == U["p_total"]
+    assert orc.compute_ess(w) == U["p_ess"]
+    np.testing.assert_allclose(orc.weighted_cov(U["p_params"], w), U["p_cov"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(orc.weighted_mean(U["p_params"], w), U["p_mean"], rtol=1e-14)
+
+
+@pytest.mark.parametrize("tag, req, prop", [("plain", 1, False), ("req", [0.3, 0.6], False),
+                                            ("prop", 1, True), ("propreq", 0.4, True)])
+def test_fixture_path(tag, req, prop):
+    lam, _ = orc.path_lambda(req)
+    ll, lp = U["path_ll"], U["path_lp"]
+    lq = U["path_lq"] if prop else None
+    phis = U["path_phis"]
+    for i in range(1, len(phis)):
+        np.testing.assert_array_equal(orc.inc_log_weights(ll, lp, phis[i], phis[i - 1], lam, lq),
+                                      U["path_%s_inc" % tag][i - 1])
+        np.testing.assert_array_equal(orc.path_logpdf(ll, lp, phis[i], lam, lq),
+                                      U["path_%s_logpdf" % tag][i - 1])
+
+
+def test_fixture_resample_likelihoods_priors():
+    np.testing.assert_array_equal(orc.resample_indices(U["rs_w"], U["rs_u"]), U["rs_idx"])
+    prob = {"model": ("linear", U["nl_x"]), "data": U["nl_data"], "loglike": ("normal", 0.7)}
+    np.testing.assert_allclose(orc.loglike_normal(prob, U["nl_theta"][:, :2]), U["nl_fixed"], rtol=1e-14)
+    prob["loglike"] = ("normal", None)
+    np.testing.assert_allclose(orc.loglike_normal(prob, U["nl_theta"]), U["nl_unknown"], rtol=1e-14)
+    prob = {"model": ("linear_features", np.arange(3.0)), "data": U["mv_data"],
+            "loglike": ("mvnormal", [None] * 6)}
+    np.testing.assert_allclose(orc.loglike_mvnormal(prob, U["mv_theta"]), U["mv_all"], rtol=1e-12)
+    prob["loglike"] = ("mvnormal", [0.5, None, 0.005, None, 0.04, 1.0])
+    np.testing.assert_allclose(orc.loglike_mvnormal(prob, U["mv_theta_mixed"]), U["mv_mixed"], rtol=1e-12)
+    np.testing.assert_array_equal(orc.logpdf_uniform(U["pr_x"], -6.0, 12.0), U["pr_uniform"])
+    np.testing.assert_array_equal(orc.logpdf_improper_uniform(U["pr_x"], -6, 6), U["pr_improper"])
+    np.testing.assert_array_equal(orc.logpdf_improper_cov(U["pr_cov_x"], 3), U["pr_cov"])
+
+
+def test_fixture_adaptive_phi():
+    for i, ll in enumerate(U["ad_ll"]):
+        ll = ll.reshape(-1, 1)
+        lp = np.full_like(ll, -np.log(144.0))
+        for j, phi_old in enumerate((0.0, 1e-4, 0.3)):
+            assert orc.optimize_phi(ll, lp, phi_old, 0.8) == U["ad_phi"][i, j]
+            m = orc.ess_margin(ll, lp, min(1.0, phi_old + 0.01), phi_old, 0.8)
+            assert m == pytest.approx(U["ad_margin"][i, j], rel=1e-13)
+
+
+@pytest.mark.parametrize("name", list(configs.CASES))
+def test_fixture_full_runs(name):
+    """Whole sample() runs: oracle driven by the same generator seed reproduces
+    the reference's phi sequence, mll, ESS, indices, covariances and particles."""
+    g = golden(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steps, mll, phis, rng = run_oracle_case(name, g)
+    np.testing.assert_allclose(phis, g["phi"], rtol=1e-13)
+    np.testing.assert_allclose(mll, g["mll"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose([s.ess for s in steps[1:]], g["ess"], rtol=1e-10)
+    np.testing.assert_array_equal([s.resampled for s in steps[1:]], g["resampled"])
+    np.testing.assert_array_equal(steps[1].resample_idx if steps[1].resampled else np.zeros(0), g["idx_1"])
+    np.testing.assert_array_equal(np.array([s.accepts for s in steps[1:]]), g["accepts"])
+    np.testing.assert_allclose(np.array([s.cov for s in steps[1:]]), g["cov"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(steps[-1].params, g["params_last"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(steps[-1].log_likes, g["log_likes_last"], rtol=1e-10)
+    np.testing.assert_allclose([s.mutation_ratio for s in steps], g["mutation_ratio"])
+    np.testing.assert_array_equal(rng.uniform(0, 1, 4), g["rng_check"])     # tape exactly exhausted
