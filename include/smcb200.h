@@ -1,0 +1,243 @@
+/*
+ * smcb200.h -- C ABI of libsmcb200.so: the B200 (sm_100a) implementation of
+ * nasa/SMCPy's data-parallel particle hot path
+ *     reweight -> ESS / phi bisection -> resample -> covariance -> K x Metropolis.
+ *
+ * The reference (pure Python, v0.1.9) has no FFI; each entry point below names the
+ * reference function(s) it replaces (file:line relative to the reference checkout).
+ * Conventions
+ *   - plain pointers and sizes only; every array pointer is a DEVICE pointer unless
+ *     the parameter is documented as host; `stream` is a cudaStream_t passed as void*;
+ *   - nothing is allocated inside: the caller owns all buffers, including one scratch
+ *     `ws` of at least smcb_workspace_bytes(n, d) bytes, zero-initialised once
+ *     (every kernel leaves its tickets / counters reset);
+ *   - all calls are asynchronous on `stream`; results the host needs are written to
+ *     device scalars and read at step boundaries;
+ *   - return value 0 = ok, otherwise an SMCB_ERR_* code; smcb_last_error() gives text;
+ *   - particles are structure-of-arrays: parameter c of particle i is
+ *     params[c * stride + i]; all arithmetic is IEEE fp64; indices are int64.
+ */
+#ifndef SMCB200_H
+#define SMCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMCB_VERSION 100            /* 0.1.0 */
+#define SMCB_MAX_PARAMS 32          /* fused Metropolis kernels: d <= 32 */
+#define SMCB_MAX_PRIORS 32
+#define SMCB_MAX_COV_ARGS 6         /* MVNormal: F <= 3 features -> F(F+1)/2 packed terms */
+#define SMCB_MAX_MCMC_STEPS 4096    /* accept-count history length per mutate call */
+
+enum { SMCB_OK = 0, SMCB_ERR_ARG = 1, SMCB_ERR_CUDA = 2, SMCB_ERR_UNSUPPORTED = 3 };
+
+/* built-in device models: a model maps (N, n_model_params) -> (N, n_data) */
+enum {
+    SMCB_MODEL_LINEAR = 1,       /* y_j = a * x_j + b           (README.md:64-79) */
+    SMCB_MODEL_SPRING_MASS = 2,  /* x'' = -K x + g, RK4 device integrator
+                                    (examples/spring_mass/spring_mass_model.py:8-52) */
+    SMCB_MODEL_IDENTITY = 3      /* y_j = theta_j               (config C5) */
+};
+/* log-likelihoods (smcpy/log_likelihoods.py) */
+enum { SMCB_LL_NORMAL = 1 /* :22-49 */, SMCB_LL_MVNORMAL = 2 /* :121-192 */ };
+/* priors (smcpy/mcmc/vector_mcmc.py:98-114) */
+enum {
+    SMCB_PRIOR_UNIFORM = 1,           /* scipy.stats.uniform(loc=a, scale=b) */
+    SMCB_PRIOR_IMPROPER_UNIFORM = 2,  /* smcpy/priors.py:6-35, bounds [a, b] inclusive */
+    SMCB_PRIOR_IMPROPER_COV = 3       /* smcpy/priors.py:93-147, ncols x ncols PD test */
+};
+/* device error-flag bits (checked by the host at step boundaries) */
+enum {
+    SMCB_FLAG_PRIOR_OOB = 1,   /* incoming particle has zero prior (vector_mcmc.py:199-203) */
+    SMCB_FLAG_MODEL_NAN = 2,   /* NaN in model output (log_likelihoods.py:14-15) */
+    SMCB_FLAG_COV_NOT_PD = 4,  /* MVNormal covariance not PD where the likelihood needed it */
+    SMCB_FLAG_CHOL_FAIL = 8    /* proposal covariance not PD (vector_mcmc.py:224-236) */
+};
+/* resampling uniforms (smcpy/resampler_rngs.py:4-9; systematic is an extension) */
+enum { SMCB_RESAMPLE_STANDARD = 0, SMCB_RESAMPLE_STRATIFIED = 1, SMCB_RESAMPLE_SYSTEMATIC = 2 };
+/* CDF scan modes */
+enum {
+    SMCB_SCAN_SEQUENTIAL = 0,  /* one fp64 add chain, bit-equal to np.cumsum (parity mode) */
+    SMCB_SCAN_LOOKBACK = 1     /* single-pass decoupled look-back, deterministic (fast mode) */
+};
+
+typedef struct smcb_prior {
+    int32_t kind;    /* SMCB_PRIOR_* */
+    int32_t ncols;   /* IMPROPER_COV: matrix size; else 1 */
+    double a, b;     /* UNIFORM: loc, scale; IMPROPER_UNIFORM: lower, upper */
+    double logp_in;  /* log-density inside the support (-log(scale), or 0) */
+} smcb_prior_t;
+
+/* model + likelihood + priors of one calibration problem; plain data, passed by value
+ * to the kernels.  Replaces the VectorMCMC constructor arguments
+ * (smcpy/mcmc/vector_mcmc.py:11-34). */
+typedef struct smcb_problem {
+    int32_t model_id;        /* SMCB_MODEL_* */
+    int32_t loglike_id;      /* SMCB_LL_* */
+    int32_t n_params;        /* d: all sampled columns, incl. sigma / covariance terms */
+    int32_t n_model_params;  /* leading columns handed to the model */
+    int32_t n_data;          /* Normal: M data points; MVNormal: F features */
+    int32_t n_snapshots;     /* MVNormal: S rows of data; else 1 */
+    int32_t sigma_is_param;  /* Normal: 1 -> last column is the std-dev (args=None) */
+    int32_t n_priors;
+    double sigma;            /* Normal: fixed std-dev when sigma_is_param == 0 */
+    double model_args[8];    /* SPRING_MASS: x0, v0, dt, nsub */
+    const double* data;      /* device: y[M] or data[S][F] row-major */
+    const double* xgrid;     /* device: LINEAR x[M] (MVNormal: X[F]); else NULL */
+    double cov_fixed[SMCB_MAX_COV_ARGS];      /* MVNormal packed upper-tri, fixed values */
+    int32_t cov_param_col[SMCB_MAX_COV_ARGS]; /* -1 = fixed, else parameter column */
+    smcb_prior_t priors[SMCB_MAX_PRIORS];
+} smcb_problem_t;
+
+/* GeometricPath state (smcpy/paths.py:64-112): exponents are derived inside the
+ * library exactly as paths.py:94-95 does. */
+typedef struct smcb_path {
+    double phi, phi_prev, lambda;
+} smcb_path_t;
+
+/* random numbers for one Metropolis step.  mode 0: Philox4x32-10 keyed by
+ * (seed; global particle id, stream) -- results do not depend on the GPU count;
+ * mode 1: replay a host tape drawn in the reference's order:
+ * z = normal(0,1,(N,d)) row-major, u = uniform(0,1,(N,1)). */
+typedef struct smcb_rng {
+    int32_t mode;
+    uint64_t seed;
+    uint64_t stream;     /* unique per use (host-incremented counter) */
+    int64_t id_offset;   /* global id of local particle 0 (multi-GPU shards) */
+    const double* z;     /* replay: device (N, d) row-major */
+    const double* u;     /* replay: device (N) */
+} smcb_rng_t;
+
+/* ---- library --------------------------------------------------------------------- */
+int smcb_version(void);
+const char* smcb_last_error(void);
+size_t smcb_workspace_bytes(int64_t n, int32_t d);
+
+/* ---- layout / plumbing ----------------------------------------------------------- */
+/* (N,d) row-major <-> SoA (d, stride); kernel_base.py:53-66 dict<->array conversions */
+int smcb_aos_to_soa(const double* aos, double* soa, int64_t n, int32_t d, int64_t stride, void* stream);
+int smcb_soa_to_aos(const double* soa, double* aos, int64_t n, int32_t d, int64_t stride, void* stream);
+int smcb_fill_f64(double* dst, int64_t n, double value, void* stream);
+
+/* ---- (a) tempered reweighting + LSE normalisation + ESS -------------------------- */
+/* un_lw = log_w_in + [target(phi) - target(phi_prev)]   (paths.py:86-105, updater.py:122-133)
+ * then normalise (particles.py:141-150), total_unnorm_log_weight (particles.py:81,200-205),
+ * ESS (particles.py:158-162).  lq = proposal logpdf or NULL (-> prior, paths.py:107-112).
+ * log_w_in NULL = uniform log(1/n_global).
+ * scalars_out (device, 8 doubles): [0] max un_lw, [1] S1 = sum exp(un_lw-max),
+ * [2] S2 = sum exp(2(un_lw-max)), [3] total_unnorm_log_weight, [4] ESS, [5] log S1. */
+int smcb_reweight(int64_t n, const double* ll, const double* lp, const double* lq,
+                  const double* log_w_in, int64_t n_global, const smcb_path_t* path,
+                  double* log_w_out, double* w_out, double* scalars_out, void* ws, void* stream);
+/* elementwise path values (host-facing GeometricPath wrappers): mode 0 = logpdf at phi
+ * (paths.py:81-84), mode 1 = inc_log_weights phi_prev -> phi (paths.py:86-91) */
+int smcb_path_eval(int64_t n, const double* ll, const double* lp, const double* lq,
+                   const smcb_path_t* path, int32_t mode, double* out, void* stream);
+/* multi-GPU split of the same: per-rank (max, S1, S2) -> [all-gather] -> merge -> finalize */
+int smcb_reweight_partials(int64_t n, const double* ll, const double* lp, const double* lq,
+                           const double* log_w_in, int64_t n_global, const smcb_path_t* path,
+                           double* partial_out /*3*/, void* ws, void* stream);
+int smcb_lse_merge(const double* partials /*n_parts x 3*/, int32_t n_parts, double* scalars_out,
+                   void* stream);
+int smcb_reweight_finalize(int64_t n, const double* ll, const double* lp, const double* lq,
+                           const double* log_w_in, int64_t n_global, const smcb_path_t* path,
+                           const double* scalars, double* log_w_out, double* w_out, void* stream);
+
+/* ---- (b) adaptive phi: device bisection of ESS(phi) = target ---------------------- */
+/* AdaptiveSampler.optimize_step / predict_ess_margin (samplers.py:250-301) with the
+ * decision sequence of scipy.optimize.bisect (xtol 2e-12, rtol 8.88e-16, maxiter 100).
+ * No host round-trip: the whole search is enqueued on `stream`.
+ * state (device, 16 doubles): [0] result phi, [1] #function evals, [2] done flag,
+ *   [3] xa, [4] dm, [5] fa, [6] current x, [7] last margin, [8] full-step margin.
+ * lp may be NULL when the summed log-prior is the same for every particle (lp_const). */
+int smcb_ess_bisect(int64_t n, const double* ll, const double* lp, const double* lq,
+                    double lp_const, double phi_old, double lambda, double target_ess,
+                    int64_t n_global, double* state, void* ws, void* stream);
+/* multi-GPU pieces: begin -> { partial -> [all-gather] -> update } x smcb_ess_bisect_max_iters */
+int smcb_ess_bisect_begin(double phi_old, double* state, void* stream);
+int smcb_ess_partial(int64_t n, const double* ll, const double* lp, const double* lq,
+                     double lp_const, double phi_old, double lambda, const double* state,
+                     double* partial_out /*3*/, void* ws, void* stream);
+int smcb_ess_bisect_update(const double* partials, int32_t n_parts, double phi_old,
+                           double target_ess, int64_t n_global, double* state, void* stream);
+int smcb_ess_bisect_max_iters(void);
+
+/* ---- (c) resampling ---------------------------------------------------------------- */
+/* u for `count` global slots starting at `first` out of n_global (resampler_rngs.py:4-9) */
+int smcb_resample_uniforms(int32_t kind, int64_t n_global, int64_t first, int64_t count,
+                           uint64_t seed, uint64_t stream_id, double* u_out, void* stream);
+/* inclusive prefix sum of normalised weights -> CDF (np.cumsum, updater.py:152) */
+int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mode, void* ws, void* stream);
+/* idx_k = #{j : cdf_j <= u_k}  (np.digitize / searchsorted side='right', updater.py:152),
+ * clamped to n_cdf-1 (documented divergence from the reference's IndexError, quirk Q4) */
+int smcb_searchsorted(const double* cdf, int64_t n_cdf, const double* u, int64_t n_u,
+                      int64_t* idx_out, void* stream);
+/* dst[c][k] = src[c][idx[k]] for n_cols SoA columns (updater.py:140-143) */
+int smcb_gather(const double* src, int64_t src_stride, double* dst, int64_t dst_stride,
+                const int64_t* idx, int64_t n_out, int32_t n_cols, void* stream);
+/* number of distinct ancestors (updater.py:154-165); flags = n_src bytes of scratch */
+int smcb_count_unique(const int64_t* idx, int64_t n_idx, int64_t n_src, int64_t* count_out,
+                      void* ws, void* stream);
+
+/* ---- weighted mean / covariance (particles.py:189-198, np.cov ddof=0 aweights) ---- */
+/* mean_out[d], cov_out[d*d] (device).  sums_out (device, 1+d+d*d doubles) receives the raw
+ * partial sums [sum w, sum w x, sum w (x-m)(x-m)^T] for the multi-GPU all-reduce. */
+int smcb_weighted_cov(const double* params, int64_t stride, const double* w, int64_t n, int32_t d,
+                      double* mean_out, double* cov_out, double* sums_out, void* ws, void* stream);
+int smcb_weighted_sums1(const double* params, int64_t stride, const double* w, int64_t n, int32_t d,
+                        double* sums_out /*1+d*/, void* ws, void* stream);
+int smcb_mean_from_sums(const double* sums /*1+d*/, int32_t d, double* mean_out, void* stream);
+int smcb_weighted_sums2(const double* params, int64_t stride, const double* w, int64_t n, int32_t d,
+                        const double* mean, double* sums_out /*d*d*/, void* ws, void* stream);
+int smcb_cov_from_sums(const double* wsum /*1*/, const double* sums2 /*d*d*/, int32_t d,
+                       double* cov_out, void* stream);
+/* lower Cholesky factor (np.linalg.cholesky, vector_mcmc.py:225); sets SMCB_FLAG_CHOL_FAIL */
+int smcb_cholesky(const double* cov, int32_t d, double* chol_out, int32_t* flags, void* stream);
+
+/* ---- (d) vectorised Metropolis ------------------------------------------------------ */
+/* log-priors + log-likelihood of incoming particles
+ * (vector_mcmc.py:162-166 _initialize_probabilities, initializer.py:66-73).
+ * lp_cols_out (optional, n_priors x stride) = un-summed log priors (vector_mcmc.py:98-111). */
+int smcb_mh_init(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
+                 double* ll_out, double* lp_out, double* lp_cols_out, int32_t* flags, void* stream);
+/* log-priors only: lp_out[n] summed (vector_mcmc_kernel.py:33-36), lp_cols_out optional
+ * (n_priors x stride) un-summed (vector_mcmc.py:98-111) */
+int smcb_log_priors(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
+                    double* lp_out, double* lp_cols_out, void* stream);
+/* one fused smc_metropolis step (vector_mcmc.py:168-183 + :55-60): Gaussian random-walk
+ * proposal x + sqrt(s) L z, priors, model, likelihood, tempered ratio, accept/reject, in place.
+ * accept_counts (device, int64[SMCB_MAX_MCMC_STEPS]): slot `step` receives this step's number
+ * of accepted particles; slots < step (already all-reduced across GPUs by the caller) give
+ * the covariance scale s (x1/5 below 30 %, x2 above 70 %). `moved` (n bytes) |= accepted. */
+int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride,
+                 int64_t n, int64_t n_global, double* ll, double* lp, uint8_t* moved,
+                 const double* chol, int64_t* accept_counts, int32_t step, const smcb_rng_t* rng,
+                 int32_t* flags, void* stream);
+/* fraction of particles that moved (mutator.py:69-71): count of non-zero bytes */
+int smcb_count_moved(const uint8_t* moved, int64_t n, int64_t* count_out, void* ws, void* stream);
+/* initial particles from uniform priors on the device (vector_mcmc.py:91-96) */
+int smcb_sample_priors(const smcb_problem_t* prob, double* params, int64_t stride, int64_t n,
+                       uint64_t seed, uint64_t stream_id, int64_t id_offset, void* stream);
+
+/* un-fused pieces for user models given as torch callables on device tensors:
+ * propose -> [user model] -> row-wise Normal log-likelihood -> accept */
+int smcb_mh_propose(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
+                    int64_t n_global, const double* chol, const int64_t* accept_counts, int32_t step,
+                    const smcb_rng_t* rng, double* new_params /*SoA*/, double* new_lp, void* stream);
+int smcb_normal_loglike_rows(const double* outputs /*(n, m) row-major*/, int64_t n, int32_t m,
+                             const double* data, const double* sigma_col /*or NULL*/, double sigma,
+                             const double* lp /*or NULL: rows with -inf keep 0*/, double* ll_out,
+                             int32_t* flags, void* stream);
+int smcb_mh_accept(const smcb_path_t* path, double* params, const double* new_params, int64_t stride,
+                   int32_t d, int64_t n, double* ll, const double* new_ll, double* lp,
+                   const double* new_lp, uint8_t* moved, int64_t* accept_counts, int32_t step,
+                   const smcb_rng_t* rng, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMCB200_H */

@@ -1,0 +1,149 @@
+"""
+ctypes binding of libsmcb200.so (C ABI in include/smcb200.h).
+
+There is no CPU fallback: importing this module without the built library, or
+using it without a CUDA device, raises.  Build with `python -m smcpy_b200.build`.
+"""
+
+import ctypes as C
+import os
+
+import torch
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libsmcb200.so")
+
+MAX_PARAMS = 32
+MAX_PRIORS = 32
+MAX_COV_ARGS = 6
+MAX_MCMC_STEPS = 4096
+
+MODEL_LINEAR, MODEL_SPRING_MASS, MODEL_IDENTITY = 1, 2, 3
+LL_NORMAL, LL_MVNORMAL = 1, 2
+PRIOR_UNIFORM, PRIOR_IMPROPER_UNIFORM, PRIOR_IMPROPER_COV = 1, 2, 3
+FLAG_PRIOR_OOB, FLAG_MODEL_NAN, FLAG_COV_NOT_PD, FLAG_CHOL_FAIL = 1, 2, 4, 8
+RESAMPLE_STANDARD, RESAMPLE_STRATIFIED, RESAMPLE_SYSTEMATIC = 0, 1, 2
+SCAN_SEQUENTIAL, SCAN_LOOKBACK = 0, 1
+
+
+class Prior(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ncols", C.c_int32), ("a", C.c_double), ("b", C.c_double),
+                ("logp_in", C.c_double)]
+
+
+class Problem(C.Structure):
+    _fields_ = [("model_id", C.c_int32), ("loglike_id", C.c_int32), ("n_params", C.c_int32),
+                ("n_model_params", C.c_int32), ("n_data", C.c_int32), ("n_snapshots", C.c_int32),
+                ("sigma_is_param", C.c_int32), ("n_priors", C.c_int32), ("sigma", C.c_double),
+                ("model_args", C.c_double * 8), ("data", C.c_void_p), ("xgrid", C.c_void_p),
+                ("cov_fixed", C.c_double * MAX_COV_ARGS), ("cov_param_col", C.c_int32 * MAX_COV_ARGS),
+                ("priors", Prior * MAX_PRIORS)]
+
+
+class Path(C.Structure):
+    _fields_ = [("phi", C.c_double), ("phi_prev", C.c_double), ("lam", C.c_double)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("seed", C.c_uint64), ("stream", C.c_uint64),
+                ("id_offset", C.c_int64), ("z", C.c_void_p), ("u", C.c_void_p)]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_I32 = C.c_int32
+_U64 = C.c_uint64
+_D = C.c_double
+_PP = C.POINTER
+
+# name -> argtypes; every function returns int except where noted below
+SIGNATURES = {
+    "smcb_aos_to_soa": [_P, _P, _I64, _I32, _I64, _P],
+    "smcb_soa_to_aos": [_P, _P, _I64, _I32, _I64, _P],
+    "smcb_fill_f64": [_P, _I64, _D, _P],
+    "smcb_reweight": [_I64, _P, _P, _P, _P, _I64, _PP(Path), _P, _P, _P, _P, _P],
+    "smcb_path_eval": [_I64, _P, _P, _P, _PP(Path), _I32, _P, _P],
+    "smcb_reweight_partials": [_I64, _P, _P, _P, _P, _I64, _PP(Path), _P, _P, _P],
+    "smcb_lse_merge": [_P, _I32, _P, _P],
+    "smcb_reweight_finalize": [_I64, _P, _P, _P, _P, _I64, _PP(Path), _P, _P, _P, _P],
+    "smcb_ess_bisect": [_I64, _P, _P, _P, _D, _D, _D, _D, _I64, _P, _P, _P],
+    "smcb_ess_bisect_begin": [_D, _P, _P],
+    "smcb_ess_partial": [_I64, _P, _P, _P, _D, _D, _D, _P, _P, _P, _P],
+    "smcb_ess_bisect_update": [_P, _I32, _D, _D, _I64, _P, _P],
+    "smcb_ess_bisect_max_iters": [],
+    "smcb_resample_uniforms": [_I32, _I64, _I64, _I64, _U64, _U64, _P, _P],
+    "smcb_cdf_scan": [_P, _P, _I64, _I32, _P, _P],
+    "smcb_searchsorted": [_P, _I64, _P, _I64, _P, _P],
+    "smcb_gather": [_P, _I64, _P, _I64, _P, _I64, _I32, _P],
+    "smcb_count_unique": [_P, _I64, _I64, _P, _P, _P],
+    "smcb_weighted_cov": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P, _P],
+    "smcb_weighted_sums1": [_P, _I64, _P, _I64, _I32, _P, _P, _P],
+    "smcb_mean_from_sums": [_P, _I32, _P, _P],
+    "smcb_weighted_sums2": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P],
+    "smcb_cov_from_sums": [_P, _P, _I32, _P, _P],
+    "smcb_cholesky": [_P, _I32, _P, _P, _P],
+    "smcb_mh_init": [_PP(Problem), _P, _I64, _I64, _P, _P, _P, _P, _P],
+    "smcb_log_priors": [_PP(Problem), _P, _I64, _I64, _P, _P, _P],
+    "smcb_mh_step": [_PP(Problem), _PP(Path), _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I32,
+                     _PP(Rng), _P, _P],
+    "smcb_count_moved": [_P, _I64, _P, _P, _P],
+    "smcb_sample_priors": [_PP(Problem), _P, _I64, _I64, _U64, _U64, _I64, _P],
+    "smcb_mh_propose": [_PP(Problem), _P, _I64, _I64, _I64, _P, _P, _I32, _PP(Rng), _P, _P, _P],
+    "smcb_normal_loglike_rows": [_P, _I64, _I32, _P, _P, _D, _P, _P, _P, _P],
+    "smcb_mh_accept": [_PP(Path), _P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _P, _I32, _PP(Rng), _P],
+}
+OTHER_SYMBOLS = ["smcb_version", "smcb_last_error", "smcb_workspace_bytes"]
+
+
+class SmcbError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libsmcb200.so is not built (%s). Run `python -m smcpy_b200.build`; smcpy_b200 has no "
+            "CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.smcb_version.restype = C.c_int
+    lib.smcb_last_error.restype = C.c_char_p
+    lib.smcb_workspace_bytes.argtypes = [_I64, _I32]
+    lib.smcb_workspace_bytes.restype = C.c_size_t
+    return lib
+
+
+lib = _load()
+# kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
+LAUNCHES = {"smcb_reweight": 3, "smcb_cdf_scan": 2, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
+            "smcb_weighted_sums1": 2, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0}
+launch_count = 0
+
+
+def call(name, *args, launches=None):
+    """Invoke a C-ABI entry point; raises SmcbError with the library's message."""
+    global launch_count
+    launch_count += LAUNCHES.get(name, 1) if launches is None else launches
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.smcb_last_error().decode()
+        if rc == 3:
+            raise NotImplementedError(msg)
+        raise SmcbError("%s failed (%d): %s" % (name, rc, msg))
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("smcpy_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,216 @@
+// common.cuh -- shared device helpers for libsmcb200 (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/smcb200.h"
+
+namespace smcb {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+constexpr double kNegInf = -__builtin_huge_val();
+
+// ---- host-side error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);   // cudaGetLastError -> SMCB_ERR_CUDA
+
+#define SMCB_REQUIRE(cond, msg)                       \
+    do {                                              \
+        if (!(cond)) {                                \
+            ::smcb::set_error("%s: %s", __func__, msg); \
+            return SMCB_ERR_ARG;                      \
+        }                                             \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// grid sized in multiples of the SM count (persistent-style grid-stride kernels)
+inline int grid_for(int64_t n, int threads, int items_per_thread, int max_blocks_per_sm) {
+    int64_t per_block = (int64_t)threads * items_per_thread;
+    int64_t want = (n + per_block - 1) / per_block;
+    int64_t cap = (int64_t)kNumSMs * max_blocks_per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+// workspace layout (bytes from the start of `ws`); the caller zero-initialises once
+constexpr size_t kWsTickets = 0;            // 64 x u32 tickets / counters
+constexpr size_t kWsPartials = 1024;        // block partials: up to 4096 blocks x 8 doubles
+constexpr size_t kWsPartialsBytes = 4u << 20;  // 4 MiB
+constexpr size_t kWsSmall = kWsPartials + kWsPartialsBytes;   // 4 KB small scalars
+constexpr size_t kWsLarge = kWsSmall + 4096;                  // scan tile state / flags
+
+// ---- warp / block reductions ---------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_ull(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum; result valid in thread 0 (deterministic order). `sh` >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (wid == 0) v = warp_sum(v);
+    return v;
+}
+
+// ---- log-sum-exp triple (max, S1 = sum e^(v-max), S2 = sum e^(2(v-max))) --------------
+struct Lse {
+    double m, s1, s2;
+};
+__device__ __forceinline__ Lse lse_empty() { return Lse{kNegInf, 0.0, 0.0}; }
+__device__ __forceinline__ Lse lse_merge(const Lse& a, const Lse& b) {
+    Lse r;
+    r.m = fmax(a.m, b.m);
+    if (r.m == kNegInf) {
+        r.s1 = 0.0;
+        r.s2 = 0.0;
+        return r;
+    }
+    const double ea = (a.m == kNegInf) ? 0.0 : exp(a.m - r.m);
+    const double eb = (b.m == kNegInf) ? 0.0 : exp(b.m - r.m);
+    r.s1 = a.s1 * ea + b.s1 * eb;
+    r.s2 = a.s2 * (ea * ea) + b.s2 * (eb * eb);
+    return r;
+}
+__device__ __forceinline__ Lse warp_lse(Lse v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Lse t;
+        t.m = __shfl_xor_sync(0xffffffffu, v.m, o);
+        t.s1 = __shfl_xor_sync(0xffffffffu, v.s1, o);
+        t.s2 = __shfl_xor_sync(0xffffffffu, v.s2, o);
+        // order the operands by lane so both partners compute the identical value
+        const bool low = (threadIdx.x & o) == 0;
+        v = low ? lse_merge(v, t) : lse_merge(t, v);
+    }
+    return v;
+}
+// block merge, result valid in thread 0. sh >= 96 doubles.
+__device__ __forceinline__ Lse block_lse(Lse v, double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_lse(v);
+    __syncthreads();
+    if (lane == 0) {
+        sh[wid] = v.m;
+        sh[32 + wid] = v.s1;
+        sh[64 + wid] = v.s2;
+    }
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    if (wid == 0) {
+        v = (lane < nw) ? Lse{sh[lane], sh[32 + lane], sh[64 + lane]} : lse_empty();
+        v = warp_lse(v);
+    }
+    return v;
+}
+// add one value with a running max (rescale only when the max moves)
+__device__ __forceinline__ void lse_push4(Lse& acc, double v0, double v1, double v2, double v3) {
+    const double tm = fmax(fmax(v0, v1), fmax(v2, v3));
+    if (tm > acc.m) {
+        if (acc.m != kNegInf) {
+            const double e = exp(acc.m - tm);
+            acc.s1 *= e;
+            acc.s2 *= e * e;
+        }
+        acc.m = tm;
+    }
+    if (acc.m == kNegInf) return;
+    const double e0 = exp(v0 - acc.m), e1 = exp(v1 - acc.m), e2 = exp(v2 - acc.m), e3 = exp(v3 - acc.m);
+    acc.s1 += (e0 + e1) + (e2 + e3);
+    acc.s2 += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+}
+
+// ---- GeometricPath arithmetic (smcpy/paths.py:81-105) ---------------------------------
+struct PathCoef {
+    double phi, pe, qe;        // exponents at phi
+    double phi0, pe0, qe0;     // exponents at phi_prev
+};
+inline PathCoef make_path_coef(double phi, double phi_prev, double lambda) {
+    PathCoef c;
+    c.phi = phi;
+    c.pe = fmin(1.0, phi / lambda);
+    c.qe = fmax(0.0, (lambda - phi) / lambda);
+    c.phi0 = phi_prev;
+    c.pe0 = fmin(1.0, phi_prev / lambda);
+    c.qe0 = fmax(0.0, (lambda - phi_prev) / lambda);
+    return c;
+}
+// row sum in the reference's column order, no FMA contraction, NaN -> -inf (paths.py:55-61)
+__device__ __forceinline__ double path_target(double ll, double lp, double lq, double phi, double pe,
+                                              double qe) {
+    double t = __dmul_rn(ll, phi);
+    t = __dadd_rn(t, pe > 0.0 ? __dmul_rn(lp, pe) : 0.0);
+    t = __dadd_rn(t, qe > 0.0 ? __dmul_rn(lq, qe) : 0.0);
+    return (t != t) ? kNegInf : t;
+}
+__device__ __forceinline__ double path_inc(double ll, double lp, double lq, const PathCoef& c) {
+    double t = __dmul_rn(ll, c.phi);
+    t = __dadd_rn(t, c.pe > 0.0 ? __dmul_rn(lp, c.pe) : 0.0);
+    t = __dadd_rn(t, c.qe > 0.0 ? __dmul_rn(lq, c.qe) : 0.0);
+    t = __dadd_rn(t, -__dmul_rn(ll, c.phi0));
+    t = __dadd_rn(t, c.pe0 > 0.0 ? -__dmul_rn(lp, c.pe0) : -0.0);
+    t = __dadd_rn(t, c.qe0 > 0.0 ? -__dmul_rn(lq, c.qe0) : -0.0);
+    return (t != t) ? kNegInf : t;
+}
+
+// ---- Philox4x32-10 counter-based generator ---------------------------------------------
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ __forceinline__ uint4 operator()(uint64_t id, uint32_t call, uint32_t stream) const {
+        uint32_t c0 = (uint32_t)id, c1 = (uint32_t)(id >> 32), c2 = call, c3 = stream;
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            const uint32_t n0 = hi1 ^ c1 ^ a, n2 = hi0 ^ c3 ^ b;
+            c0 = n0;
+            c1 = lo1;
+            c2 = n2;
+            c3 = lo0;
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+// 53-bit uniform in [0,1) from two 32-bit words (same construction as numpy's next_double)
+__device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
+    const uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+// two standard normals from two 32-bit words (Box-Muller in fp32; proposals only need a
+// symmetric, well-distributed z -- see DESIGN.md "RNG")
+__device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, double& z0, double& z1) {
+    const float u1 = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
+    const float u2 = (float)(w1 >> 8) * (2.0f / 16777216.0f);            // [0,2)
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(u2, &s, &c);
+    z0 = (double)(r * c);
+    z1 = (double)(r * s);
+}
+
+}  // namespace smcb

@@ -1,0 +1,802 @@
+// metropolis.cu -- kernel (d): the fused VectorMCMC.smc_metropolis step.
+//
+// One launch = one Metropolis step for every particle (smcpy/mcmc/vector_mcmc.py:168-183):
+//   Gaussian random-walk proposal x' = x + sqrt(s) L z          (:124-129, cov scale rule :55-60)
+//   prior log-pdfs of x'                                         (:98-111)
+//   model + log-likelihood where the prior is finite             (:205-214, log_likelihoods.py)
+//   tempered acceptance ratio exp(target(x') - target(x))        (:131-146, paths.py:81-84)
+//   reject iff ratio < u, select                                 (:148-151, :176-181)
+// in one pass over structure-of-arrays particles: thread i owns particle i, reads its d
+// parameters + ll + lp (coalesced column loads), keeps proposal, model outputs and residuals in
+// registers, stages the shared data vector in shared memory, and writes back only accepted
+// rows.  Algorithmic HBM bytes per particle-step: 2 * 8 * (d + 2).
+//
+// The same kernels with kInit = true evaluate log-priors and log-likelihood of incoming
+// particles (vector_mcmc.py:162-166, initializer.py:66-73).
+#include "common.cuh"
+
+namespace smcb {
+
+constexpr int kMhThreads = 128;
+constexpr int kChunk = 1024;          // data points staged per shared-memory chunk
+
+enum Kind { K_LINEAR_NORMAL = 0, K_SPRING_NORMAL = 1, K_IDENTITY_NORMAL = 2, K_LINEAR_MVN = 3 };
+
+// per-column view of the prior table (host-built from smcb_problem_t::priors)
+struct ColPriors {
+    int8_t kind[SMCB_MAX_PARAMS];        // 0 = column belongs to a matrix prior
+    int8_t prior_of_col[SMCB_MAX_PARAMS];
+    double a[SMCB_MAX_PARAMS], b[SMCB_MAX_PARAMS], logp[SMCB_MAX_PARAMS];
+    int32_t n_cov;                        // number of IMPROPER_COV priors (<= 2)
+    int32_t cov_c0[2], cov_ncols[2], cov_prior[2];
+};
+
+struct MhArgs {
+    smcb_problem_t prob;
+    ColPriors cp;
+    double* params;
+    int64_t stride, n;
+    double n_global;
+    double* ll;
+    double* lp;
+    uint8_t* moved;
+    const double* chol;
+    unsigned long long* accept_counts;
+    int32_t step;
+    double phi, pe, qe;
+    smcb_rng_t rng;
+    int32_t* flags;
+    double* lp_cols;      // init only (optional)
+    double* new_params;   // propose only
+    double* new_lp;       // propose only
+};
+
+// covariance scale after the first `step` Metropolis steps (vector_mcmc.py:55-60):
+// cov/5 below 30 % acceptance, cov*2 above 70 %; chol(s C) = sqrt(s) chol(C).
+__device__ __forceinline__ double cov_scale_sqrt(const unsigned long long* counts, int step, double n_global) {
+    double s = 1.0;
+    for (int k = 0; k < step; ++k) {
+        const double acc = (double)counts[k];
+        if (acc < n_global * 0.3) s = s * 1 / 5;
+        if (acc > n_global * 0.7) s = s * 2;
+    }
+    return sqrt(s);
+}
+
+// ---- priors -----------------------------------------------------------------------------------
+// scipy uniform: support test on (x-loc)/scale in [0,1]; with t = fl(x-loc) this is exactly
+// 0 <= t <= scale (DESIGN.md "priors"), no division needed.
+template <int KIND, int DMAX>
+__device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th)[DMAX], double* lp_cols_row,
+                                              int64_t col_stride) {
+    const int d = a.prob.n_params;
+    double lps = 0.0;
+#pragma unroll
+    for (int c = 0; c < DMAX; ++c) {
+        if (c < d) {
+            const int kind = a.cp.kind[c];
+            if (kind == SMCB_PRIOR_UNIFORM) {
+                const double t = th[c] - a.cp.a[c];
+                const double v = (t >= 0.0 && t <= a.cp.b[c]) ? a.cp.logp[c] : kNegInf;
+                lps += v;
+                if (lp_cols_row) lp_cols_row[(int64_t)a.cp.prior_of_col[c] * col_stride] = v;
+            } else if (kind == SMCB_PRIOR_IMPROPER_UNIFORM) {
+                const double v = (th[c] >= a.cp.a[c] && th[c] <= a.cp.b[c]) ? 0.0 : kNegInf;
+                lps += v;
+                if (lp_cols_row) lp_cols_row[(int64_t)a.cp.prior_of_col[c] * col_stride] = v;
+            }
+        }
+    }
+    // matrix priors: packed upper-triangular columns must form a Cholesky-PD matrix.
+    // Compiled for the MVNormal kind only: the runtime column selects would otherwise push
+    // th[] into local memory for every kernel.
+    if constexpr (KIND == K_LINEAR_MVN)
+    for (int q = 0; q < a.cp.n_cov; ++q) {
+        const int c0 = a.cp.cov_c0[q], nc = a.cp.cov_ncols[q];
+        double m[3][3];
+        int e = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = r; s < 3; ++s) {
+                double v = (r == s) ? 1.0 : 0.0;
+                if (r < nc && s < nc) {
+                    v = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DMAX; ++c) v = (c == c0 + e) ? th[c] : v;
+                    ++e;
+                }
+                m[r][s] = v;
+                m[s][r] = v;
+            }
+        // unblocked Cholesky pivots (LAPACK dpotf2 failure rule: pivot <= 0 or NaN)
+        bool pd = true;
+        const double l00 = m[0][0];
+        pd = pd && (l00 > 0.0);
+        const double r00 = sqrt(l00);
+        const double l10 = m[1][0] / r00, l20 = m[2][0] / r00;
+        const double p11 = m[1][1] - l10 * l10;
+        pd = pd && (p11 > 0.0);
+        const double r11 = sqrt(p11);
+        const double l21 = (m[2][1] - l20 * l10) / r11;
+        const double p22 = m[2][2] - l20 * l20 - l21 * l21;
+        pd = pd && (p22 > 0.0);
+        const double v = pd ? 0.0 : kNegInf;
+        lps += v;
+        if (lp_cols_row) lp_cols_row[(int64_t)a.cp.cov_prior[q] * col_stride] = v;
+    }
+    return lps;
+}
+
+// ---- models + likelihoods ------------------------------------------------------------------------
+// All threads of the block call these (they stage data through shared memory); `run` says
+// whether this thread's particle needs the evaluation.
+
+__device__ __forceinline__ double normal_ll(double ssq, double sigma, int m) {
+    // log_likelihoods.py:42-49: term1 = -log(2 pi var) * (M/2); term2 = -1/2 * ssqe / var
+    const double var = sigma * sigma;
+    const double term1 = -log(2 * 3.141592653589793 * var) * ((double)m / 2.0);
+    const double term2 = -1 / 2.0 * ssq / var;
+    return term1 + term2;
+}
+
+template <int DMAX>
+__device__ __forceinline__ double ll_linear_normal(const MhArgs& a, const double (&th)[DMAX], bool run,
+                                                   double2* sxy) {
+    const int m = a.prob.n_data;
+    const double aa = th[0], bb = th[1];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int base = 0; base < m; base += kChunk) {
+        const int cnt = (m - base < kChunk) ? (m - base) : kChunk;
+        __syncthreads();
+        for (int j = threadIdx.x; j < cnt; j += kMhThreads)
+            sxy[j] = make_double2(a.prob.xgrid[base + j], a.prob.data[base + j]);
+        __syncthreads();
+        if (run) {
+            int j = 0;
+            for (; j + 4 <= cnt; j += 4) {
+                const double2 p0 = sxy[j], p1 = sxy[j + 1], p2 = sxy[j + 2], p3 = sxy[j + 3];
+                const double d0 = fma(aa, p0.x, bb) - p0.y;
+                const double d1 = fma(aa, p1.x, bb) - p1.y;
+                const double d2 = fma(aa, p2.x, bb) - p2.y;
+                const double d3 = fma(aa, p3.x, bb) - p3.y;
+                s0 = fma(d0, d0, s0);
+                s1 = fma(d1, d1, s1);
+                s2 = fma(d2, d2, s2);
+                s3 = fma(d3, d3, s3);
+            }
+            for (; j < cnt; ++j) {
+                const double2 p = sxy[j];
+                const double dd = fma(aa, p.x, bb) - p.y;
+                s0 = fma(dd, dd, s0);
+            }
+        }
+    }
+    const double sigma = a.prob.sigma_is_param ? th[DMAX > 2 ? 2 : 0] : a.prob.sigma;
+    return normal_ll((s0 + s1) + (s2 + s3), sigma, m);
+}
+
+template <int DMAX>
+__device__ __forceinline__ double ll_spring_normal(const MhArgs& a, const double (&th)[DMAX], bool run,
+                                                   double* sy) {
+    const int m = a.prob.n_data;
+    const double K = th[0], g = th[1];
+    double x = a.prob.model_args[0], v = a.prob.model_args[1];
+    const int nsub = (int)a.prob.model_args[3];
+    const double h = a.prob.model_args[2] / (double)nsub;
+    const double hh = 0.5 * h, h6 = h / 6.0;
+    double ssq = 0.0;
+    for (int base = 0; base < m; base += kChunk) {
+        const int cnt = (m - base < kChunk) ? (m - base) : kChunk;
+        __syncthreads();
+        for (int j = threadIdx.x; j < cnt; j += kMhThreads) sy[j] = a.prob.data[base + j];
+        __syncthreads();
+        if (run) {
+            for (int j = 0; j < cnt; ++j) {
+                if (base + j > 0) {
+                    for (int s = 0; s < nsub; ++s) {       // classical RK4 on (x, v)
+                        const double k1x = v, k1v = g - K * x;
+                        const double x2 = x + hh * k1x, v2 = v + hh * k1v;
+                        const double k2x = v2, k2v = g - K * x2;
+                        const double x3 = x + hh * k2x, v3 = v + hh * k2v;
+                        const double k3x = v3, k3v = g - K * x3;
+                        const double x4 = x + h * k3x, v4 = v + h * k3v;
+                        const double k4x = v4, k4v = g - K * x4;
+                        x = x + h6 * (k1x + 2.0 * k2x + 2.0 * k3x + k4x);
+                        v = v + h6 * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
+                    }
+                }
+                const double dd = x - sy[j];
+                ssq = fma(dd, dd, ssq);
+            }
+        }
+    }
+    const double sigma = a.prob.sigma_is_param ? th[DMAX > 2 ? 2 : 0] : a.prob.sigma;
+    return normal_ll(ssq, sigma, m);
+}
+
+template <int DMAX>
+__device__ __forceinline__ double ll_identity_normal(const MhArgs& a, const double (&th)[DMAX], bool run,
+                                                     double* sy) {
+    const int m = a.prob.n_data;          // == n_model_params <= DMAX
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += kMhThreads) sy[j] = a.prob.data[j];
+    __syncthreads();
+    double s0 = 0.0, s1 = 0.0;
+    double sigma = a.prob.sigma;
+    if (run) {
+#pragma unroll
+        for (int j = 0; j < DMAX; j += 2) {
+            if (j < m) { const double dd = th[j] - sy[j]; s0 = fma(dd, dd, s0); }
+            if (j + 1 < m) { const double dd = th[j + 1] - sy[j + 1]; s1 = fma(dd, dd, s1); }
+        }
+    }
+    return normal_ll(s0 + s1, sigma, m);
+}
+
+// MVNormal (log_likelihoods.py:150-192) with one Cholesky per particle:
+//   sum_s [ -F/2 log 2pi - 1/2 log det C - 1/2 e_s^T C^-1 e_s ],  e_s = model - data_s
+template <int DMAX>
+__device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&th)[DMAX], bool run,
+                                                double* sdat, bool& not_pd) {
+    const int F = a.prob.n_data, S = a.prob.n_snapshots;
+    __syncthreads();
+    for (int j = threadIdx.x; j < S * F; j += kMhThreads) sdat[j] = a.prob.data[j];
+    for (int j = threadIdx.x; j < F; j += kMhThreads) sdat[S * F + j] = a.prob.xgrid[j];
+    __syncthreads();
+    if (!run) return 0.0;
+    const double* X = sdat + S * F;
+    double c[3][3];
+    int e = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = r; s < 3; ++s) {
+            double v = (r == s) ? 1.0 : 0.0;
+            if (r < F && s < F) {
+                v = a.prob.cov_fixed[e];
+                const int col = a.prob.cov_param_col[e];
+#pragma unroll
+                for (int k = 0; k < DMAX; ++k) v = (k == col) ? th[k] : v;
+                ++e;
+            }
+            c[r][s] = v;
+            c[s][r] = v;
+        }
+    const double p00 = c[0][0];
+    const double r00 = sqrt(p00);
+    const double l10 = c[1][0] / r00, l20 = c[2][0] / r00;
+    const double p11 = c[1][1] - l10 * l10;
+    const double r11 = sqrt(p11);
+    const double l21 = (c[2][1] - l20 * l10) / r11;
+    const double p22 = c[2][2] - l20 * l20 - l21 * l21;
+    const double r22 = sqrt(p22);
+    if (!(p00 > 0.0 && p11 > 0.0 && p22 > 0.0)) not_pd = true;
+    const double logdet = 2.0 * (log(r00) + log(r11) + log(r22));
+    const double i00 = 1.0 / r00, i11 = 1.0 / r11, i22 = 1.0 / r22;
+    double out[3];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) out[f] = (f < F) ? fma(th[0], X[f < F ? f : 0], th[1]) : 0.0;
+    double quad = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const double e0 = out[0] - sdat[s * F];
+        const double e1 = (F > 1) ? out[1] - sdat[s * F + 1] : 0.0;
+        const double e2 = (F > 2) ? out[2] - sdat[s * F + 2] : 0.0;
+        const double y0 = e0 * i00;
+        const double y1 = (e1 - l10 * y0) * i11;
+        const double y2 = (e2 - l20 * y0 - l21 * y1) * i22;
+        quad += y0 * y0 + y1 * y1 + y2 * y2;
+    }
+    const double term1 = -(double)F / 2 * log(2 * 3.141592653589793);
+    return (double)S * (term1 - 0.5 * logdet) - 0.5 * quad;
+}
+
+// mode: 0 = init (evaluate incoming particles), 1 = fused Metropolis step, 2 = propose only,
+//       3 = log-priors only
+template <int KIND, int DMAX, int MODE>
+__global__ void __launch_bounds__(kMhThreads) mh_kernel(const __grid_constant__ MhArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double sh_scale;
+    const int d = a.prob.n_params;
+    double* sL = smem;                       // d*d lower Cholesky factor
+    double* sdata = smem + ((d * d + 1) & ~1);   // 16-byte aligned data staging area
+
+    if (MODE == 1 || MODE == 2) {
+        for (int e = threadIdx.x; e < d * d; e += kMhThreads) sL[e] = a.chol[e];
+        if (threadIdx.x == 0) sh_scale = cov_scale_sqrt(a.accept_counts, a.step, a.n_global);
+    }
+    __syncthreads();
+
+    const int64_t i = (int64_t)blockIdx.x * kMhThreads + threadIdx.x;
+    const bool valid = i < a.n;
+    const int64_t ii = valid ? i : 0;
+
+    double th[DMAX];
+#pragma unroll
+    for (int c = 0; c < DMAX; ++c) th[c] = (c < d) ? a.params[(int64_t)c * a.stride + ii] : 0.0;
+    double ll_old = 0.0, lp_old = 0.0;
+    if (MODE == 1) {
+        ll_old = a.ll[ii];
+        lp_old = a.lp[ii];
+    }
+
+    if (MODE == 1 || MODE == 2) {
+        // proposal: th += sqrt(s) * L z, rows from last to first so th is updated in place
+        const double sc = sh_scale;
+        if (a.rng.mode == 1) {
+            const double* zt = a.rng.z + ii * d;
+#pragma unroll
+            for (int r = DMAX - 1; r >= 0; --r) {
+                if (r < d) {
+                    double acc = 0.0;
+                    for (int j = 0; j <= r; ++j) acc = fma(sL[r * d + j], zt[j], acc);
+                    th[r] += sc * acc;
+                }
+            }
+        } else {
+            float zf[DMAX];
+            const Philox rng(a.rng.seed);
+            const uint64_t pid = (uint64_t)(a.rng.id_offset + ii);
+#pragma unroll
+            for (int c = 0; c < DMAX; c += 4) {
+                if (c < d) {
+                    const uint4 r = rng(pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
+                    double z0, z1, z2, z3;
+                    normal_pair(r.x, r.y, z0, z1);
+                    normal_pair(r.z, r.w, z2, z3);
+                    zf[c] = (float)z0;
+                    if (c + 1 < DMAX) zf[c + 1] = (float)z1;
+                    if (c + 2 < DMAX) zf[c + 2] = (float)z2;
+                    if (c + 3 < DMAX) zf[c + 3] = (float)z3;
+                }
+            }
+#pragma unroll
+            for (int r = DMAX - 1; r >= 0; --r) {
+                if (r < d) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j <= r; ++j) acc = fma(sL[r * d + j], (double)zf[j], acc);
+                    th[r] += sc * acc;
+                }
+            }
+        }
+    }
+
+    double* lp_cols_row = ((MODE == 0 || MODE == 3) && a.lp_cols && valid) ? a.lp_cols + ii : nullptr;
+    const double lp_new = eval_priors<KIND, DMAX>(a, th, lp_cols_row, a.stride);
+    const bool prior_ok = lp_new != kNegInf;
+
+    if (MODE == 3) {
+        if (valid) a.lp[i] = lp_new;
+        return;
+    }
+    if (MODE == 2) {
+        if (valid) {
+#pragma unroll
+            for (int c = 0; c < DMAX; ++c)
+                if (c < d) a.new_params[(int64_t)c * a.stride + i] = th[c];
+            a.new_lp[i] = lp_new;
+        }
+        return;
+    }
+
+    const bool run = valid && prior_ok;     // rows with a -inf prior are not evaluated (quirk Q6)
+    bool not_pd = false;
+    double ll_new;
+    if (KIND == K_LINEAR_NORMAL) ll_new = ll_linear_normal<DMAX>(a, th, run, reinterpret_cast<double2*>(sdata));
+    else if (KIND == K_SPRING_NORMAL) ll_new = ll_spring_normal<DMAX>(a, th, run, sdata);
+    else if (KIND == K_IDENTITY_NORMAL) ll_new = ll_identity_normal<DMAX>(a, th, run, sdata);
+    else ll_new = ll_linear_mvn<DMAX>(a, th, run, sdata, not_pd);
+    if (!run) ll_new = 0.0;                 // placeholder (vector_mcmc.py:207)
+    int flag = 0;
+    if (run && ll_new != ll_new) flag |= SMCB_FLAG_MODEL_NAN;
+    if (run && not_pd) flag |= SMCB_FLAG_COV_NOT_PD;
+
+    if (MODE == 0) {
+        if (valid) {
+            a.ll[i] = ll_new;
+            a.lp[i] = lp_new;
+            if (!prior_ok) flag |= SMCB_FLAG_PRIOR_OOB;
+        }
+        if (flag) atomicOr(a.flags, flag);
+        return;
+    }
+
+    // acceptance (vector_mcmc.py:131-151 with evaluate_log_posterior = path.logpdf)
+    bool accepted = false;
+    if (valid) {
+        const double t_old = path_target(ll_old, lp_old, lp_old, a.phi, a.pe, a.qe);
+        const double t_new = path_target(ll_new, lp_new, lp_new, a.phi, a.pe, a.qe);
+        const double ratio = exp(t_new - t_old);
+        double u;
+        if (a.rng.mode == 1) {
+            u = a.rng.u[i];
+        } else {
+            const Philox rng(a.rng.seed);
+            const uint4 r = rng((uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
+            u = u01_53(r.x, r.y);
+        }
+        const bool rejected = ratio < u;     // NaN compares false -> accept, as numpy does
+        accepted = !rejected && !(run && not_pd);
+        if (accepted) {
+#pragma unroll
+            for (int c = 0; c < DMAX; ++c)
+                if (c < d) a.params[(int64_t)c * a.stride + i] = th[c];
+            a.ll[i] = ll_new;
+            a.lp[i] = lp_new;
+            a.moved[i] = 1;
+        }
+    }
+    if (flag) atomicOr(a.flags, flag);
+    const int n_acc = __syncthreads_count(accepted ? 1 : 0);
+    if (threadIdx.x == 0 && n_acc) atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
+}
+
+// ---- un-fused pieces (torch-callable user models) ---------------------------------------------------
+// row-wise Normal log-likelihood of model outputs (n, m) row-major: one warp per row
+__global__ void __launch_bounds__(256) normal_ll_rows_kernel(const double* __restrict__ out, int64_t n, int m,
+                                                             const double* __restrict__ data,
+                                                             const double* sigma_col, double sigma,
+                                                             const double* lp, double* ll, int* flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += n_warps) {
+        if (lp && lp[r] == kNegInf) {
+            if (lane == 0) ll[r] = 0.0;
+            continue;
+        }
+        const double* row = out + r * m;
+        double s = 0.0;
+        for (int j = lane; j < m; j += 32) {
+            const double dd = row[j] - data[j];
+            s = fma(dd, dd, s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+            const double v = normal_ll(s, sigma_col ? sigma_col[r] : sigma, m);
+            ll[r] = v;
+            if (v != v) atomicOr(flags, SMCB_FLAG_MODEL_NAN);
+        }
+    }
+}
+
+struct AcceptArgs {
+    double* params;
+    const double* new_params;
+    int64_t stride, n;
+    int32_t d;
+    double* ll;
+    const double* new_ll;
+    double* lp;
+    const double* new_lp;
+    uint8_t* moved;
+    unsigned long long* accept_counts;
+    int32_t step;
+    double phi, pe, qe;
+    smcb_rng_t rng;
+};
+
+__global__ void __launch_bounds__(256) mh_accept_kernel(const AcceptArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool accepted = false;
+    if (i < a.n) {
+        const double t_old = path_target(a.ll[i], a.lp[i], a.lp[i], a.phi, a.pe, a.qe);
+        const double t_new = path_target(a.new_ll[i], a.new_lp[i], a.new_lp[i], a.phi, a.pe, a.qe);
+        const double ratio = exp(t_new - t_old);
+        double u;
+        if (a.rng.mode == 1) {
+            u = a.rng.u[i];
+        } else {
+            const Philox rng(a.rng.seed);
+            const uint4 r = rng((uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
+            u = u01_53(r.x, r.y);
+        }
+        accepted = !(ratio < u);
+        if (accepted) {
+            for (int c = 0; c < a.d; ++c)
+                a.params[(int64_t)c * a.stride + i] = a.new_params[(int64_t)c * a.stride + i];
+            a.ll[i] = a.new_ll[i];
+            a.lp[i] = a.new_lp[i];
+            a.moved[i] = 1;
+        }
+    }
+    const int n_acc = __syncthreads_count(accepted ? 1 : 0);
+    if (threadIdx.x == 0 && n_acc) atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
+}
+
+// initial particles from uniform priors: x = loc + scale * U  (scipy uniform.rvs)
+__global__ void __launch_bounds__(256) sample_priors_kernel(ColPriors cp, int d, double* params, int64_t stride,
+                                                            int64_t n, uint64_t seed, uint32_t stream_id,
+                                                            int64_t id_offset) {
+    const Philox rng(seed);
+    const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        for (int c = 0; c < d; c += 2) {
+            const uint4 r = rng((uint64_t)(id_offset + i), (uint32_t)(c >> 1), stream_id);
+            params[(int64_t)c * stride + i] = cp.a[c] + cp.b[c] * u01_53(r.x, r.y);
+            if (c + 1 < d) params[(int64_t)(c + 1) * stride + i] = cp.a[c + 1] + cp.b[c + 1] * u01_53(r.z, r.w);
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+static int build_col_priors(const smcb_problem_t* p, ColPriors* cp) {
+    memset(cp, 0, sizeof(*cp));
+    int col = 0;
+    for (int q = 0; q < p->n_priors; ++q) {
+        const smcb_prior_t& pr = p->priors[q];
+        if (pr.kind == SMCB_PRIOR_UNIFORM || pr.kind == SMCB_PRIOR_IMPROPER_UNIFORM) {
+            if (col >= SMCB_MAX_PARAMS) return -1;
+            cp->kind[col] = (int8_t)pr.kind;
+            cp->prior_of_col[col] = (int8_t)q;
+            cp->a[col] = pr.a;
+            cp->b[col] = pr.b;
+            cp->logp[col] = pr.logp_in;
+            col += 1;
+        } else if (pr.kind == SMCB_PRIOR_IMPROPER_COV) {
+            if (cp->n_cov >= 2 || pr.ncols < 1 || pr.ncols > 3) return -1;
+            cp->cov_c0[cp->n_cov] = col;
+            cp->cov_ncols[cp->n_cov] = pr.ncols;
+            cp->cov_prior[cp->n_cov] = q;
+            cp->n_cov += 1;
+            col += pr.ncols * (pr.ncols + 1) / 2;
+        } else {
+            return -1;
+        }
+    }
+    return col;
+}
+
+static size_t mh_smem_bytes(const smcb_problem_t* p) {
+    const int d = p->n_params;
+    size_t data = 0;
+    if (p->loglike_id == SMCB_LL_MVNORMAL) data = (size_t)(p->n_snapshots * p->n_data + p->n_data) * 8;
+    else if (p->model_id == SMCB_MODEL_LINEAR) data = (size_t)kChunk * 16;
+    else if (p->model_id == SMCB_MODEL_SPRING_MASS) data = (size_t)kChunk * 8;
+    else data = (size_t)SMCB_MAX_PARAMS * 8;
+    return (size_t)((d * d + 1) & ~1) * 8 + data + 16;
+}
+
+template <int KIND, int DMAX, int MODE>
+static int launch_one(const MhArgs& a, cudaStream_t s) {
+    const size_t smem = mh_smem_bytes(&a.prob);
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+        cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr = true;
+    }
+    const unsigned grid = (unsigned)((a.n + kMhThreads - 1) / kMhThreads);
+    mh_kernel<KIND, DMAX, MODE><<<grid, kMhThreads, smem, s>>>(a);
+    return check_launch("mh_kernel");
+}
+
+template <int MODE>
+static int dispatch(const MhArgs& a, cudaStream_t s) {
+    const smcb_problem_t& p = a.prob;
+    const int d = p.n_params;
+#define SMCB_CASE(KIND, DMAX) return launch_one<KIND, DMAX, MODE>(a, s)
+    if constexpr (MODE == 3) {           // priors only: matrix priors need the MVN instantiation
+        if (a.cp.n_cov > 0) {
+            if (d <= 4) SMCB_CASE(K_LINEAR_MVN, 4);
+            if (d <= 8) SMCB_CASE(K_LINEAR_MVN, 8);
+        } else {
+            if (d <= 2) SMCB_CASE(K_IDENTITY_NORMAL, 2);
+            if (d <= 4) SMCB_CASE(K_IDENTITY_NORMAL, 4);
+            if (d <= 8) SMCB_CASE(K_IDENTITY_NORMAL, 8);
+            if (d <= 16) SMCB_CASE(K_IDENTITY_NORMAL, 16);
+            if (d <= 32) SMCB_CASE(K_IDENTITY_NORMAL, 32);
+        }
+    } else if constexpr (MODE == 2) {    // the proposal does not depend on the model
+        if (d <= 2) SMCB_CASE(K_IDENTITY_NORMAL, 2);
+        if (d <= 4) SMCB_CASE(K_IDENTITY_NORMAL, 4);
+        if (d <= 8) SMCB_CASE(K_IDENTITY_NORMAL, 8);
+        if (d <= 16) SMCB_CASE(K_IDENTITY_NORMAL, 16);
+        if (d <= 32) SMCB_CASE(K_IDENTITY_NORMAL, 32);
+    } else if (p.loglike_id == SMCB_LL_NORMAL && p.model_id == SMCB_MODEL_LINEAR) {
+        if (d == 2) SMCB_CASE(K_LINEAR_NORMAL, 2);
+        if (d == 3) SMCB_CASE(K_LINEAR_NORMAL, 4);
+    } else if (p.loglike_id == SMCB_LL_NORMAL && p.model_id == SMCB_MODEL_SPRING_MASS) {
+        if (d == 2) SMCB_CASE(K_SPRING_NORMAL, 2);
+        if (d == 3) SMCB_CASE(K_SPRING_NORMAL, 4);
+    } else if (p.loglike_id == SMCB_LL_NORMAL && p.model_id == SMCB_MODEL_IDENTITY) {
+        if (d <= 2) SMCB_CASE(K_IDENTITY_NORMAL, 2);
+        if (d <= 4) SMCB_CASE(K_IDENTITY_NORMAL, 4);
+        if (d <= 8) SMCB_CASE(K_IDENTITY_NORMAL, 8);
+        if (d <= 16) SMCB_CASE(K_IDENTITY_NORMAL, 16);
+        if (d <= 32) SMCB_CASE(K_IDENTITY_NORMAL, 32);
+    } else if (p.loglike_id == SMCB_LL_MVNORMAL && p.model_id == SMCB_MODEL_LINEAR) {
+        if (d <= 4) SMCB_CASE(K_LINEAR_MVN, 4);
+        if (d <= 8) SMCB_CASE(K_LINEAR_MVN, 8);
+    }
+#undef SMCB_CASE
+    set_error("no fused kernel for model %d / loglike %d / d=%d", p.model_id, p.loglike_id, d);
+    return SMCB_ERR_UNSUPPORTED;
+}
+
+static int validate_problem(const smcb_problem_t* p, ColPriors* cp) {
+    if (!p) { set_error("problem is NULL"); return SMCB_ERR_ARG; }
+    if (p->n_params < 1 || p->n_params > SMCB_MAX_PARAMS) { set_error("n_params out of range"); return SMCB_ERR_ARG; }
+    if (p->n_priors < 1 || p->n_priors > SMCB_MAX_PRIORS) { set_error("n_priors out of range"); return SMCB_ERR_ARG; }
+    const int cols = build_col_priors(p, cp);
+    if (cols != p->n_params) {
+        set_error("Num prior distributions != num input params (%d prior columns, %d params)", cols, p->n_params);
+        return SMCB_ERR_ARG;
+    }
+    if (!p->data) { set_error("data pointer is NULL"); return SMCB_ERR_ARG; }
+    if (p->loglike_id == SMCB_LL_NORMAL) {
+        const int extra = p->sigma_is_param ? 1 : 0;
+        if (p->n_model_params + extra != p->n_params) { set_error("Normal: n_model_params + sigma != n_params"); return SMCB_ERR_ARG; }
+        if (p->model_id == SMCB_MODEL_LINEAR && (!p->xgrid || p->n_model_params != 2)) { set_error("linear model needs xgrid and 2 params"); return SMCB_ERR_ARG; }
+        if (p->model_id == SMCB_MODEL_SPRING_MASS && (p->n_model_params != 2 || p->model_args[3] < 1)) { set_error("spring-mass model needs 2 params and nsub >= 1"); return SMCB_ERR_ARG; }
+        if (p->model_id == SMCB_MODEL_IDENTITY && p->n_model_params != p->n_data) { set_error("identity model needs n_data == n_model_params"); return SMCB_ERR_ARG; }
+        if (p->model_id == SMCB_MODEL_IDENTITY && p->sigma_is_param) { set_error("identity model: fused kernels need a fixed sigma"); return SMCB_ERR_UNSUPPORTED; }
+        if (cp->n_cov > 0) { set_error("ImproperCov priors are fused for the MVNormal likelihood only"); return SMCB_ERR_UNSUPPORTED; }
+    } else if (p->loglike_id == SMCB_LL_MVNORMAL) {
+        if (p->model_id != SMCB_MODEL_LINEAR || !p->xgrid || p->n_model_params != 2) { set_error("MVNormal is built in for the linear model only"); return SMCB_ERR_ARG; }
+        if (p->n_data < 1 || p->n_data > 3 || p->n_snapshots < 1 || p->n_snapshots * p->n_data > 4096) { set_error("MVNormal: 1..3 features, S*F <= 4096"); return SMCB_ERR_ARG; }
+    } else {
+        set_error("unknown loglike_id");
+        return SMCB_ERR_ARG;
+    }
+    return SMCB_OK;
+}
+
+}  // namespace smcb
+
+using namespace smcb;
+
+extern "C" int smcb_mh_init(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
+                            double* ll_out, double* lp_out, double* lp_cols_out, int32_t* flags, void* stream) {
+    MhArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = validate_problem(prob, &a.cp);
+    if (rc) return rc;
+    SMCB_REQUIRE(params && ll_out && lp_out && flags && n > 0 && stride >= n, "bad argument");
+    a.prob = *prob;
+    a.params = const_cast<double*>(params);
+    a.stride = stride;
+    a.n = n;
+    a.ll = ll_out;
+    a.lp = lp_out;
+    a.lp_cols = lp_cols_out;
+    a.flags = flags;
+    return dispatch<0>(a, as_stream(stream));
+}
+
+static void fill_step_args(MhArgs& a, const smcb_problem_t* prob, const smcb_path_t* path, int64_t stride, int64_t n,
+                           int64_t n_global, const double* chol, int64_t* accept_counts, int32_t step,
+                           const smcb_rng_t* rng) {
+    a.prob = *prob;
+    a.stride = stride;
+    a.n = n;
+    a.n_global = (double)n_global;
+    a.chol = chol;
+    a.accept_counts = reinterpret_cast<unsigned long long*>(accept_counts);
+    a.step = step;
+    a.rng = *rng;
+    if (path) {
+        const PathCoef c = make_path_coef(path->phi, path->phi_prev, path->lambda);
+        a.phi = c.phi;
+        a.pe = c.pe;
+        a.qe = c.qe;
+    }
+}
+
+extern "C" int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride,
+                            int64_t n, int64_t n_global, double* ll, double* lp, uint8_t* moved, const double* chol,
+                            int64_t* accept_counts, int32_t step, const smcb_rng_t* rng, int32_t* flags,
+                            void* stream) {
+    MhArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = validate_problem(prob, &a.cp);
+    if (rc) return rc;
+    SMCB_REQUIRE(path && params && ll && lp && moved && chol && accept_counts && rng && flags, "NULL argument");
+    SMCB_REQUIRE(n > 0 && stride >= n && n_global >= n, "bad sizes");
+    SMCB_REQUIRE(step >= 0 && step < SMCB_MAX_MCMC_STEPS, "step out of range");
+    SMCB_REQUIRE(rng->mode == 0 || (rng->z && rng->u), "replay mode needs z and u tapes");
+    fill_step_args(a, prob, path, stride, n, n_global, chol, accept_counts, step, rng);
+    a.params = params;
+    a.ll = ll;
+    a.lp = lp;
+    a.moved = moved;
+    a.flags = flags;
+    return dispatch<1>(a, as_stream(stream));
+}
+
+extern "C" int smcb_mh_propose(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
+                               int64_t n_global, const double* chol, const int64_t* accept_counts, int32_t step,
+                               const smcb_rng_t* rng, double* new_params, double* new_lp, void* stream) {
+    MhArgs a;
+    memset(&a, 0, sizeof(a));
+    SMCB_REQUIRE(prob && params && chol && accept_counts && rng && new_params && new_lp, "NULL argument");
+    SMCB_REQUIRE(n > 0 && stride >= n && prob->n_params >= 1 && prob->n_params <= SMCB_MAX_PARAMS, "bad sizes");
+    const int cols = build_col_priors(prob, &a.cp);
+    if (cols != prob->n_params) {
+        set_error("Num prior distributions != num input params");
+        return SMCB_ERR_ARG;
+    }
+    fill_step_args(a, prob, nullptr, stride, n, n_global, chol, const_cast<int64_t*>(accept_counts), step, rng);
+    a.params = const_cast<double*>(params);
+    a.new_params = new_params;
+    a.new_lp = new_lp;
+    return dispatch<2>(a, as_stream(stream));
+}
+
+extern "C" int smcb_log_priors(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
+                               double* lp_out, double* lp_cols_out, void* stream) {
+    MhArgs a;
+    memset(&a, 0, sizeof(a));
+    SMCB_REQUIRE(prob && params && lp_out && n > 0 && stride >= n, "bad argument");
+    SMCB_REQUIRE(prob->n_params >= 1 && prob->n_params <= SMCB_MAX_PARAMS, "n_params out of range");
+    const int cols = build_col_priors(prob, &a.cp);
+    if (cols != prob->n_params) {
+        set_error("Num prior distributions != num input params");
+        return SMCB_ERR_ARG;
+    }
+    a.prob = *prob;
+    a.params = const_cast<double*>(params);
+    a.stride = stride;
+    a.n = n;
+    a.lp = lp_out;
+    a.lp_cols = lp_cols_out;
+    return dispatch<3>(a, as_stream(stream));
+}
+
+extern "C" int smcb_normal_loglike_rows(const double* outputs, int64_t n, int32_t m, const double* data,
+                                        const double* sigma_col, double sigma, const double* lp, double* ll_out,
+                                        int32_t* flags, void* stream) {
+    SMCB_REQUIRE(outputs && data && ll_out && flags && n > 0 && m > 0, "bad argument");
+    const int grid = grid_for(n * 32, 256, 1, 8);
+    normal_ll_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(outputs, n, m, data, sigma_col, sigma, lp, ll_out, flags);
+    return check_launch("normal_ll_rows_kernel");
+}
+
+extern "C" int smcb_mh_accept(const smcb_path_t* path, double* params, const double* new_params, int64_t stride,
+                              int32_t d, int64_t n, double* ll, const double* new_ll, double* lp, const double* new_lp,
+                              uint8_t* moved, int64_t* accept_counts, int32_t step, const smcb_rng_t* rng,
+                              void* stream) {
+    SMCB_REQUIRE(path && params && new_params && ll && new_ll && lp && new_lp && moved && accept_counts && rng,
+                 "NULL argument");
+    SMCB_REQUIRE(n > 0 && d > 0 && stride >= n && step >= 0 && step < SMCB_MAX_MCMC_STEPS, "bad sizes");
+    AcceptArgs a;
+    a.params = params;
+    a.new_params = new_params;
+    a.stride = stride;
+    a.n = n;
+    a.d = d;
+    a.ll = ll;
+    a.new_ll = new_ll;
+    a.lp = lp;
+    a.new_lp = new_lp;
+    a.moved = moved;
+    a.accept_counts = reinterpret_cast<unsigned long long*>(accept_counts);
+    a.step = step;
+    const PathCoef c = make_path_coef(path->phi, path->phi_prev, path->lambda);
+    a.phi = c.phi;
+    a.pe = c.pe;
+    a.qe = c.qe;
+    a.rng = *rng;
+    mh_accept_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(a);
+    return check_launch("mh_accept_kernel");
+}
+
+extern "C" int smcb_sample_priors(const smcb_problem_t* prob, double* params, int64_t stride, int64_t n,
+                                  uint64_t seed, uint64_t stream_id, int64_t id_offset, void* stream) {
+    SMCB_REQUIRE(prob && params && n > 0 && stride >= n, "bad argument");
+    ColPriors cp;
+    const int cols = build_col_priors(prob, &cp);
+    if (cols != prob->n_params) {
+        set_error("Num prior distributions != num input params");
+        return SMCB_ERR_ARG;
+    }
+    for (int c = 0; c < cols; ++c) {
+        if (cp.kind[c] != SMCB_PRIOR_UNIFORM) {
+            set_error("device prior sampling supports scipy-uniform priors only (column %d)", c);
+            return SMCB_ERR_UNSUPPORTED;
+        }
+    }
+    sample_priors_kernel<<<grid_for(n, 256, 1, 8), 256, 0, as_stream(stream)>>>(cp, cols, params, stride, n, seed,
+                                                                                  (uint32_t)stream_id, id_offset);
+    return check_launch("sample_priors_kernel");
+}

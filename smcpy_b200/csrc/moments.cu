@@ -1,0 +1,334 @@
+// moments.cu -- weighted mean / covariance of the particle cloud, Cholesky factor, layout.
+//
+// Reference: Particles.compute_covariance = np.cov(params.T, ddof=0, aweights=w)
+// (smcpy/smc/particles.py:189-198): two passes,
+//     mean = sum(w x) / sum(w);   C = sum(w (x-mean)(x-mean)^T) * (1 / sum(w)).
+// np.linalg.cholesky of the result (smcpy/mcmc/vector_mcmc.py:225).
+// Algorithmic bytes per particle: pass 1 reads d+1 doubles, pass 2 reads d+1 doubles.
+#include "common.cuh"
+
+namespace smcb {
+
+constexpr int kMomThreads = 256;
+
+// ---- pass 1: sum w, sum w x_c for a chunk of DC columns ---------------------------------------
+template <int DC>
+__global__ void __launch_bounds__(kMomThreads) wsums1_kernel(const double* __restrict__ params, int64_t pstride,
+                                                             const double* __restrict__ w, int64_t n, int d,
+                                                             double* partials /* [grid.x][1+d] */) {
+    __shared__ double sh[32];
+    const int c0 = blockIdx.y * DC;
+    double aw = 0.0, ax[DC];
+#pragma unroll
+    for (int j = 0; j < DC; ++j) ax[j] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double wi = w[i];
+        aw += wi;
+#pragma unroll
+        for (int j = 0; j < DC; ++j)
+            if (c0 + j < d) ax[j] += __dmul_rn(params[(int64_t)(c0 + j) * pstride + i], wi);
+    }
+    double* out = partials + (int64_t)blockIdx.x * (1 + d);
+    const double tw = block_sum(aw, sh);
+    if (threadIdx.x == 0 && blockIdx.y == 0) out[0] = tw;
+#pragma unroll
+    for (int j = 0; j < DC; ++j) {
+        const double t = block_sum(ax[j], sh);
+        if (threadIdx.x == 0 && c0 + j < d) out[1 + c0 + j] = t;
+    }
+}
+
+// out[j] = sum over blocks (in block order) of partials[b][j]
+__global__ void reduce_partials_kernel(const double* partials, int n_blocks, int n_vals, double* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_vals) return;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += partials[(int64_t)b * n_vals + j];
+    out[j] = s;
+}
+
+__global__ void mean_from_sums_kernel(const double* sums, int d, double* mean) {
+    const int j = threadIdx.x;
+    if (j < d) mean[j] = sums[1 + j] / sums[0];
+}
+
+// ---- pass 2: sum w (x_i - m_i)(x_j - m_j), smem-tiled, 4x4 register blocks ----------------------
+// Tile of P particles x d columns is staged (centred) in shared memory; thread (slice, blk)
+// accumulates one upper-triangular 4x4 block over its slice of the tile.
+constexpr int kTileP = 128;
+
+struct Blk { unsigned char bi, bj; };
+
+__global__ void __launch_bounds__(kMomThreads) wsums2_kernel(const double* __restrict__ params, int64_t pstride,
+                                                             const double* __restrict__ w, int64_t n, int d,
+                                                             const double* __restrict__ mean,
+                                                             double* partials /* [grid][nbu*16] */) {
+    extern __shared__ double smem[];
+    const int nb = (d + 3) >> 2;                 // 4-wide column blocks
+    const int dp = nb * 4;                       // padded column count
+    const int nbu = nb * (nb + 1) / 2;           // upper-triangular blocks
+    const int nslices = kMomThreads / nbu;
+    constexpr int ld = kTileP + 1;               // odd leading dimension: conflict-free column reads
+    double* xc = smem;                           // [dp][ld] centred columns
+    double* ws = smem + dp * ld;                 // [kTileP] weights
+
+    const int t = threadIdx.x;
+    const int blk = t % nbu, slice = t / nbu;
+    // decode blk -> (bi <= bj)
+    int bi = 0, rem = blk;
+    while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+    const int bj = bi + rem;
+    const bool active = slice < nslices;
+
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+
+    const int64_t n_tiles = (n + kTileP - 1) / kTileP;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * kTileP;
+        __syncthreads();
+        for (int e = t; e < dp * kTileP; e += kMomThreads) {
+            const int c = e / kTileP, p = e - c * kTileP;
+            double v = 0.0;
+            if (c < d && base + p < n) v = params[(int64_t)c * pstride + base + p] - mean[c];
+            xc[c * ld + p] = v;
+        }
+        for (int p = t; p < kTileP; p += kMomThreads) ws[p] = (base + p < n) ? w[base + p] : 0.0;
+        __syncthreads();
+        if (active) {
+            for (int p = slice; p < kTileP; p += nslices) {
+                const double wp = ws[p];
+                double xi[4], xj[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    xi[a] = __dmul_rn(xc[(bi * 4 + a) * ld + p], wp);
+                    xj[a] = xc[(bj * 4 + a) * ld + p];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fma(xi[a], xj[b], acc[a][b]);
+            }
+        }
+    }
+    // reduce the slices of this block in slice order (deterministic)
+    __syncthreads();
+    double* red = smem;                           // reuse: [kMomThreads][16]
+    if (active) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) red[(slice * nbu + blk) * 16 + a * 4 + b] = acc[a][b];
+    }
+    __syncthreads();
+    for (int e = t; e < nbu * 16; e += kMomThreads) {
+        double s = 0.0;
+        for (int sl = 0; sl < nslices; ++sl) s += red[sl * nbu * 16 + e];
+        partials[(int64_t)blockIdx.x * (nbu * 16) + e] = s;
+    }
+}
+
+// expand the block-packed upper triangle to a full symmetric d x d matrix
+__global__ void sums2_unpack_kernel(const double* packed, int d, double* full) {
+    const int nb = (d + 3) >> 2;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d * d) return;
+    int i = e / d, j = e - i * d;
+    if (i > j) { const int tmp = i; i = j; j = tmp; }
+    const int bi = i >> 2, bj = j >> 2;
+    // index of block (bi, bj) in the upper-triangular enumeration
+    const int blk = bi * nb - bi * (bi - 1) / 2 + (bj - bi);
+    full[e] = packed[blk * 16 + (i & 3) * 4 + (j & 3)];
+}
+
+__global__ void cov_from_sums_kernel(const double* wsum, const double* sums2, int d, double* cov) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d * d) return;
+    const double fact = 1.0 / wsum[0];            // np.cov: c *= true_divide(1, fact)
+    cov[e] = __dmul_rn(sums2[e], fact);
+}
+
+// ---- Cholesky (lower), one warp; LAPACK dpotrf failure rule: pivot <= 0 or NaN --------------------
+__global__ void cholesky_kernel(const double* cov, int d, double* L, int* flags) {
+    __shared__ double a[SMCB_MAX_PARAMS * (SMCB_MAX_PARAMS + 1)];
+    const int lane = threadIdx.x;
+    const int ld = d + 1;
+    for (int e = lane; e < d * d; e += 32) a[(e / d) * ld + (e % d)] = cov[e];
+    __syncwarp();
+    bool fail = false;
+    for (int j = 0; j < d; ++j) {
+        // row `lane` (>= j): s = a[i][j] - sum_k<j L[i][k] L[j][k]
+        double s = 0.0;
+        const int i = lane;
+        if (i >= j && i < d) {
+            s = a[i * ld + j];
+            for (int k = 0; k < j; ++k) s -= a[i * ld + k] * a[j * ld + k];
+        }
+        const double pivot = __shfl_sync(0xffffffffu, s, j);
+        if (!(pivot > 0.0)) { fail = true; break; }
+        const double r = sqrt(pivot);
+        if (i >= j && i < d) a[i * ld + j] = (i == j) ? r : s / r;
+        __syncwarp();
+    }
+    for (int e = lane; e < d * d; e += 32) {
+        const int i = e / d, j = e % d;
+        L[e] = (j <= i && !fail) ? a[i * ld + j] : 0.0;
+    }
+    if (fail && lane == 0) atomicOr(flags, SMCB_FLAG_CHOL_FAIL);
+}
+
+// ---- layout -----------------------------------------------------------------------------------------
+// AoS (n, d) row-major <-> SoA (d, stride); staged through shared memory so both sides coalesce
+template <bool kToSoa>
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                                        int64_t n, int d, int64_t stride, int pb) {
+    extern __shared__ double tile[];
+    const int ldp = d | 1;                         // odd row length
+    const int64_t n_chunks = (n + pb - 1) / pb;
+    for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const int64_t base = ch * pb;
+        const int m = (int)((n - base < pb) ? (n - base) : pb);
+        __syncthreads();
+        if (kToSoa) {
+            for (int e = threadIdx.x; e < m * d; e += blockDim.x) tile[(e / d) * ldp + (e % d)] = src[base * d + e];
+            __syncthreads();
+            for (int e = threadIdx.x; e < m * d; e += blockDim.x) {
+                const int c = e / m, p = e - c * m;
+                dst[(int64_t)c * stride + base + p] = tile[p * ldp + c];
+            }
+        } else {
+            for (int e = threadIdx.x; e < m * d; e += blockDim.x) {
+                const int c = e / m, p = e - c * m;
+                tile[p * ldp + c] = src[(int64_t)c * stride + base + p];
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < m * d; e += blockDim.x) dst[base * d + e] = tile[(e / d) * ldp + (e % d)];
+        }
+    }
+}
+
+__global__ void fill_kernel(double* dst, int64_t n, double v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
+}
+
+static int sums2_grid(int64_t n) {
+    const int64_t tiles = (n + kTileP - 1) / kTileP;
+    const int64_t cap = (int64_t)kNumSMs * 4;
+    return (int)(tiles < cap ? tiles : cap);
+}
+static size_t sums2_smem(int d) {
+    const int dp = ((d + 3) / 4) * 4;
+    size_t a = (size_t)(dp * (kTileP + 1) + kTileP) * sizeof(double);
+    size_t b = (size_t)kMomThreads * 16 * sizeof(double);
+    return a > b ? a : b;
+}
+
+}  // namespace smcb
+
+using namespace smcb;
+
+extern "C" int smcb_weighted_sums1(const double* params, int64_t stride, const double* w, int64_t n, int32_t d,
+                                   double* sums_out, void* ws, void* stream) {
+    SMCB_REQUIRE(params && w && sums_out && ws && n > 0 && d > 0 && d <= 64, "bad argument");
+    double* partials = (double*)((char*)ws + kWsPartials);
+    int grid = grid_for(n, kMomThreads, 4, 2);
+    const int maxb = (int)(kWsPartialsBytes / sizeof(double) / (1 + d));
+    if (grid > maxb) grid = maxb;
+    cudaStream_t s = as_stream(stream);
+    if (d <= 1) wsums1_kernel<1><<<dim3(grid, 1), kMomThreads, 0, s>>>(params, stride, w, n, d, partials);
+    else if (d <= 2) wsums1_kernel<2><<<dim3(grid, 1), kMomThreads, 0, s>>>(params, stride, w, n, d, partials);
+    else if (d <= 4) wsums1_kernel<4><<<dim3(grid, 1), kMomThreads, 0, s>>>(params, stride, w, n, d, partials);
+    else wsums1_kernel<8><<<dim3(grid, (d + 7) / 8), kMomThreads, 0, s>>>(params, stride, w, n, d, partials);
+    reduce_partials_kernel<<<(1 + d + 63) / 64, 64, 0, s>>>(partials, grid, 1 + d, sums_out);
+    return check_launch("wsums1_kernel");
+}
+
+extern "C" int smcb_mean_from_sums(const double* sums, int32_t d, double* mean_out, void* stream) {
+    SMCB_REQUIRE(sums && mean_out && d > 0 && d <= 64, "bad argument");
+    mean_from_sums_kernel<<<1, 64, 0, as_stream(stream)>>>(sums, d, mean_out);
+    return check_launch("mean_from_sums_kernel");
+}
+
+extern "C" int smcb_weighted_sums2(const double* params, int64_t stride, const double* w, int64_t n, int32_t d,
+                                   const double* mean, double* sums_out, void* ws, void* stream) {
+    SMCB_REQUIRE(params && w && mean && sums_out && ws && n > 0 && d > 0 && d <= SMCB_MAX_PARAMS, "bad argument");
+    static bool attr_set = false;
+    const size_t smem = sums2_smem(d);
+    if (!attr_set) {
+        cudaFuncSetAttribute(wsums2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
+    const int nb = (d + 3) / 4, nbu = nb * (nb + 1) / 2;
+    double* partials = (double*)((char*)ws + kWsPartials);
+    int grid = sums2_grid(n);
+    const int maxb = (int)(kWsPartialsBytes / sizeof(double) / (nbu * 16 + 0)) - 1;
+    if (grid > maxb) grid = maxb;
+    cudaStream_t s = as_stream(stream);
+    wsums2_kernel<<<grid, kMomThreads, smem, s>>>(params, stride, w, n, d, mean, partials);
+    // packed block sums live after the per-block partials
+    double* packed = partials + (int64_t)grid * nbu * 16;
+    reduce_partials_kernel<<<(nbu * 16 + 63) / 64, 64, 0, s>>>(partials, grid, nbu * 16, packed);
+    sums2_unpack_kernel<<<(d * d + 63) / 64, 64, 0, s>>>(packed, d, sums_out);
+    return check_launch("wsums2_kernel");
+}
+
+extern "C" int smcb_cov_from_sums(const double* wsum, const double* sums2, int32_t d, double* cov_out,
+                                  void* stream) {
+    SMCB_REQUIRE(wsum && sums2 && cov_out && d > 0 && d <= SMCB_MAX_PARAMS, "bad argument");
+    cov_from_sums_kernel<<<(d * d + 63) / 64, 64, 0, as_stream(stream)>>>(wsum, sums2, d, cov_out);
+    return check_launch("cov_from_sums_kernel");
+}
+
+extern "C" int smcb_weighted_cov(const double* params, int64_t stride, const double* w, int64_t n, int32_t d,
+                                 double* mean_out, double* cov_out, double* sums_out, void* ws, void* stream) {
+    SMCB_REQUIRE(sums_out != nullptr, "sums_out required (1 + d + d*d doubles)");
+    int rc = smcb_weighted_sums1(params, stride, w, n, d, sums_out, ws, stream);
+    if (rc) return rc;
+    rc = smcb_mean_from_sums(sums_out, d, mean_out, stream);
+    if (rc) return rc;
+    rc = smcb_weighted_sums2(params, stride, w, n, d, mean_out, sums_out + 1 + d, ws, stream);
+    if (rc) return rc;
+    return smcb_cov_from_sums(sums_out, sums_out + 1 + d, d, cov_out, stream);
+}
+
+extern "C" int smcb_cholesky(const double* cov, int32_t d, double* chol_out, int32_t* flags, void* stream) {
+    SMCB_REQUIRE(cov && chol_out && flags && d > 0 && d <= SMCB_MAX_PARAMS, "bad argument");
+    cholesky_kernel<<<1, 32, 0, as_stream(stream)>>>(cov, d, chol_out, flags);
+    return check_launch("cholesky_kernel");
+}
+
+static int transpose_launch(bool to_soa, const double* src, double* dst, int64_t n, int d, int64_t stride,
+                            void* stream) {
+    int pb = 4096 / (d | 1);
+    if (pb > 256) pb = 256;
+    if (pb < 1) pb = 1;
+    const size_t smem = (size_t)pb * (d | 1) * sizeof(double);
+    const int64_t chunks = (n + pb - 1) / pb;
+    const int grid = (int)(chunks < (int64_t)kNumSMs * 8 ? chunks : (int64_t)kNumSMs * 8);
+    if (to_soa) transpose_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(src, dst, n, d, stride, pb);
+    else transpose_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(src, dst, n, d, stride, pb);
+    return check_launch("transpose_kernel");
+}
+
+extern "C" int smcb_aos_to_soa(const double* aos, double* soa, int64_t n, int32_t d, int64_t stride,
+                               void* stream) {
+    SMCB_REQUIRE(aos && soa && n > 0 && d > 0 && d <= 4095 && stride >= n, "bad argument");
+    return transpose_launch(true, aos, soa, n, d, stride, stream);
+}
+
+extern "C" int smcb_soa_to_aos(const double* soa, double* aos, int64_t n, int32_t d, int64_t stride,
+                               void* stream) {
+    SMCB_REQUIRE(aos && soa && n > 0 && d > 0 && d <= 4095 && stride >= n, "bad argument");
+    return transpose_launch(false, soa, aos, n, d, stride, stream);
+}
+
+extern "C" int smcb_fill_f64(double* dst, int64_t n, double value, void* stream) {
+    SMCB_REQUIRE(dst && n > 0, "bad argument");
+    fill_kernel<<<grid_for(n, 256, 4, 8), 256, 0, as_stream(stream)>>>(dst, n, value);
+    return check_launch("fill_kernel");
+}

@@ -1,0 +1,322 @@
+// resample.cu -- kernel (c): resampling.
+//   uniforms (standard / stratified / systematic)      smcpy/resampler_rngs.py:4-9
+//   CDF = inclusive scan of the normalised weights      np.cumsum, smcpy/smc/updater.py:152
+//   idx_k = #{j : cdf_j <= u_k}                         np.digitize, updater.py:152
+//   gather of the particle columns                      updater.py:140-143
+//   distinct-ancestor count                             updater.py:154-165
+//
+// Two scans: SEQUENTIAL reproduces np.cumsum's single fp64 add chain bit for bit (parity
+// mode: bit-exact indices for the same weights and uniforms); LOOKBACK is a single-pass
+// decoupled look-back scan whose cross-tile carries are 2^-61 fixed-point integers, so the
+// result does not depend on the order in which tiles publish (deterministic run to run).
+// Algorithmic bytes per particle: scan 16, search 16 (+ CDF probes, L2 resident), gather
+// 16 (d + 2) + 8.
+#include "common.cuh"
+
+namespace smcb {
+
+// ---- uniforms ------------------------------------------------------------------------------
+__global__ void resample_uniforms_kernel(int kind, int64_t n_global, int64_t first, int64_t count,
+                                         uint64_t seed, uint32_t stream_id, double* u) {
+    const Philox rng(seed);
+    const double inv_n = 1.0 / (double)n_global;          // resampler_rngs.py:9: 1 / N * (...)
+    double u_sys = 0.0;
+    if (kind == SMCB_RESAMPLE_SYSTEMATIC) {
+        const uint4 r = rng(0, 0, stream_id);
+        u_sys = u01_53(r.x, r.y);
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const int64_t k = first + i;
+        double v;
+        if (kind == SMCB_RESAMPLE_SYSTEMATIC) {
+            v = __dmul_rn(inv_n, __dadd_rn((double)k, u_sys));
+        } else {
+            const uint4 r = rng((uint64_t)k, 0, stream_id);
+            const double x = u01_53(r.x, r.y);
+            v = (kind == SMCB_RESAMPLE_STRATIFIED) ? __dmul_rn(inv_n, __dadd_rn((double)k, x)) : x;
+        }
+        u[i] = v;
+    }
+}
+
+// ---- sequential scan: bit-equal to np.cumsum ----------------------------------------------------
+constexpr int kSeqChunk = 2048;
+__global__ void __launch_bounds__(256) scan_sequential_kernel(const double* __restrict__ w,
+                                                              double* __restrict__ cdf, int64_t n) {
+    __shared__ double buf[kSeqChunk];
+    __shared__ double carry;
+    if (threadIdx.x == 0) carry = 0.0;
+    for (int64_t base = 0; base < n; base += kSeqChunk) {
+        const int m = (int)((n - base < kSeqChunk) ? (n - base) : kSeqChunk);
+        __syncthreads();
+        for (int j = threadIdx.x; j < m; j += blockDim.x) buf[j] = w[base + j];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double c = carry;
+            const bool first = (base == 0);
+            for (int j = 0; j < m; ++j) {
+                // np.cumsum: out[0] = w[0]; out[i] = out[i-1] + w[i]
+                c = (first && j == 0) ? buf[0] : __dadd_rn(c, buf[j]);
+                buf[j] = c;
+            }
+            carry = c;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < m; j += blockDim.x) cdf[base + j] = buf[j];
+    }
+}
+
+// ---- decoupled look-back scan -------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr double kFix = 2305843009213693952.0;          // 2^61
+constexpr double kFixInv = 1.0 / 2305843009213693952.0;
+constexpr unsigned long long kFlagAgg = 1ull, kFlagPrefix = 2ull;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void scan_reset_kernel(unsigned long long* state, int64_t n_tiles, unsigned int* counter) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles; i += stride) state[i] = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const double* __restrict__ w,
+                                                                     double* __restrict__ cdf, int64_t n,
+                                                                     unsigned long long* state,
+                                                                     unsigned int* counter) {
+    __shared__ double sh_warp[kScanThreads / 32];
+    __shared__ unsigned int sh_tile;
+    __shared__ double sh_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    // tiles are handed out in launch order so every predecessor is already resident
+    if (tid == 0) sh_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const int64_t tile = sh_tile;
+    const int64_t base = tile * kScanTile + (int64_t)tid * kScanItems;
+
+    double v[kScanItems];
+    if (base + kScanItems <= n) {
+        const double2* p = reinterpret_cast<const double2*>(w + base);
+#pragma unroll
+        for (int j = 0; j < kScanItems / 2; ++j) {
+            const double2 t = p[j];
+            v[2 * j] = t.x;
+            v[2 * j + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) v[j] = (base + j < n) ? w[base + j] : 0.0;
+    }
+    // thread-local inclusive scan
+#pragma unroll
+    for (int j = 1; j < kScanItems; ++j) v[j] += v[j - 1];
+    const double tsum = v[kScanItems - 1];
+    // warp inclusive scan of thread totals
+    double x = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sh_warp[wid] = x;
+    __syncthreads();
+    double warp_off = 0.0, tile_agg = 0.0;
+#pragma unroll
+    for (int k = 0; k < kScanThreads / 32; ++k) {
+        const double s = sh_warp[k];
+        if (k < wid) warp_off += s;
+        tile_agg += s;
+    }
+    const double thread_excl = warp_off + (x - tsum);
+
+    // cross-tile carry by decoupled look-back on fixed-point aggregates
+    if (wid == 0) {
+        const unsigned long long agg_fx = __double2ull_rn(tile_agg * kFix);
+        unsigned long long excl = 0ull;
+        if (tile == 0) {
+            if (lane == 0) st_state(state, (agg_fx << 2) | kFlagPrefix);
+        } else {
+            if (lane == 0) st_state(state + tile, (agg_fx << 2) | kFlagAgg);
+            int64_t look = tile - 1;
+            while (true) {
+                const int64_t idx = look - lane;
+                unsigned long long word = kFlagPrefix;            // virtual predecessor: prefix 0
+                if (idx >= 0) {
+                    word = ld_state(state + idx);
+                    while ((word & 3ull) == 0ull) word = ld_state(state + idx);
+                }
+                const unsigned pmask = __ballot_sync(0xffffffffu, (word & 3ull) == kFlagPrefix);
+                const int firstp = pmask ? (__ffs(pmask) - 1) : 31;  // nearest predecessor with a prefix
+                const unsigned long long val = (lane <= firstp) ? (word >> 2) : 0ull;
+                excl += warp_sum_ull(val);
+                if (pmask) break;                                  // (always true once idx < 0 appears)
+                look -= 32;
+            }
+            if (lane == 0) st_state(state + tile, ((excl + agg_fx) << 2) | kFlagPrefix);
+        }
+        if (lane == 0) sh_prefix = (double)excl * kFixInv;
+    }
+    __syncthreads();
+    const double off = sh_prefix + thread_excl;
+    if (base + kScanItems <= n) {
+        double2* q = reinterpret_cast<double2*>(cdf + base);
+#pragma unroll
+        for (int j = 0; j < kScanItems / 2; ++j) q[j] = make_double2(off + v[2 * j], off + v[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j)
+            if (base + j < n) cdf[base + j] = off + v[j];
+    }
+}
+
+// ---- search -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) searchsorted_kernel(const double* __restrict__ cdf, int64_t n_cdf,
+                                                           const double* __restrict__ u, int64_t n_u,
+                                                           int64_t* __restrict__ idx) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_u; k += stride) {
+        const double x = u[k];
+        int64_t lo = 0, hi = n_cdf;                 // first j with cdf_j > x
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(cdf + mid) <= x) lo = mid + 1; else hi = mid;
+        }
+        idx[k] = (lo < n_cdf) ? lo : (n_cdf - 1);   // clamp (quirk Q4)
+    }
+}
+
+// ---- gather -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ src, int64_t src_stride,
+                                                     double* __restrict__ dst, int64_t dst_stride,
+                                                     const int64_t* __restrict__ idx, int64_t n_out,
+                                                     int n_cols) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_out; k += stride) {
+        const int64_t a = idx[k];
+        int c = 0;
+        for (; c + 4 <= n_cols; c += 4) {           // four independent loads in flight
+            const double v0 = __ldg(src + (int64_t)(c + 0) * src_stride + a);
+            const double v1 = __ldg(src + (int64_t)(c + 1) * src_stride + a);
+            const double v2 = __ldg(src + (int64_t)(c + 2) * src_stride + a);
+            const double v3 = __ldg(src + (int64_t)(c + 3) * src_stride + a);
+            dst[(int64_t)(c + 0) * dst_stride + k] = v0;
+            dst[(int64_t)(c + 1) * dst_stride + k] = v1;
+            dst[(int64_t)(c + 2) * dst_stride + k] = v2;
+            dst[(int64_t)(c + 3) * dst_stride + k] = v3;
+        }
+        for (; c < n_cols; ++c) dst[(int64_t)c * dst_stride + k] = __ldg(src + (int64_t)c * src_stride + a);
+    }
+}
+
+// ---- distinct ancestors -------------------------------------------------------------------------------
+__global__ void mark_kernel(const int64_t* __restrict__ idx, int64_t n_idx, uint8_t* flags) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_idx; k += stride) flags[idx[k]] = 1;
+}
+
+__global__ void __launch_bounds__(256) count_bytes_kernel(const uint8_t* __restrict__ flags, int64_t n,
+                                                          unsigned long long* acc, unsigned int* ticket,
+                                                          int64_t* out) {
+    unsigned long long c = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) c += (flags[k] != 0);
+    c = warp_sum_ull(c);
+    __shared__ unsigned long long sh[8];
+    __shared__ bool is_last;
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sh[k];
+        atomicAdd(acc, t);                          // integer: order-independent
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        if (is_last) {
+            *out = (int64_t)atomicAdd(acc, 0ull);
+            *acc = 0ull;
+            *ticket = 0u;
+        }
+    }
+}
+
+}  // namespace smcb
+
+using namespace smcb;
+
+extern "C" int smcb_resample_uniforms(int32_t kind, int64_t n_global, int64_t first, int64_t count,
+                                      uint64_t seed, uint64_t stream_id, double* u_out, void* stream) {
+    SMCB_REQUIRE(kind >= 0 && kind <= 2 && n_global > 0 && count > 0 && u_out, "bad argument");
+    const int grid = grid_for(count, 256, 4, 8);
+    resample_uniforms_kernel<<<grid, 256, 0, as_stream(stream)>>>(kind, n_global, first, count, seed,
+                                                                   (uint32_t)stream_id, u_out);
+    return check_launch("resample_uniforms_kernel");
+}
+
+extern "C" int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mode, void* ws, void* stream) {
+    SMCB_REQUIRE(w && cdf && n > 0 && ws, "bad argument");
+    if (mode == SMCB_SCAN_SEQUENTIAL) {
+        scan_sequential_kernel<<<1, 256, 0, as_stream(stream)>>>(w, cdf, n);
+        return check_launch("scan_sequential_kernel");
+    }
+    SMCB_REQUIRE(mode == SMCB_SCAN_LOOKBACK, "unknown scan mode");
+    SMCB_REQUIRE((((uintptr_t)w | (uintptr_t)cdf) & 15) == 0, "w and cdf must be 16-byte aligned");
+    char* base = (char*)ws;
+    unsigned long long* state = (unsigned long long*)(base + kWsLarge);
+    unsigned int* counter = (unsigned int*)(base + kWsTickets) + 1;
+    const int64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+    scan_reset_kernel<<<grid_for(n_tiles, 256, 1, 4), 256, 0, as_stream(stream)>>>(state, n_tiles, counter);
+    scan_lookback_kernel<<<(unsigned)n_tiles, kScanThreads, 0, as_stream(stream)>>>(w, cdf, n, state, counter);
+    return check_launch("scan_lookback_kernel");
+}
+
+extern "C" int smcb_searchsorted(const double* cdf, int64_t n_cdf, const double* u, int64_t n_u,
+                                 int64_t* idx_out, void* stream) {
+    SMCB_REQUIRE(cdf && u && idx_out && n_cdf > 0 && n_u > 0, "bad argument");
+    searchsorted_kernel<<<grid_for(n_u, 256, 1, 8), 256, 0, as_stream(stream)>>>(cdf, n_cdf, u, n_u, idx_out);
+    return check_launch("searchsorted_kernel");
+}
+
+extern "C" int smcb_gather(const double* src, int64_t src_stride, double* dst, int64_t dst_stride,
+                           const int64_t* idx, int64_t n_out, int32_t n_cols, void* stream) {
+    SMCB_REQUIRE(src && dst && idx && n_out > 0 && n_cols > 0, "bad argument");
+    gather_kernel<<<grid_for(n_out, 256, 1, 8), 256, 0, as_stream(stream)>>>(src, src_stride, dst, dst_stride,
+                                                                              idx, n_out, n_cols);
+    return check_launch("gather_kernel");
+}
+
+extern "C" int smcb_count_unique(const int64_t* idx, int64_t n_idx, int64_t n_src, int64_t* count_out,
+                                 void* ws, void* stream) {
+    SMCB_REQUIRE(idx && count_out && ws && n_idx > 0 && n_src > 0, "bad argument");
+    char* base = (char*)ws;
+    uint8_t* flags = (uint8_t*)(base + kWsLarge);
+    cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)n_src, as_stream(stream));
+    if (e != cudaSuccess) {
+        set_error("smcb_count_unique: memset: %s", cudaGetErrorString(e));
+        return SMCB_ERR_CUDA;
+    }
+    mark_kernel<<<grid_for(n_idx, 256, 1, 8), 256, 0, as_stream(stream)>>>(idx, n_idx, flags);
+    count_bytes_kernel<<<grid_for(n_src, 256, 8, 4), 256, 0, as_stream(stream)>>>(
+        flags, n_src, (unsigned long long*)(base + kWsSmall + 64), (unsigned int*)(base + kWsTickets) + 2,
+        count_out);
+    return check_launch("count_bytes_kernel");
+}
+
+extern "C" int smcb_count_moved(const uint8_t* moved, int64_t n, int64_t* count_out, void* ws, void* stream) {
+    SMCB_REQUIRE(moved && count_out && ws && n > 0, "bad argument");
+    char* base = (char*)ws;
+    count_bytes_kernel<<<grid_for(n, 256, 8, 4), 256, 0, as_stream(stream)>>>(
+        moved, n, (unsigned long long*)(base + kWsSmall + 64), (unsigned int*)(base + kWsTickets) + 2,
+        count_out);
+    return check_launch("count_bytes_kernel");
+}

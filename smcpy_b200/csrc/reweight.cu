@@ -1,0 +1,372 @@
+// reweight.cu -- kernel (a): fused tempered reweighting + log-sum-exp normalisation + ESS,
+// and kernel (b): device-side bisection of ESS(phi) = target.
+//
+// Reference: smcpy/paths.py:86-105 (inc_log_weights), smcpy/smc/updater.py:122-133,
+// smcpy/smc/particles.py:141-162,200-205, smcpy/smc/samplers.py:250-301.
+//
+// Bytes per particle (algorithmic): partial pass reads ll, lp, log_w (24 B; 16 B when the
+// weights are uniform), finalize pass reads them again and writes log_w, w (16 B).
+#include "common.cuh"
+
+namespace smcb {
+
+constexpr int kRwThreads = 256;
+constexpr int kRwItems = 4;
+
+struct RwIn {
+    const double* ll;
+    const double* lp;
+    const double* lq;      // nullptr -> lp
+    const double* lw;      // nullptr -> uniform
+    double lw_uniform;     // log(1/n_global)
+    double lp_const;       // used when lp == nullptr (bisection fast path)
+    PathCoef c;
+};
+
+__device__ __forceinline__ double rw_value(const RwIn& in, int64_t i) {
+    const double ll = in.ll[i];
+    const double lp = in.lp ? in.lp[i] : in.lp_const;
+    const double lq = in.lq ? in.lq[i] : lp;
+    const double inc = path_inc(ll, lp, lq, in.c);
+    const double lw = in.lw ? in.lw[i] : in.lw_uniform;
+    return __dadd_rn(lw, inc);
+}
+
+// incremental weight only (bisection: previous weights are ignored, samplers.py:264-276)
+__device__ __forceinline__ double inc_value(const RwIn& in, int64_t i) {
+    const double ll = in.ll[i];
+    const double lp = in.lp ? in.lp[i] : in.lp_const;
+    const double lq = in.lq ? in.lq[i] : lp;
+    return path_inc(ll, lp, lq, in.c);
+}
+
+// Per-block (max, S1, S2) partials; the last block to finish merges them in block order
+// (deterministic) and writes the merged triple to `out3`.
+template <bool kIncOnly>
+__device__ __forceinline__ bool lse_partials_body(const RwIn& in, int64_t n, double* partials,
+                                                  unsigned int* ticket, double* out3, Lse& merged) {
+    __shared__ double sh[96];
+    __shared__ bool is_last;
+    Lse acc = lse_empty();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const double v0 = kIncOnly ? inc_value(in, i) : rw_value(in, i);
+        const double v1 = kIncOnly ? inc_value(in, i + stride) : rw_value(in, i + stride);
+        const double v2 = kIncOnly ? inc_value(in, i + 2 * stride) : rw_value(in, i + 2 * stride);
+        const double v3 = kIncOnly ? inc_value(in, i + 3 * stride) : rw_value(in, i + 3 * stride);
+        lse_push4(acc, v0, v1, v2, v3);
+    }
+    for (; i < n; i += stride) {
+        const double v = kIncOnly ? inc_value(in, i) : rw_value(in, i);
+        lse_push4(acc, v, kNegInf, kNegInf, kNegInf);
+    }
+    acc = block_lse(acc, sh);
+    if (threadIdx.x == 0) {
+        partials[3 * blockIdx.x + 0] = acc.m;
+        partials[3 * blockIdx.x + 1] = acc.s1;
+        partials[3 * blockIdx.x + 2] = acc.s2;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    // warp 0: lane l merges partials l, l+32, ... in order, then a fixed shuffle tree
+    if (threadIdx.x < 32) {
+        Lse a = lse_empty();
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) {
+            const volatile double* p = partials + 3 * b;
+            a = lse_merge(a, Lse{p[0], p[1], p[2]});
+        }
+        a = warp_lse(a);
+        if (threadIdx.x == 0) {
+            out3[0] = a.m;
+            out3[1] = a.s1;
+            out3[2] = a.s2;
+            *ticket = 0u;
+            merged = a;
+            return true;      // the one finalizer thread of the grid
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kRwThreads) rw_partials_kernel(RwIn in, int64_t n, double* partials,
+                                                                 unsigned int* ticket, double* out3) {
+    Lse merged;
+    lse_partials_body<false>(in, n, partials, ticket, out3, merged);
+}
+
+// scalars: [0] max, [1] S1, [2] S2, [3] total_unnorm_log_weight, [4] ESS, [5] log S1
+__device__ __forceinline__ void write_scalars(const Lse& a, double* sc) {
+    sc[0] = a.m;
+    sc[1] = a.s1;
+    sc[2] = a.s2;
+    const double ls = log(a.s1);
+    sc[3] = a.m + ls;                       // = Z0 + log(1 + sum exp(Z - Z0)), particles.py:200-205
+    sc[4] = (a.s1 * a.s1) / a.s2;           // = 1 / sum w^2, particles.py:158-162
+    sc[5] = ls;
+}
+
+__global__ void lse_merge_kernel(const double* parts, int n_parts, double* sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Lse a = lse_empty();
+    for (int r = 0; r < n_parts; ++r) a = lse_merge(a, Lse{parts[3 * r], parts[3 * r + 1], parts[3 * r + 2]});
+    write_scalars(a, sc);
+}
+
+// normalised log-weights and weights (particles.py:141-150,130-131):
+// log_w = (v - max) - log S1, w = exp(log_w); weights that underflow get log_w = -inf.
+__global__ void __launch_bounds__(kRwThreads) rw_finalize_kernel(RwIn in, int64_t n, const double* sc,
+                                                                 double* log_w, double* w) {
+    const double m = sc[0], ls = sc[5];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = rw_value(in, i);
+        double lw = (v - m) - ls;
+        double wi = exp(lw);
+        if (!(wi > 0.0)) {           // underflow or -inf (NaN when every weight is -inf)
+            lw = (wi != wi) ? wi : kNegInf;
+        }
+        log_w[i] = lw;
+        w[i] = wi;
+    }
+}
+
+// elementwise path values for host-facing wrappers: mode 0 = logpdf(phi), 1 = inc_log_weights
+__global__ void __launch_bounds__(kRwThreads) path_eval_kernel(RwIn in, int64_t n, int mode, double* out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ll = in.ll[i], lp = in.lp[i];
+        const double lq = in.lq ? in.lq[i] : lp;
+        out[i] = mode ? path_inc(ll, lp, lq, in.c) : path_target(ll, lp, lq, in.c.phi, in.c.pe, in.c.qe);
+    }
+}
+
+// ---- (b) bisection ----------------------------------------------------------------------
+// state: [0] result, [1] n_evals, [2] done, [3] xa, [4] dm, [5] fa, [6] x, [7] margin,
+//        [8] full-step margin, [9] phase (0: f(a)... see below)
+// Phases mirror AdaptiveSampler.optimize_step (samplers.py:250-259) followed by
+// scipy/optimize/Zeros/bisect.c:
+//   eval 0: x = 1     -> full-step test (_full_step_meets_target): margin > 0 -> phi = 1, done
+//   eval 1: x = phi_old (fa; delta_phi = 0 -> beta = 0 -> ESS = N exactly)  [computed in closed form]
+//   eval 2: x = 1 (fb)                                                      [reuses eval 0]
+//   eval k: midpoints
+constexpr double kXtol = 2e-12;
+constexpr double kRtol = 8.881784197001252e-16;
+constexpr int kBisectMaxIters = 48;   // (1-0)/2^41 < 2e-12: scipy stops after <= 40 halvings
+
+__global__ void bisect_begin_kernel(double phi_old, double* st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    st[0] = 1.0;
+    st[1] = 0.0;
+    st[2] = 0.0;
+    st[3] = phi_old;
+    st[4] = 1.0 - phi_old;
+    st[5] = 0.0;
+    st[6] = 1.0;      // first evaluation point: full step
+    st[7] = 0.0;
+    st[8] = 0.0;
+    st[9] = 0.0;
+}
+
+__device__ __forceinline__ double margin_from(const Lse& a, double n_global, double target) {
+    // predict_ess_margin (samplers.py:264-276): ESS = exp(2 LSE(b) - LSE(2b)) = S1^2/S2,
+    // ESS = 0 when either log-sum is -inf
+    double ess = 0.0;
+    if (a.m != kNegInf && a.s1 > 0.0 && a.s2 > 0.0) ess = (a.s1 * a.s1) / a.s2;
+    return ess - n_global * target;
+}
+
+__device__ void bisect_advance(double* st, const Lse& a, double phi_old, double target, double n_global) {
+    if (st[2] != 0.0) return;
+    const double f = margin_from(a, n_global, target);
+    st[7] = f;
+    st[1] += 1.0;
+    const int phase = (int)st[9];
+    if (phase == 0) {
+        st[8] = f;
+        if (f > 0.0) {                 // full step meets the target
+            st[0] = 1.0;
+            st[2] = 1.0;
+            return;
+        }
+        // scipy: fa = f(xa) with delta_phi = 0 -> ESS = N; fb = f(1) = f
+        const double fa = n_global - n_global * target;
+        st[1] += 2.0;                  // scipy evaluates f(a) and f(b)
+        st[5] = fa;
+        if (fa == 0.0) { st[0] = phi_old; st[2] = 1.0; return; }
+        if (f == 0.0) { st[0] = 1.0; st[2] = 1.0; return; }
+        // first midpoint
+        st[4] *= 0.5;
+        st[6] = st[3] + st[4];
+        st[9] = 1.0;
+        return;
+    }
+    const double xm = st[6], fa = st[5];
+    if (f * fa >= 0.0) st[3] = xm;
+    if (f == 0.0 || fabs(st[4]) < kXtol + kRtol * fabs(xm)) {
+        st[0] = xm;
+        st[2] = 1.0;
+        return;
+    }
+    st[4] *= 0.5;
+    st[6] = st[3] + st[4];
+}
+
+// one ESS evaluation at x = state[6]; the last block advances the bisection (single GPU)
+__global__ void __launch_bounds__(kRwThreads) ess_eval_kernel(RwIn in, int64_t n, double phi_old,
+                                                             double lambda, double target, double n_global,
+                                                             double* st, double* partials,
+                                                             unsigned int* ticket, double* out3,
+                                                             int advance) {
+    if (st[2] != 0.0) return;          // search finished: remaining launches are no-ops
+    const double x = st[6];
+    in.c.phi = x;
+    in.c.pe = fmin(1.0, x / lambda);
+    in.c.qe = fmax(0.0, (lambda - x) / lambda);
+    Lse merged;
+    const bool fin = lse_partials_body<true>(in, n, partials, ticket, out3, merged);
+    // single GPU: the finalizer thread advances the search; every other block has already
+    // read st[] (it took its ticket after its loads), the next launch is stream-ordered
+    if (fin && advance) bisect_advance(st, merged, phi_old, target, n_global);
+}
+
+__global__ void bisect_update_kernel(const double* parts, int n_parts, double phi_old, double target,
+                                     double n_global, double* st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Lse a = lse_empty();
+    for (int r = 0; r < n_parts; ++r) a = lse_merge(a, Lse{parts[3 * r], parts[3 * r + 1], parts[3 * r + 2]});
+    bisect_advance(st, a, phi_old, target, n_global);
+}
+
+static RwIn make_in(const double* ll, const double* lp, const double* lq, const double* lw,
+                    int64_t n_global, const smcb_path_t* path) {
+    RwIn in;
+    in.ll = ll;
+    in.lp = lp;
+    in.lq = lq;
+    in.lw = lw;
+    in.lw_uniform = log(1.0 / (double)n_global);
+    in.lp_const = 0.0;
+    in.c = make_path_coef(path->phi, path->phi_prev, path->lambda);
+    return in;
+}
+
+}  // namespace smcb
+
+using namespace smcb;
+
+extern "C" int smcb_path_eval(int64_t n, const double* ll, const double* lp, const double* lq,
+                              const smcb_path_t* path, int32_t mode, double* out, void* stream) {
+    SMCB_REQUIRE(n > 0 && ll && lp && path && out && (mode == 0 || mode == 1), "bad argument");
+    RwIn in = make_in(ll, lp, lq, nullptr, 1, path);
+    path_eval_kernel<<<grid_for(n, kRwThreads, 1, 8), kRwThreads, 0, as_stream(stream)>>>(in, n, mode, out);
+    return check_launch("path_eval_kernel");
+}
+
+extern "C" int smcb_reweight_partials(int64_t n, const double* ll, const double* lp, const double* lq,
+                                      const double* log_w_in, int64_t n_global, const smcb_path_t* path,
+                                      double* partial_out, void* ws, void* stream) {
+    SMCB_REQUIRE(n > 0 && ll && lp && path && partial_out && ws, "bad argument");
+    RwIn in = make_in(ll, lp, lq, log_w_in, n_global, path);
+    const int grid = grid_for(n, kRwThreads, kRwItems, 8);
+    char* w = (char*)ws;
+    rw_partials_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(
+        in, n, (double*)(w + kWsPartials), (unsigned int*)(w + kWsTickets), partial_out);
+    return check_launch("rw_partials_kernel");
+}
+
+extern "C" int smcb_lse_merge(const double* partials, int32_t n_parts, double* scalars_out, void* stream) {
+    SMCB_REQUIRE(partials && n_parts > 0 && scalars_out, "bad argument");
+    lse_merge_kernel<<<1, 32, 0, as_stream(stream)>>>(partials, n_parts, scalars_out);
+    return check_launch("lse_merge_kernel");
+}
+
+extern "C" int smcb_reweight_finalize(int64_t n, const double* ll, const double* lp, const double* lq,
+                                      const double* log_w_in, int64_t n_global, const smcb_path_t* path,
+                                      const double* scalars, double* log_w_out, double* w_out,
+                                      void* stream) {
+    SMCB_REQUIRE(n > 0 && ll && lp && path && scalars && log_w_out && w_out, "bad argument");
+    RwIn in = make_in(ll, lp, lq, log_w_in, n_global, path);
+    const int grid = grid_for(n, kRwThreads, kRwItems, 8);
+    rw_finalize_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(in, n, scalars, log_w_out, w_out);
+    return check_launch("rw_finalize_kernel");
+}
+
+extern "C" int smcb_reweight(int64_t n, const double* ll, const double* lp, const double* lq,
+                             const double* log_w_in, int64_t n_global, const smcb_path_t* path,
+                             double* log_w_out, double* w_out, double* scalars_out, void* ws,
+                             void* stream) {
+    SMCB_REQUIRE(ws != nullptr, "workspace required");
+    double* part = (double*)((char*)ws + kWsSmall);
+    int rc = smcb_reweight_partials(n, ll, lp, lq, log_w_in, n_global, path, part, ws, stream);
+    if (rc) return rc;
+    rc = smcb_lse_merge(part, 1, scalars_out, stream);
+    if (rc) return rc;
+    return smcb_reweight_finalize(n, ll, lp, lq, log_w_in, n_global, path, scalars_out, log_w_out, w_out,
+                                  stream);
+}
+
+extern "C" int smcb_ess_bisect_max_iters(void) { return kBisectMaxIters; }
+
+
+extern "C" int smcb_ess_bisect_begin(double phi_old, double* state, void* stream) {
+    SMCB_REQUIRE(state, "bad argument");
+    bisect_begin_kernel<<<1, 32, 0, as_stream(stream)>>>(phi_old, state);
+    return check_launch("bisect_begin_kernel");
+}
+
+extern "C" int smcb_ess_partial(int64_t n, const double* ll, const double* lp, const double* lq,
+                                double lp_const, double phi_old, double lambda, const double* state,
+                                double* partial_out, void* ws, void* stream) {
+    SMCB_REQUIRE(n > 0 && ll && state && partial_out && ws, "bad argument");
+    smcb_path_t p{phi_old, phi_old, lambda};
+    RwIn in = make_in(ll, lp, lq, nullptr, 1, &p);
+    in.lp_const = lp_const;
+    const int grid = grid_for(n, kRwThreads, kRwItems, 8);
+    char* w = (char*)ws;
+    ess_eval_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(
+        in, n, phi_old, lambda, 0.0, 0.0, const_cast<double*>(state), (double*)(w + kWsPartials),
+        (unsigned int*)(w + kWsTickets), partial_out, 0);
+    return check_launch("ess_eval_kernel");
+}
+
+extern "C" int smcb_ess_bisect_update(const double* partials, int32_t n_parts, double phi_old,
+                                      double target_ess, int64_t n_global, double* state, void* stream) {
+    SMCB_REQUIRE(partials && n_parts > 0 && state, "bad argument");
+    bisect_update_kernel<<<1, 32, 0, as_stream(stream)>>>(partials, n_parts, phi_old, target_ess,
+                                                          (double)n_global, state);
+    return check_launch("bisect_update_kernel");
+}
+
+static int bisect_iters(double phi_old) {
+    // 1 full-step evaluation + halvings until dm < xtol (bisect.c stopping rule), + slack
+    const double span = 1.0 - phi_old;
+    int k = 3;
+    if (span > kXtol) k = 3 + (int)ceil(log2(span / kXtol));
+    return k < kBisectMaxIters ? k : kBisectMaxIters;
+}
+
+extern "C" int smcb_ess_bisect(int64_t n, const double* ll, const double* lp, const double* lq,
+                               double lp_const, double phi_old, double lambda, double target_ess,
+                               int64_t n_global, double* state, void* ws, void* stream) {
+    SMCB_REQUIRE(n > 0 && ll && state && ws, "bad argument");
+    SMCB_REQUIRE(phi_old >= 0.0 && phi_old < 1.0, "phi_old must be in [0, 1)");
+    int rc = smcb_ess_bisect_begin(phi_old, state, stream);
+    if (rc) return rc;
+    smcb_path_t p{phi_old, phi_old, lambda};
+    RwIn in = make_in(ll, lp, lq, nullptr, 1, &p);
+    in.lp_const = lp_const;
+    const int grid = grid_for(n, kRwThreads, kRwItems, 8);
+    char* w = (char*)ws;
+    const int iters = bisect_iters(phi_old);
+    for (int it = 0; it < iters; ++it) {
+        ess_eval_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(
+            in, n, phi_old, lambda, target_ess, (double)n_global, state, (double*)(w + kWsPartials),
+            (unsigned int*)(w + kWsTickets), (double*)(w + kWsSmall), 1);
+    }
+    return check_launch("ess_eval_kernel");
+}

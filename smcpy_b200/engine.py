@@ -1,0 +1,536 @@
+"""
+Device-resident engine: the host side of the hot path
+    reweight -> ESS / phi bisection -> resample -> covariance -> K x Metropolis
+driving the C-ABI kernels of libsmcb200.so on torch device tensors (PyTorch is plumbing:
+memory, streams, torch.distributed).  Every numerical step is a call into the library.
+
+Particle store (structure of arrays, fp64): one (d+2, N) tensor `cols` per shard whose rows are
+the d parameter columns, the log-likelihood and the summed log-prior, so a resample is one
+gather over d+2 columns into the ping-pong twin.
+"""
+
+import ctypes as C
+import math
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+
+# ---------------------------------------------------------------------------------------------
+# runtime: device, workspace, process group
+# ---------------------------------------------------------------------------------------------
+class Runtime:
+    _inst = None
+
+    def __init__(self):
+        _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._ws = None
+        self._ws_bytes = 0
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None or cls._inst.device.index != torch.cuda.current_device():
+            cls._inst = Runtime()
+        return cls._inst
+
+    def workspace(self, n, d):
+        need = int(_lib.lib.smcb_workspace_bytes(int(n), int(d)))
+        if need > self._ws_bytes:
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+            self._ws_bytes = need
+        return self._ws
+
+
+def dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n_global, rank, world):
+    """Contiguous block partition of global particle ids (np.array_split sizes, as
+    smcpy/mcmc/parallel_vector_mcmc.py:38 splits the model inputs)."""
+    base, rem = divmod(int(n_global), world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class PhiloxRNG:
+    """Native counter-based generator: (seed, per-use stream counter).  Streams are consumed
+    identically on every rank so multi-GPU runs stay in lock step."""
+
+    def __init__(self, seed=None):
+        if seed is None:
+            seed = int(np.random.SeedSequence().entropy) & ((1 << 63) - 1)
+        self.seed = int(seed) & ((1 << 64) - 1)
+        self._stream = 0
+
+    def next_stream(self):
+        self._stream += 1
+        return self._stream
+
+
+def dev(a, dtype=torch.float64):
+    """Host array -> device tensor (contiguous)."""
+    rt = Runtime.get()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(rt.device, non_blocking=False)
+
+
+def make_path(phi, phi_prev, lam):
+    return _lib.Path(float(phi), float(phi_prev), float(lam))
+
+
+# ---------------------------------------------------------------------------------------------
+# problem specification
+# ---------------------------------------------------------------------------------------------
+class ProblemSpec:
+    """Model + data + priors + likelihood bound to device buffers (the VectorMCMC constructor
+    arguments, smcpy/mcmc/vector_mcmc.py:11-34, as an smcb_problem_t)."""
+
+    def __init__(self, model, data, priors, log_like_args, kind):
+        from .models import DeviceModel
+        from .priors import describe_prior
+        rt = Runtime.get()
+        self.model = model
+        self.kind = kind
+        self.priors = list(priors)
+        self.fused = isinstance(model, DeviceModel)
+        c = _lib.Problem()
+        descs = [describe_prior(p) for p in self.priors]
+        if len(descs) > _lib.MAX_PRIORS:
+            raise NotImplementedError("at most %d priors" % _lib.MAX_PRIORS)
+        d = 0
+        for i, (k, ncols, a, b, lpin) in enumerate(descs):
+            c.priors[i] = _lib.Prior(k, ncols, a, b, lpin)
+            d += ncols * (ncols + 1) // 2 if k == _lib.PRIOR_IMPROPER_COV else 1
+        c.n_priors = len(descs)
+        c.n_params = d
+        self.d = d
+        self.n_priors = len(descs)
+        # summed log-prior of any particle inside the support (all device priors are flat)
+        self.lp_const = float(np.sum([lpin for (_, _, _, _, lpin) in descs]))
+        data = np.asarray(data, dtype=np.float64)
+        self._data_dev = dev(data.reshape(-1))
+        c.data = self._data_dev.data_ptr()
+        self._x_dev = None
+        if kind == "normal":
+            c.loglike_id = _lib.LL_NORMAL
+            c.n_data = int(data.reshape(-1).shape[0])
+            c.n_snapshots = 1
+            c.sigma_is_param = 1 if log_like_args is None else 0
+            c.sigma = 0.0 if log_like_args is None else float(np.asarray(log_like_args).reshape(-1)[0])
+            c.n_model_params = d - c.sigma_is_param
+        elif kind == "mvnormal":
+            if data.ndim != 2:
+                raise ValueError("MVNormal data must be (snapshots, features)")
+            c.loglike_id = _lib.LL_MVNORMAL
+            c.n_snapshots, c.n_data = int(data.shape[0]), int(data.shape[1])
+            args = list(log_like_args)
+            if len(args) != c.n_data * (c.n_data + 1) // 2:
+                raise ValueError("MVNormal args must hold F(F+1)/2 covariance terms")
+            if len(args) > _lib.MAX_COV_ARGS:
+                raise NotImplementedError("MVNormal on the device supports up to 3 features")
+            n_none = args.count(None)
+            j = 0
+            for i, a in enumerate(args):
+                if a is None:
+                    c.cov_param_col[i] = d - n_none + j
+                    j += 1
+                else:
+                    c.cov_param_col[i] = -1
+                    c.cov_fixed[i] = float(a)
+            c.n_model_params = d - n_none
+        else:
+            raise NotImplementedError(kind)
+        if self.fused:
+            c.model_id = model.model_id
+            if model.n_model_params != c.n_model_params:
+                raise ValueError("model takes %d parameters but the priors/likelihood leave %d"
+                                 % (model.n_model_params, c.n_model_params))
+            if model.model_id == _lib.MODEL_LINEAR:
+                if model.n_out != c.n_data:
+                    raise ValueError("linear model grid and data length differ")
+                self._x_dev = dev(model.x)
+                c.xgrid = self._x_dev.data_ptr()
+            elif model.model_id == _lib.MODEL_SPRING_MASS:
+                if model.n_out != c.n_data:
+                    raise ValueError("spring-mass output count and data length differ")
+                c.model_args[0], c.model_args[1] = model.x0, model.v0
+                c.model_args[2], c.model_args[3] = model.dt, float(model.nsub)
+            elif model.model_id == _lib.MODEL_IDENTITY:
+                if model.n_out != c.n_data:
+                    raise ValueError("identity model size and data length differ")
+        else:
+            if not callable(model):
+                raise TypeError("model must be a smcpy_b200.models.DeviceModel or a torch callable")
+            if kind != "normal":
+                raise NotImplementedError("torch-callable models support the Normal likelihood")
+            c.model_id = _lib.MODEL_IDENTITY      # unused by the un-fused kernels
+        self.c = c
+        self.device = rt.device
+
+    @property
+    def n_model_params(self):
+        return int(self.c.n_model_params)
+
+
+# ---------------------------------------------------------------------------------------------
+# particle state
+# ---------------------------------------------------------------------------------------------
+class DeviceState:
+    """Working set of one particle shard."""
+
+    def __init__(self, n_local, n_global, d, id_offset=0):
+        rt = Runtime.get()
+        dv = rt.device
+        self.n, self.n_global, self.d, self.id_offset = int(n_local), int(n_global), int(d), int(id_offset)
+        f64 = torch.float64
+        self.cols = torch.empty((d + 2, self.n), dtype=f64, device=dv)
+        self.cols_alt = torch.empty((d + 2, self.n), dtype=f64, device=dv)
+        self.log_w = torch.empty(self.n, dtype=f64, device=dv)
+        self.w = torch.empty(self.n, dtype=f64, device=dv)
+        self.log_w_alt = torch.empty(self.n, dtype=f64, device=dv)
+        self.w_alt = torch.empty(self.n, dtype=f64, device=dv)
+        self.lq = None
+        self.cdf = torch.empty(self.n, dtype=f64, device=dv)
+        self.u = torch.empty(self.n, dtype=f64, device=dv)
+        self.idx = torch.empty(self.n, dtype=torch.int64, device=dv)
+        self.moved = torch.zeros(self.n, dtype=torch.uint8, device=dv)
+        self.accept_counts = torch.zeros(_lib.MAX_MCMC_STEPS, dtype=torch.int64, device=dv)
+        self.flags = torch.zeros(1, dtype=torch.int32, device=dv)
+        self.scalars = torch.zeros(16, dtype=f64, device=dv)
+        self.bis = torch.zeros(16, dtype=f64, device=dv)
+        self.counts = torch.zeros(4, dtype=torch.int64, device=dv)
+        self.mean = torch.zeros(d, dtype=f64, device=dv)
+        self.cov = torch.zeros((d, d), dtype=f64, device=dv)
+        self.chol = torch.zeros((d, d), dtype=f64, device=dv)
+        self.sums = torch.zeros(1 + d + d * d, dtype=f64, device=dv)
+        self.ws = rt.workspace(self.n, d)
+        self.uniform_weights = False
+        self.total_unnorm_log_weight = None
+
+    @property
+    def params(self):
+        return self.cols[:self.d]
+
+    @property
+    def ll(self):
+        return self.cols[self.d]
+
+    @property
+    def lp(self):
+        return self.cols[self.d + 1]
+
+    def set_params_host(self, params):
+        """(n, d) host array -> SoA columns."""
+        a = dev(np.asarray(params, dtype=np.float64))
+        call("smcb_aos_to_soa", ptr(a), ptr(self.cols), self.n, self.d, self.n, stream_ptr())
+
+    def params_host(self):
+        out = torch.empty((self.n, self.d), dtype=torch.float64, device=self.cols.device)
+        call("smcb_soa_to_aos", ptr(self.cols), ptr(out), self.n, self.d, self.n, stream_ptr())
+        return out.cpu().numpy()
+
+    def set_uniform_weights(self):
+        """Weights after initialisation / resampling: log(1/N) normalised the reference's way
+        (particles.py:141-150: exp(log((1/N)...)))."""
+        n = self.n_global
+        lw = float(np.log(1.0 / n))
+        w = float(np.exp(lw))
+        call("smcb_fill_f64", ptr(self.log_w), self.n, lw, stream_ptr())
+        call("smcb_fill_f64", ptr(self.w), self.n, w, stream_ptr())
+        self.uniform_weights = True
+
+    def check_flags(self, where):
+        f = int(self.flags.item())
+        if f == 0:
+            return 0
+        self.flags.zero_()
+        if f & _lib.FLAG_PRIOR_OOB:
+            raise ValueError("Initial inputs are out of bounds; prior log prob = -inf (%s)" % where)
+        if f & _lib.FLAG_MODEL_NAN:
+            raise ValueError("nan in model output.")
+        if f & _lib.FLAG_COV_NOT_PD:
+            raise ValueError("MVNormal covariance is not positive definite for a particle with "
+                             "finite prior (%s); add an ImproperCov prior" % where)
+        return f
+
+
+# ---------------------------------------------------------------------------------------------
+# collectives (only when a process group exists)
+# ---------------------------------------------------------------------------------------------
+def _all_gather_rows(t):
+    import torch.distributed as dist
+    rank, world = dist_info()
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous())
+    return out
+
+
+def _all_reduce_sum(t):
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# (a) reweight
+# ---------------------------------------------------------------------------------------------
+def reweight(st, path):
+    """Updater._compute_new_weights + Particles normalisation (updater.py:122-133,
+    particles.py:141-162).  Returns (ess, total_unnorm_log_weight) after one host sync."""
+    _, world = dist_info()
+    lw_in = None if st.uniform_weights else st.log_w
+    s = stream_ptr()
+    if world == 1:
+        call("smcb_reweight", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
+             C.byref(path), ptr(st.log_w_alt), ptr(st.w_alt), ptr(st.scalars), ptr(st.ws), s)
+    else:
+        part = st.scalars[8:11]
+        call("smcb_reweight_partials", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
+             C.byref(path), ptr(part), ptr(st.ws), s)
+        parts = _all_gather_rows(part)                       # rank-ordered (max, S1, S2)
+        call("smcb_lse_merge", ptr(parts), world, ptr(st.scalars), s)
+        call("smcb_reweight_finalize", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
+             C.byref(path), ptr(st.scalars), ptr(st.log_w_alt), ptr(st.w_alt), s)
+    st.log_w, st.log_w_alt = st.log_w_alt, st.log_w
+    st.w, st.w_alt = st.w_alt, st.w
+    st.uniform_weights = False
+    sc = st.scalars[:6].cpu().numpy()                        # step-boundary sync
+    st.total_unnorm_log_weight = float(sc[3])
+    return float(sc[4]), float(sc[3])
+
+
+# ---------------------------------------------------------------------------------------------
+# (b) adaptive phi
+# ---------------------------------------------------------------------------------------------
+def bisect_iters(phi_old):
+    span = 1.0 - phi_old
+    k = 3
+    if span > 2e-12:
+        k = 3 + int(math.ceil(math.log2(span / 2e-12)))
+    return min(k, int(_lib.lib.smcb_ess_bisect_max_iters()))
+
+
+def find_phi(st, spec, phi_old, target_ess, lam=1.0):
+    """AdaptiveSampler.optimize_step's root search (samplers.py:250-259) on the device."""
+    _, world = dist_info()
+    s = stream_ptr()
+    lp = None if (st.lq is None and spec is not None) else st.lp
+    lp_const = spec.lp_const if spec is not None else 0.0
+    if world == 1:
+        call("smcb_ess_bisect", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
+             float(target_ess), st.n_global, ptr(st.bis), ptr(st.ws), s, launches=1 + bisect_iters(phi_old))
+    else:
+        call("smcb_ess_bisect_begin", float(phi_old), ptr(st.bis), s)
+        part = st.scalars[8:11]
+        for _ in range(bisect_iters(phi_old)):
+            call("smcb_ess_partial", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
+                 ptr(st.bis), ptr(part), ptr(st.ws), s)
+            parts = _all_gather_rows(part)
+            call("smcb_ess_bisect_update", ptr(parts), world, float(phi_old), float(target_ess), st.n_global,
+                 ptr(st.bis), s)
+    b = st.bis[:10].cpu().numpy()
+    if b[2] == 0.0:
+        raise RuntimeError("device bisection did not converge")
+    return float(b[0])
+
+
+def ess_margin(st, spec, phi_new, phi_old, target_ess, lam=1.0):
+    """AdaptiveSampler.predict_ess_margin (samplers.py:264-276) for one candidate phi."""
+    _, world = dist_info()
+    s = stream_ptr()
+    lp = None if (st.lq is None and spec is not None) else st.lp
+    lp_const = spec.lp_const if spec is not None else 0.0
+    st.bis.zero_()
+    st.bis[6] = float(phi_new)
+    part = st.scalars[8:11]
+    call("smcb_ess_partial", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
+         ptr(st.bis), ptr(part), ptr(st.ws), s)
+    parts = _all_gather_rows(part) if world > 1 else part.reshape(1, 3)
+    call("smcb_lse_merge", ptr(parts.contiguous()), world, ptr(st.scalars), s)
+    sc = st.scalars[:3].cpu().numpy()
+    ess = 0.0
+    if np.isfinite(sc[0]) and sc[1] > 0 and sc[2] > 0:
+        ess = sc[1] * sc[1] / sc[2]
+    return ess - st.n_global * target_ess
+
+
+# ---------------------------------------------------------------------------------------------
+# (c) resample
+# ---------------------------------------------------------------------------------------------
+def resample_indices(st, u_dev, scan_mode):
+    """idx = digitize(u, cumsum(w)) for the local shard (single GPU)."""
+    s = stream_ptr()
+    call("smcb_cdf_scan", ptr(st.w), ptr(st.cdf), st.n, int(scan_mode), ptr(st.ws), s,
+         launches=1 if scan_mode == _lib.SCAN_SEQUENTIAL else 2)
+    call("smcb_searchsorted", ptr(st.cdf), st.n, ptr(u_dev), st.n, ptr(st.idx), s)
+    return st.idx
+
+
+def count_unique(st, idx):
+    call("smcb_count_unique", ptr(idx), st.n, st.n, ptr(st.counts), ptr(st.ws), stream_ptr())
+    return st.counts[0]
+
+
+def gather_particles(st, idx):
+    call("smcb_gather", ptr(st.cols), st.n, ptr(st.cols_alt), st.n, ptr(idx), st.n, st.d + 2, stream_ptr())
+    st.cols, st.cols_alt = st.cols_alt, st.cols
+    st.set_uniform_weights()
+
+
+def resample(st, kernel, resample_rng, warn_threshold):
+    """Updater._resample (updater.py:135-165).  Replay mode (numpy Generator): both uniform
+    draws of the reference (quirk Q1) are made on the host, the sequential scan gives
+    bit-exact indices.  Native mode: uniforms on the device, look-back scan, the distinct
+    ancestors are counted from the indices actually used."""
+    _, world = dist_info()
+    if world > 1:
+        from .sharded import resample_sharded
+        return resample_sharded(st, kernel, resample_rng, warn_threshold)
+    n = st.n
+    host_rng = isinstance(kernel.rng, np.random.Generator)
+    kind = getattr(resample_rng, "kind", None)
+    if host_rng or kind is None:
+        u1 = np.asarray(resample_rng(kernel, n), dtype=np.float64)
+        idx = resample_indices(st, dev(u1), _lib.SCAN_SEQUENTIAL)
+        idx_sel = idx.clone()
+        u2 = np.asarray(resample_rng(kernel, n), dtype=np.float64)
+        call("smcb_searchsorted", ptr(st.cdf), n, ptr(dev(u2)), n, ptr(st.idx), stream_ptr())
+        n_unique = count_unique(st, st.idx)
+        idx = idx_sel
+    else:
+        rng = kernel.rng
+        call("smcb_resample_uniforms", int(kind), st.n_global, 0, n, rng.seed, rng.next_stream(), ptr(st.u),
+             stream_ptr())
+        idx = resample_indices(st, st.u, _lib.SCAN_LOOKBACK)
+        n_unique = count_unique(st, idx)
+    gather_particles(st, idx)
+    if int(n_unique.item()) <= max(1, warn_threshold * st.n_global):
+        warnings.warn(f"Resampled to less than {warn_threshold * 100}% of particles; ", UserWarning)
+    return idx
+
+
+# ---------------------------------------------------------------------------------------------
+# covariance + Cholesky
+# ---------------------------------------------------------------------------------------------
+def _host_chol_psd(cov):
+    """vector_mcmc.py:216-236 fallback for a non-PD covariance (quirk Q9), on the host."""
+    warnings.warn("Covariance matrix is not positive semi-definite; forcing negative eigenvalues "
+                  "to zero and rebuilding covariance matrix.")
+    eigval, eigvec = np.linalg.eigh(cov)
+    eigval[eigval < 0] = 0
+    cov = (eigvec @ np.diag(eigval)) @ eigvec.T
+    cov += 1e-14 * np.eye(len(eigval))
+    return np.linalg.cholesky(cov)
+
+
+def covariance(st):
+    """Particles.compute_covariance (particles.py:189-198) + its Cholesky factor; leaves
+    st.cov / st.chol on the device and returns the host copy of cov."""
+    _, world = dist_info()
+    s = stream_ptr()
+    d = st.d
+    if world == 1:
+        call("smcb_weighted_cov", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.mean), ptr(st.cov),
+             ptr(st.sums), ptr(st.ws), s)
+    else:
+        call("smcb_weighted_sums1", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.sums), ptr(st.ws), s)
+        _all_reduce_sum(st.sums[:1 + d])
+        call("smcb_mean_from_sums", ptr(st.sums), d, ptr(st.mean), s)
+        s2 = st.sums[1 + d:]
+        call("smcb_weighted_sums2", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.mean), ptr(s2),
+             ptr(st.ws), s)
+        _all_reduce_sum(s2)
+        call("smcb_cov_from_sums", ptr(st.sums), ptr(s2), d, ptr(st.cov), s)
+    return st.cov
+
+
+def cholesky(st, cov_dev=None):
+    call("smcb_cholesky", ptr(st.cov if cov_dev is None else cov_dev), st.d, ptr(st.chol), ptr(st.flags),
+         stream_ptr())
+    f = int(st.flags.item())
+    if f & _lib.FLAG_CHOL_FAIL:
+        st.flags.zero_()
+        cov = (st.cov if cov_dev is None else cov_dev).cpu().numpy()
+        st.chol.copy_(dev(_host_chol_psd(cov)))
+    return st.chol
+
+
+# ---------------------------------------------------------------------------------------------
+# (d) Metropolis
+# ---------------------------------------------------------------------------------------------
+def eval_incoming(st, spec, lp_cols=None):
+    """log-priors + log-likelihood of the particles in st.cols (vector_mcmc.py:162-166)."""
+    if spec.fused:
+        call("smcb_mh_init", C.byref(spec.c), ptr(st.cols), st.n, st.n, ptr(st.ll), ptr(st.lp), ptr(lp_cols),
+             ptr(st.flags), stream_ptr())
+    else:
+        from .callable_route import eval_incoming_callable
+        eval_incoming_callable(st, spec, lp_cols)
+
+
+def mutate(st, spec, num_samples, path, rng, check_incoming=False):
+    """VectorMCMC.smc_metropolis (vector_mcmc.py:46-62): `num_samples` fused Metropolis steps in
+    place, proposal covariance rescaled from the global accept count after every step.
+    st.chol must hold the Cholesky factor of the proposal covariance.  Returns the list of
+    per-step accept counts lazily (device tensor)."""
+    if num_samples > _lib.MAX_MCMC_STEPS:
+        raise ValueError("num_mcmc_samples > %d" % _lib.MAX_MCMC_STEPS)
+    _, world = dist_info()
+    s = stream_ptr()
+    st.accept_counts[:max(1, num_samples)].zero_()
+    st.moved.zero_()
+    host_rng = isinstance(rng, np.random.Generator)
+    r = _lib.Rng()
+    r.id_offset = st.id_offset
+    keep = []
+    for k in range(num_samples):
+        if host_rng:
+            z = dev(rng.normal(0, 1, (st.n, st.d)))
+            u = dev(rng.uniform(0, 1, (st.n, 1)).reshape(-1))
+            keep.append((z, u))
+            r.mode, r.z, r.u = 1, z.data_ptr(), u.data_ptr()
+        else:
+            r.mode, r.seed, r.stream = 0, rng.seed, rng.next_stream()
+        if spec.fused:
+            call("smcb_mh_step", C.byref(spec.c), C.byref(path), ptr(st.cols), st.n, st.n, st.n_global,
+                 ptr(st.ll), ptr(st.lp), ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), k, C.byref(r),
+                 ptr(st.flags), s)
+        else:
+            from .callable_route import mh_step_callable
+            mh_step_callable(st, spec, path, k, r)
+        if world > 1:
+            _all_reduce_sum(st.accept_counts[k:k + 1])
+    call("smcb_count_moved", ptr(st.moved), st.n, ptr(st.counts[1:]), ptr(st.ws), s)
+    moved = st.counts[1:2].clone()
+    if world > 1:
+        _all_reduce_sum(moved)
+    st.check_flags("smc_metropolis")                         # sync; raises on NaN
+    return float(moved.item()) / st.n_global
+
+
+# ---------------------------------------------------------------------------------------------
+# host-array wrappers of the path arithmetic (GeometricPath.logpdf / inc_log_weights)
+# ---------------------------------------------------------------------------------------------
+def _path_eval(ll, lp, lq, path, mode):
+    n = ll.shape[0]
+    out = torch.empty(n, dtype=torch.float64, device=Runtime.get().device)
+    a, b = dev(ll.reshape(-1)), dev(lp.reshape(-1))
+    c = None if lq is None else dev(lq.reshape(-1))
+    call("smcb_path_eval", n, ptr(a), ptr(b), ptr(c), C.byref(path), mode, ptr(out), stream_ptr())
+    return out.cpu().numpy().reshape(-1, 1)
+
+
+def host_path_logpdf(ll, lp, lq, phi, lam):
+    return _path_eval(ll, lp, lq, make_path(phi, phi, lam), 0)
+
+
+def host_inc_log_weights(ll, lp, lq, phi, phi_prev, lam):
+    return _path_eval(ll, lp, lq, make_path(phi, phi_prev, lam), 1)

@@ -1,0 +1,60 @@
+"""Initial particles: prior (or proposal) draw, one log-likelihood evaluation, uniform
+log-weights  (smcpy/smc/initializer.py:42-78)."""
+
+import numpy as np
+
+from . import engine
+from ._lib import call, ptr, stream_ptr
+from .kernel import KernelBase
+from .particles import Particles
+
+import ctypes as C
+
+
+class Initializer:
+    def __init__(self, mcmc_kernel):
+        self.mcmc_kernel = mcmc_kernel
+
+    @property
+    def mcmc_kernel(self):
+        return self._mcmc_kernel
+
+    @mcmc_kernel.setter
+    def mcmc_kernel(self, mcmc_kernel):
+        if not isinstance(mcmc_kernel, KernelBase):
+            raise TypeError
+        self._mcmc_kernel = mcmc_kernel
+
+    def initialize_state(self, num_particles):
+        """Device working set for `num_particles` global particles (this rank's shard)."""
+        kernel = self.mcmc_kernel
+        spec = kernel.spec
+        rank, world = engine.dist_info()
+        lo, hi = engine.shard_bounds(num_particles, rank, world)
+        st = engine.DeviceState(hi - lo, num_particles, spec.d, id_offset=lo)
+        host_rng = isinstance(kernel.rng, np.random.Generator)
+        if kernel.has_proposal() or host_rng:
+            if kernel.has_proposal():
+                params = kernel.sample_from_proposal(num_particles)
+            else:
+                params = kernel.sample_from_prior(num_particles)
+            arr = np.column_stack([np.asarray(params[k], dtype=np.float64) for k in kernel.param_order])
+            st.set_params_host(arr[lo:hi])
+        else:
+            rng = kernel.rng
+            call("smcb_sample_priors", C.byref(spec.c), ptr(st.cols), st.n, st.n, rng.seed, rng.next_stream(),
+                 st.id_offset, stream_ptr())
+        engine.eval_incoming(st, spec)
+        st.check_flags("initialize_particles")
+        st.set_uniform_weights()
+        lw0 = np.log(1 / num_particles)
+        st.total_unnorm_log_weight = float(lw0 + np.log(1 + (num_particles - 1) * 1.0))   # _logsum of N equal terms
+        return st
+
+    def initialize_particles(self, num_particles):
+        st = self.initialize_state(num_particles)
+        return self.particles_from_state(st)
+
+    def particles_from_state(self, st):
+        attrs = {"total_unnorm_log_weight": st.total_unnorm_log_weight, "phi": 0, "mutation_ratio": 0}
+        return Particles.from_state(st, self.mcmc_kernel.param_order, attrs)

@@ -1,0 +1,172 @@
+"""
+B200VectorMCMC -- drop-in sibling of smcpy.VectorMCMC / ParallelVectorMCMC
+(smcpy/mcmc/vector_mcmc.py:10-236, parallel_vector_mcmc.py:7-47) whose smc_metropolis,
+log-prior and log-likelihood evaluations run as sm_100a kernels.
+
+Same constructor and method names, numpy in / numpy out, so it can sit inside the reference's
+own VectorMCMCKernel and samplers (parity path: arrays cross the bus every SMC step and the
+host numpy Generator supplies the normals and uniforms in the reference's order).  The
+device-resident samplers in smcpy_b200.samplers bypass the host arrays altogether.
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from ._lib import call, ptr, stream_ptr
+from .log_likelihoods import Normal, loglike_kind
+from .priors import prior_dim
+
+
+def _spec_for_priors(priors):
+    """Minimal problem carrying only a prior table (for stand-alone prior log-pdfs)."""
+    from .priors import describe_prior
+    c = _lib.Problem()
+    d = 0
+    for i, p in enumerate(priors):
+        k, ncols, a, b, lpin = describe_prior(p)
+        c.priors[i] = _lib.Prior(k, ncols, a, b, lpin)
+        d += ncols * (ncols + 1) // 2 if k == _lib.PRIOR_IMPROPER_COV else 1
+    c.n_priors = len(priors)
+    c.n_params = d
+    return c, d
+
+
+def device_log_priors(priors, x, problem_c=None):
+    """(N, n_priors) un-summed log-priors of host rows x (N, d)  (vector_mcmc.py:98-111)."""
+    x = np.asarray(x, dtype=np.float64)
+    if problem_c is None:
+        problem_c, d = _spec_for_priors(priors)
+    else:
+        d = int(problem_c.n_params)
+    if x.ndim != 2 or x.shape[1] != d:
+        raise ValueError("Num prior distributions != num input params")
+    n = x.shape[0]
+    rt = engine.Runtime.get()
+    soa = torch.empty((d, n), dtype=torch.float64, device=rt.device)
+    call("smcb_aos_to_soa", ptr(engine.dev(x)), ptr(soa), n, d, n, stream_ptr())
+    lp = torch.empty(n, dtype=torch.float64, device=rt.device)
+    cols = torch.empty((int(problem_c.n_priors), n), dtype=torch.float64, device=rt.device)
+    call("smcb_log_priors", C.byref(problem_c), ptr(soa), n, n, ptr(lp), ptr(cols), stream_ptr())
+    return cols.t().contiguous().cpu().numpy()
+
+
+def device_log_likelihood(loglike, inputs):
+    """(N,1) log-likelihoods for a log-likelihood descriptor whose priors are irrelevant:
+    evaluated with wide improper-uniform priors so every row is evaluated."""
+    from .priors import ImproperUniform
+    inputs = np.asarray(inputs, dtype=np.float64)
+    priors = [ImproperUniform() for _ in range(inputs.shape[1])]
+    mc = B200VectorMCMC(loglike._model, loglike._data, priors, loglike._args, type(loglike))
+    return mc.evaluate_log_likelihood(inputs)
+
+
+class B200VectorMCMC:
+    def __init__(self, model, data, priors, log_like_args=None, log_like_func=Normal):
+        """
+        :param model: a smcpy_b200.models.DeviceModel (fused kernels) or a torch callable
+            mapping a device tensor (N, d_model) to (N, M) (un-fused route)
+        :param data: 1-D data array (Normal) or (snapshots, features) array (MVNormal)
+        :param priors: scipy.stats.uniform frozen objects, ImproperUniform, ImproperCov
+        :param log_like_args: likelihood hyper-parameters as in the reference
+        :param log_like_func: Normal or MVNormal (these or the reference's classes)
+        """
+        self._eval_model = model
+        self._data = data
+        self._priors = priors
+        self._log_like_args = log_like_args
+        self._kind = loglike_kind(log_like_func)
+        self._log_like_func = log_like_func(model, data, log_like_args)
+        self._rng = np.random.default_rng()
+        self._spec = None
+
+    # -- reference surface ---------------------------------------------------------------------
+    @property
+    def rng(self):
+        return self._rng
+
+    @rng.setter
+    def rng(self, rng):
+        if isinstance(rng, (np.random.Generator, engine.PhiloxRNG)):
+            self._rng = rng
+        else:
+            raise TypeError("Random number generator must be a numpy generator.")
+
+    @property
+    def spec(self):
+        if self._spec is None:
+            self._spec = engine.ProblemSpec(self._eval_model, self._data, self._priors, self._log_like_args,
+                                            self._kind)
+        return self._spec
+
+    @staticmethod
+    def evaluate_log_posterior(inputs, log_likelihood, log_priors):
+        """vector_mcmc.py:120-122; VectorMCMCKernel overwrites this attribute with path.logpdf."""
+        return np.sum(np.hstack((log_likelihood, log_priors)), axis=1)
+
+    def evaluate_model(self, inputs):
+        return self._eval_model(inputs)
+
+    def sample_from_priors(self, num_samples):
+        """vector_mcmc.py:91-96 (host draw from the shared generator, reference order)."""
+        if not isinstance(self._rng, np.random.Generator):
+            raise TypeError("host prior sampling needs a numpy Generator; the native sampler draws "
+                            "uniform priors on the device")
+        samples = [p.rvs(num_samples, random_state=self._rng).T for p in self._priors]
+        return np.vstack(samples).T
+
+    def _get_prior_dims(self):
+        return [prior_dim(p) for p in self._priors]
+
+    def evaluate_log_priors(self, inputs):
+        inputs = np.asarray(inputs, dtype=np.float64)
+        if inputs.shape[1] != sum(self._get_prior_dims()):
+            raise ValueError("Num prior distributions != num input params")
+        return device_log_priors(self._priors, inputs, self.spec.c)
+
+    def _load(self, inputs):
+        inputs = np.ascontiguousarray(np.asarray(inputs, dtype=np.float64))
+        if inputs.ndim != 2 or inputs.shape[1] != self.spec.d:
+            raise ValueError("Num prior distributions != num input params")
+        st = engine.DeviceState(inputs.shape[0], inputs.shape[0], self.spec.d)
+        st.set_params_host(inputs)
+        return st
+
+    def evaluate_log_likelihood(self, inputs):
+        """(N,1)  (vector_mcmc.py:116-118).  Rows outside the prior support keep 0 as in
+        _eval_log_like_if_prior_nonzero (:205-210)."""
+        st = self._load(inputs)
+        engine.eval_incoming(st, self.spec)
+        f = int(st.flags.item())
+        if f & _lib.FLAG_MODEL_NAN:
+            raise ValueError("nan in model output.")
+        return st.ll.cpu().numpy().reshape(-1, 1)
+
+    def _path_from_posterior(self):
+        """The tempered target reaches VectorMCMC only through the bound method the kernel
+        assigns (vector_mcmc_kernel.py:10): recover the path object from it."""
+        owner = getattr(self.evaluate_log_posterior, "__self__", None)
+        if owner is not None and hasattr(owner, "phi") and hasattr(owner, "_lambda"):
+            if getattr(owner, "proposal", None):
+                raise NotImplementedError("GeometricPath(proposal=...) inside smc_metropolis is not on the "
+                                          "device yet (SURVEY.md section 8f-2)")
+            return engine.make_path(owner.phi, owner.phi, owner._lambda)
+        return engine.make_path(1.0, 1.0, 1.0)       # plain posterior: ll + sum(log priors)
+
+    def smc_metropolis(self, inputs, num_samples, cov):
+        """vector_mcmc.py:46-62 on the device; returns (inputs (N,d), log_like (N,1))."""
+        st = self._load(inputs)
+        path = self._path_from_posterior()
+        engine.eval_incoming(st, self.spec)
+        st.check_flags("smc_metropolis")
+        cov = np.asarray(cov, dtype=np.float64).reshape(self.spec.d, self.spec.d)
+        st.cov.copy_(engine.dev(cov))
+        engine.cholesky(st)
+        engine.mutate(st, self.spec, num_samples, path, self._rng)
+        return st.params_host(), st.ll.cpu().numpy().reshape(-1, 1)
+
+    def metropolis(self, *args, **kwargs):
+        raise NotImplementedError("stand-alone long-chain metropolis() is outside the SMC hot path "
+                                  "(SURVEY.md section 8f-4)")

@@ -33,3 +33,53 @@ def run_oracle_case(name, g=None):
                                           rng, kw["resampler"], init_params=init)
         phis = np.asarray(kw["phi"], float)
     return steps, mll, phis, rng
+
+
+# ---- product-side builders (need the built library; GPU only when something is evaluated) ----
+def make_b200(problem, rng=None, path=None):
+    """B200VectorMCMC + VectorMCMCKernel for an oracle-style problem dict."""
+    from scipy import stats
+    import smcpy_b200 as sb
+    kind, arg = problem["model"]
+    if kind in ("linear", "linear_features"):
+        model = sb.LinearModel(arg)
+    elif kind == "spring_mass":
+        model = sb.SpringMassModel(arg["dt"], arg["n_out"], arg["nsub"], arg["x0"], arg["v0"])
+    elif kind == "identity":
+        model = sb.IdentityModel(arg)
+    else:
+        raise ValueError(kind)
+    priors = []
+    for p in problem["priors"]:
+        if p[0] == "uniform":
+            priors.append(stats.uniform(p[1], p[2]))
+        elif p[0] == "improper_uniform":
+            priors.append(sb.ImproperUniform(p[1], p[2]))
+        elif p[0] == "improper_cov":
+            priors.append(sb.ImproperCov(int(p[1]), dof=5, S=np.eye(int(p[1]))))
+    lk, largs = problem["loglike"]
+    cls = sb.Normal if lk == "normal" else sb.MVNormal
+    mcmc = sb.B200VectorMCMC(model, problem["data"], priors, largs, cls)
+    kernel = sb.VectorMCMCKernel(mcmc, param_order=problem["names"], rng=rng, path=path)
+    return mcmc, kernel
+
+
+def run_b200_case(name, g=None, rng=None):
+    """Runs the product sampler for a configs.py case (replay mode when rng is a numpy
+    Generator seeded like the fixture)."""
+    import smcpy_b200 as sb
+    build, kind, kw, seed = configs.CASES[name]
+    problem = build()
+    rng = np.random.default_rng(seed) if rng is None else rng
+    mcmc, kernel = make_b200(problem, rng=rng)
+    if g is not None and "init_params" in g:
+        init = g["init_params"]
+        kernel.sample_from_prior = lambda n: dict(zip(kernel.param_order, init.T))
+    res = {"standard": sb.standard, "stratified": sb.stratified}[kw["resampler"]]
+    if kind == "adaptive":
+        smc = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+        steps, mll = smc.sample(kw["n"], kw["K"], target_ess=kw["target_ess"], resample_rng=res)
+    else:
+        smc = sb.FixedPhiSampler(kernel, show_progress_bar=False)
+        steps, mll = smc.sample(kw["n"], kw["K"], kw["phi"], kw["ess_threshold"], resample_rng=res)
+    return smc, list(steps), mll, rng

@@ -1,0 +1,526 @@
+"""
+GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every check calls the CUDA path
+through the C ABI (directly or via the host mirror of the reference interface) and compares
+with the oracle on the same seeded inputs and with the committed reference fixtures.
+Tolerances: indices / counts bit-exact; floating point 1e-10 relative (BASELINE.json
+north_star), written at each assertion.
+"""
+
+import ctypes as C
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import smc_oracle as orc
+from tests.golden import configs
+from tests.helpers import golden, make_b200, run_b200_case
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import smcpy_b200
+    return smcpy_b200
+
+
+def _state(sb, n, d):
+    from smcpy_b200 import engine
+    return engine.DeviceState(n, n, d)
+
+
+# ------------------------------------------------------------------ (a) reweight + ESS
+@pytest.mark.parametrize("n", [1, 5, 257, 100003])
+def test_reweight_matches_oracle(sb, n):
+    from smcpy_b200 import engine
+    rng = np.random.default_rng(n)
+    ll = rng.normal(-40, 25, n)
+    lp = np.full(n, -2 * np.log(12.0))
+    lw = rng.normal(-3, 2, n)
+    if n > 10:
+        ll[3] = -np.inf
+        lw[7] = -np.inf
+        lw[9] = -900.0
+    st = _state(sb, n, 2)
+    st.ll.copy_(engine.dev(ll))
+    st.lp.copy_(engine.dev(lp))
+    st.log_w.copy_(engine.dev(lw))
+    ess, tot = engine.reweight(st, engine.make_path(0.35, 0.2, 1.0))
+    un = lw.reshape(-1, 1) + orc.inc_log_weights(ll.reshape(-1, 1), lp.reshape(-1, 1), 0.35, 0.2)
+    o_lw, o_w = orc.normalize_log_weights(un)
+    g_lw, g_w = st.log_w.cpu().numpy(), st.w.cpu().numpy()
+    fin = np.isfinite(o_lw[:, 0])
+    np.testing.assert_array_equal(np.isfinite(g_lw), fin)
+    np.testing.assert_allclose(g_lw[fin], o_lw[fin, 0], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(g_w, o_w[:, 0], rtol=RTOL, atol=1e-300)
+    assert ess == pytest.approx(orc.compute_ess(o_w), rel=RTOL)
+    assert tot == pytest.approx(orc.logsum(un), rel=RTOL)
+
+
+@pytest.mark.parametrize("tag, req, prop", [("plain", 1, False), ("req", [0.3, 0.6], False),
+                                            ("prop", 1, True), ("propreq", 0.4, True)])
+def test_path_arithmetic_bit_exact_vs_reference_fixture(sb, tag, req, prop):
+    """inc_log_weights / logpdf incl. proposal and required-phi forms: the device sums the
+    six column blocks in the reference's order without FMA contraction -> bit-equal."""
+    U = golden("unit_vectors")
+
+    class FakeProposal:
+        def logpdf(self, x):
+            return U["path_lq"]
+    path = sb.GeometricPath(proposal=FakeProposal() if prop else None, required_phi=req)
+    phis = U["path_phis"]
+    with np.errstate(invalid="ignore"):
+        for i in range(1, len(phis)):
+            path.phi = phis[i]
+            inc = path.inc_log_weights(None, U["path_ll"], U["path_lp"])
+            lpdf = path.logpdf(None, U["path_ll"], U["path_lp"])
+            np.testing.assert_array_equal(inc, U["path_%s_inc" % tag][i - 1])
+            np.testing.assert_array_equal(lpdf, U["path_%s_logpdf" % tag][i - 1])
+
+
+def test_particles_container_vs_reference_fixture(sb):
+    U = golden("unit_vectors")
+    prm = {"a": U["p_params"][:, 0], "b": U["p_params"][:, 1], "c": U["p_params"][:, 2]}
+    p = sb.Particles(prm, np.zeros(len(U["p_lw_in"])), U["p_lw_in"])
+    fin = np.isfinite(U["p_log_w"][:, 0])
+    np.testing.assert_array_equal(np.isfinite(p.log_weights[:, 0]), fin)
+    np.testing.assert_allclose(p.log_weights[fin], U["p_log_w"][fin], rtol=RTOL)
+    np.testing.assert_allclose(p.weights, U["p_w"], rtol=RTOL, atol=1e-300)
+    assert p.total_unnorm_log_weight == pytest.approx(float(U["p_total"]), rel=RTOL)
+    assert p.compute_ess() == pytest.approx(float(U["p_ess"]), rel=RTOL)
+    np.testing.assert_allclose(p.compute_covariance(), U["p_cov"], rtol=RTOL, atol=1e-14)
+    np.testing.assert_allclose(p.compute_mean(package=False), U["p_mean"], rtol=RTOL)
+    np.testing.assert_allclose(p.compute_variance(package=False), U["p_var"], rtol=RTOL)
+    np.testing.assert_array_equal(p.params, U["p_params"])
+    # reference KAT tests/unit/test_particles.py:34-53
+    q = sb.Particles({"a": [1] * 10, "b": [2] * 10}, [0.1] * 10, [0.2] * 10)
+    assert q.total_unnorm_log_weight == pytest.approx(2.50258509)
+    np.testing.assert_allclose(q.weights, 0.1, rtol=1e-15)
+    # tests/integration/test_single_param_cov.py:7-16
+    r = sb.Particles({"a": [np.sqrt(2), 2 * np.sqrt(2)]}, [0, 0], np.log([0.5, 0.5]))
+    c = r.compute_covariance()
+    assert c.shape == (1, 1) and c[0, 0] == pytest.approx(0.5)
+
+
+# ------------------------------------------------------------------ (b) bisection
+def test_bisect_phi_vs_reference_fixture(sb):
+    from smcpy_b200 import engine
+    U = golden("unit_vectors")
+    for i, ll in enumerate(U["ad_ll"]):
+        n = ll.shape[0]
+        st = _state(sb, n, 2)
+        st.ll.copy_(engine.dev(ll))
+        st.lp.fill_(-np.log(144.0))
+
+        class Spec:
+            lp_const = -np.log(144.0)
+        for j, phi_old in enumerate((0.0, 1e-4, 0.3)):
+            phi = engine.find_phi(st, Spec, phi_old, 0.8)
+            assert phi == pytest.approx(U["ad_phi"][i, j], rel=RTOL)
+            m = engine.ess_margin(st, Spec, min(1.0, phi_old + 0.01), phi_old, 0.8)
+            assert m == pytest.approx(U["ad_margin"][i, j], rel=1e-9, abs=1e-7)
+
+
+def test_bisect_kat_ess_margin(sb):
+    # tests/unit/test_samplers.py:97-127
+    from smcpy_b200 import engine
+    st = _state(sb, 5, 1)
+    st.ll.copy_(engine.dev(np.arange(5.0)))
+
+    class Spec:
+        lp_const = 1.0
+    for phi_old, target, want in ((0.5, 0.8, -0.5364679374), (0.0, 0.8, -1.8650126)):
+        assert engine.ess_margin(st, Spec, 1.0, phi_old, target) == pytest.approx(want)
+
+
+# ------------------------------------------------------------------ (c) resampling
+def test_resample_indices_bit_exact_vs_reference_fixture(sb):
+    from smcpy_b200 import engine, _lib
+    U = golden("unit_vectors")
+    n = U["rs_w"].shape[0]
+    st = _state(sb, n, 1)
+    st.w.copy_(engine.dev(U["rs_w"]))
+    u = engine.dev(U["rs_u"])
+    idx = engine.torch.empty(u.shape[0], dtype=engine.torch.int64, device=u.device)
+    _lib.call("smcb_cdf_scan", _lib.ptr(st.w), _lib.ptr(st.cdf), n, _lib.SCAN_SEQUENTIAL, _lib.ptr(st.ws),
+              _lib.stream_ptr())
+    _lib.call("smcb_searchsorted", _lib.ptr(st.cdf), n, _lib.ptr(u), u.shape[0], _lib.ptr(idx), _lib.stream_ptr())
+    np.testing.assert_array_equal(idx.cpu().numpy(), U["rs_idx"])
+    np.testing.assert_array_equal(st.cdf.cpu().numpy(), np.cumsum(U["rs_w"]))
+
+
+@pytest.mark.parametrize("u, expected", [
+    ([0.3, 0.3, 0.7], [1, 1, 2]), ([0.3, 0.05, 0.05], [1, 0, 0]), ([0.3, 0.05, 0.7], [1, 0, 2]),
+    ([0.05, 0.05, 0.7], [0, 0, 2]), ([0.3, 0.7, 0.3], [1, 2, 1])])
+def test_resample_kat(sb, u, expected):
+    # tests/unit/test_updater.py:279-325
+    from smcpy_b200 import engine, _lib
+    p = sb.Particles({"a": [1.0, 1, 2], "b": [2.0, 3, 4]}, [-1.0, -2, -3], np.log([0.1, 0.4, 0.5]))
+    st = p.to_state()
+    idx = engine.resample_indices(st, engine.dev(np.array(u)), _lib.SCAN_SEQUENTIAL)
+    np.testing.assert_array_equal(idx.cpu().numpy(), expected)
+    engine.gather_particles(st, idx)
+    np.testing.assert_array_equal(st.params_host(), p.params[expected])
+    np.testing.assert_array_equal(st.ll.cpu().numpy(), p.log_likes[expected, 0])
+    np.testing.assert_array_equal(st.log_w.cpu().numpy(), np.log(np.ones(3) * 1 / 3))
+
+
+@pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 1 << 20, (1 << 22) + 13])
+def test_scans_large(sb, n):
+    """Sequential scan == np.cumsum bit for bit; look-back scan deterministic, monotone and
+    within a few ulps of the exact CDF (size-independent properties at BASELINE sizes)."""
+    from smcpy_b200 import engine, _lib
+    rng = np.random.default_rng(7)
+    w = rng.exponential(1.0, n)
+    w[rng.integers(0, n, max(1, n // 10))] = 0.0
+    w /= w.sum()
+    st = _state(sb, n, 1)
+    st.w.copy_(engine.dev(w))
+    ref = np.cumsum(w)
+    if n <= (1 << 20):
+        _lib.call("smcb_cdf_scan", _lib.ptr(st.w), _lib.ptr(st.cdf), n, _lib.SCAN_SEQUENTIAL, _lib.ptr(st.ws),
+                  _lib.stream_ptr())
+        np.testing.assert_array_equal(st.cdf.cpu().numpy(), ref)
+    outs = []
+    for _ in range(3):
+        st.cdf.zero_()
+        _lib.call("smcb_cdf_scan", _lib.ptr(st.w), _lib.ptr(st.cdf), n, _lib.SCAN_LOOKBACK, _lib.ptr(st.ws),
+                  _lib.stream_ptr())
+        outs.append(st.cdf.cpu().numpy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], outs[2])
+    assert np.all(np.diff(outs[0]) >= 0)
+    exact = np.cumsum(w.astype(np.longdouble)).astype(np.float64)
+    np.testing.assert_allclose(outs[0], exact, rtol=0, atol=4e-16 * 8)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_native_resampling_properties(sb, kind):
+    """Device uniforms + look-back scan + search + gather at 2^20: indices in range,
+    sorted for stratified / systematic, offspring counts match N*w within the scheme's bound,
+    unique-ancestor count equals numpy's."""
+    from smcpy_b200 import engine, _lib
+    n = 1 << 20
+    rng = np.random.default_rng(11)
+    w = rng.exponential(1.0, n)
+    w /= w.sum()
+    st = _state(sb, n, 2)
+    st.w.copy_(engine.dev(w))
+    st.cols.copy_(engine.dev(rng.normal(0, 1, (4, n))))
+    src = st.cols.clone()
+    _lib.call("smcb_resample_uniforms", kind, n, 0, n, 1234, 5, _lib.ptr(st.u), _lib.stream_ptr())
+    u = st.u.cpu().numpy()
+    assert u.min() >= 0 and u.max() < 1
+    if kind:
+        assert np.all(np.floor(u * n) == np.arange(n))       # one uniform per stratum
+    else:
+        assert abs(u.mean() - 0.5) < 5e-3 and abs(u.var() - 1 / 12) < 1e-3
+    idx = engine.resample_indices(st, st.u, _lib.SCAN_LOOKBACK).cpu().numpy()
+    assert idx.min() >= 0 and idx.max() < n
+    np.testing.assert_array_equal(idx, np.minimum(np.searchsorted(st.cdf.cpu().numpy(), u, side="right"), n - 1))
+    counts = np.bincount(idx, minlength=n)
+    if kind:
+        assert np.all(np.diff(idx) >= 0)
+        assert np.max(np.abs(counts - n * w)) < 2.0 + 1e-6
+    assert int(engine.count_unique(st, engine.dev(idx, engine.torch.int64)).item()) == len(np.unique(idx))
+    engine.gather_particles(st, engine.dev(idx, engine.torch.int64))
+    np.testing.assert_array_equal(st.cols.cpu().numpy(), src.cpu().numpy()[:, idx])
+
+
+# ------------------------------------------------------------------ covariance / Cholesky
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 8, 17, 32])
+@pytest.mark.parametrize("n", [7, 1000, 50000])
+def test_weighted_cov_and_cholesky(sb, d, n):
+    from smcpy_b200 import engine
+    rng = np.random.default_rng(d * 1000 + n)
+    A = rng.normal(0, 1, (d, d))
+    x = rng.normal(0, 1, (n, d)) @ A + rng.normal(0, 50, d)
+    w = rng.exponential(1.0, n)
+    w /= w.sum()
+    st = _state(sb, n, d)
+    st.set_params_host(x)
+    st.w.copy_(engine.dev(w))
+    cov = engine.covariance(st).cpu().numpy()
+    ref = orc.weighted_cov(x, w)
+    np.testing.assert_allclose(cov, ref, rtol=RTOL, atol=1e-12 * np.abs(ref).max())
+    np.testing.assert_array_equal(cov, cov.T)
+    if n > d:
+        L = engine.cholesky(st).cpu().numpy()
+        np.testing.assert_allclose(L, np.linalg.cholesky(ref), rtol=1e-8, atol=1e-10)
+
+
+def test_cholesky_non_psd_falls_back_like_reference(sb):
+    # vector_mcmc.py:216-236 (quirk Q9)
+    from smcpy_b200 import engine
+    st = _state(sb, 4, 2)
+    bad = np.array([[1.0, 2.0], [2.0, 1.0]])
+    st.cov.copy_(engine.dev(bad))
+    with pytest.warns(UserWarning, match="not positive semi-definite"):
+        L = engine.cholesky(st).cpu().numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.testing.assert_allclose(L, orc.chol_psd(bad.copy()), rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------ priors / likelihoods
+def test_priors_vs_reference_fixture(sb):
+    from scipy import stats
+    U = golden("unit_vectors")
+    from smcpy_b200.vector_mcmc import device_log_priors
+    x = U["pr_x"].reshape(-1, 1)
+    np.testing.assert_array_equal(device_log_priors([stats.uniform(-6, 12)], x)[:, 0], U["pr_uniform"])
+    np.testing.assert_array_equal(sb.ImproperUniform(-6, 6).logpdf(U["pr_x"]), U["pr_improper"])
+    np.testing.assert_array_equal(sb.ImproperCov(3).logpdf(U["pr_cov_x"])[:, 0], U["pr_cov"])
+    # multi-dim prior slicing (tests/unit/test_vector_mcmc.py:299-326 idea): columns map to priors in order
+    mix = np.column_stack([x[:40, 0], U["pr_cov_x"][:40], x[:40, 0]])
+    got = device_log_priors([stats.uniform(-6, 12), sb.ImproperCov(3), sb.ImproperUniform(-6, 6)], mix)
+    np.testing.assert_array_equal(got[:, 0], U["pr_uniform"][:40])
+    np.testing.assert_array_equal(got[:, 1], U["pr_cov"][:40])
+    np.testing.assert_array_equal(got[:, 2], U["pr_improper"][:40])
+    with pytest.raises(ValueError):
+        device_log_priors([stats.uniform(0, 1)], np.zeros((3, 2)))
+
+
+def test_loglikes_vs_reference_fixture(sb):
+    from scipy import stats
+    U = golden("unit_vectors")
+    wide = [stats.uniform(-100, 200)] * 2
+    mc = sb.B200VectorMCMC(sb.LinearModel(U["nl_x"]), U["nl_data"], wide, 0.7)
+    np.testing.assert_allclose(mc.evaluate_log_likelihood(U["nl_theta"][:, :2])[:, 0], U["nl_fixed"], rtol=RTOL)
+    mc = sb.B200VectorMCMC(sb.LinearModel(U["nl_x"]), U["nl_data"], wide + [stats.uniform(0, 10)], None)
+    np.testing.assert_allclose(mc.evaluate_log_likelihood(U["nl_theta"])[:, 0], U["nl_unknown"], rtol=RTOL)
+    X = np.arange(3.0)
+    mc = sb.B200VectorMCMC(sb.LinearModel(X), U["mv_data"], wide + [sb.ImproperCov(3)], [None] * 6, sb.MVNormal)
+    np.testing.assert_allclose(mc.evaluate_log_likelihood(U["mv_theta"])[:, 0], U["mv_all"], rtol=RTOL)
+    args = [0.5, None, 0.005, None, 0.04, 1.0]
+    mc = sb.B200VectorMCMC(sb.LinearModel(X), U["mv_data"], wide + [stats.uniform(-1, 2)] * 2, args, sb.MVNormal)
+    np.testing.assert_allclose(mc.evaluate_log_likelihood(U["mv_theta_mixed"])[:, 0], U["mv_mixed"], rtol=RTOL)
+    # reference KAT tests/unit/test_likelihoods.py:107-119: -4 pi per snapshot
+    mc = sb.B200VectorMCMC(sb.LinearModel(np.array([0.0])), np.full((5, 1), 3.0), wide, [1 / (2 * np.pi)], sb.MVNormal)
+    np.testing.assert_allclose(mc.evaluate_log_likelihood(np.array([[0.0, 1.0]] * 4)), -4 * np.pi * 5, rtol=1e-14)
+
+
+def test_error_behaviour(sb):
+    from scipy import stats
+    x = np.linspace(0, 1, 5)
+    mc = sb.B200VectorMCMC(sb.LinearModel(x), np.zeros(5), [stats.uniform(0, 1)] * 2, 1.0)
+    k = sb.VectorMCMCKernel(mc, ["a", "b"], rng=np.random.default_rng(0))
+    with pytest.raises(ValueError, match="out of bounds"):        # vector_mcmc.py:199-203
+        mc.smc_metropolis(np.array([[0.5, 0.5], [2.0, 0.5]]), 1, np.eye(2))
+    with pytest.raises(ValueError, match="nan in model output"):  # log_likelihoods.py:14-15
+        mc2 = sb.B200VectorMCMC(sb.LinearModel(np.array([np.nan, 1, 2, 3, 4])), np.zeros(5),
+                                [stats.uniform(0, 1)] * 2, 1.0)
+        mc2.evaluate_log_likelihood(np.array([[0.5, 0.5]]))
+    with pytest.raises(ValueError):                               # vector_mcmc.py:101-102
+        mc.evaluate_log_priors(np.zeros((2, 3)))
+    with pytest.raises(ValueError):                               # paths.py:20-23
+        k.path.phi = 0.0
+
+
+# ------------------------------------------------------------------ (d) Metropolis, replay
+@pytest.mark.parametrize("name", list(configs.CASES))
+def test_smc_metropolis_replay_vs_oracle(sb, name):
+    """B200VectorMCMC.smc_metropolis (drop-in boundary) against the oracle's restatement of
+    VectorMCMC.smc_metropolis on identical inputs and identical injected normals/uniforms."""
+    build, kind, kw, seed = configs.CASES[name]
+    problem = build()
+    g = golden(name)
+    n, K = 300, 6
+    theta = g["params_last"][:n] if g["params_last"].shape[0] >= n else g["params_last"]
+    n = theta.shape[0]
+    cov = orc.weighted_cov(theta, np.full(n, 1.0 / n)) * 0.5
+    phi = 0.37
+    accepts = []
+    o_rng = np.random.default_rng(99)
+    o_theta, o_ll = orc.smc_metropolis(problem, theta, K, cov, phi, o_rng, trace=accepts)
+    mc, kernel = make_b200(problem, rng=np.random.default_rng(99))
+    kernel.path.phi = phi
+    g_theta, g_ll = mc.smc_metropolis(theta, K, cov)
+    assert g_theta.shape == o_theta.shape and g_ll.shape == (n, 1)
+    np.testing.assert_allclose(g_theta, o_theta, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(g_ll, o_ll, rtol=RTOL)
+    assert 0 < sum(accepts) < n * K
+    assert kernel.rng.uniform() == o_rng.uniform()          # same tape position afterwards
+
+
+@pytest.mark.parametrize("name", list(configs.CASES))
+def test_full_sampler_replay_vs_reference_fixture(sb, name):
+    """Whole AdaptiveSampler / FixedPhiSampler runs in replay mode against the unmodified
+    reference's recorded run: resampled indices bit-exact; phi sequence, ESS, log-weights,
+    marginal log-likelihood, covariances and particles within 1e-10 relative."""
+    g = golden(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        smc, steps, mll, rng = run_b200_case(name, g)
+    np.testing.assert_allclose(smc.phi_sequence, g["phi"], rtol=RTOL)
+    np.testing.assert_allclose(mll, g["mll"], rtol=RTOL, atol=1e-10)
+    assert len(steps) == len(g["phi"])
+    np.testing.assert_allclose([s.attrs["mutation_ratio"] for s in steps], g["mutation_ratio"])
+    np.testing.assert_allclose([s.total_unnorm_log_weight for s in steps], g["total_unnorm_log_weight"],
+                               rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(steps[1].params, g["params_1"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(steps[1].log_likes, g["log_likes_1"], rtol=RTOL)
+    np.testing.assert_allclose(steps[1].log_weights, g["log_weights_1"], rtol=RTOL)
+    np.testing.assert_allclose(steps[-1].params, g["params_last"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(steps[-1].log_likes, g["log_likes_last"], rtol=RTOL)
+    np.testing.assert_allclose(steps[-1].log_weights, g["log_weights_last"], rtol=RTOL)
+    np.testing.assert_allclose(np.array([s.compute_mean(package=False) for s in steps]), g["mean"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(rng.uniform(0, 1, 4), g["rng_check"])       # tape exactly exhausted
+    assert steps[0].attrs["phi"] == 0 and steps[0].attrs["mutation_ratio"] == 0
+    assert steps[-1].param_names == tuple(configs.CASES[name][0]()["names"])
+
+
+def test_sampler_internals_replay_vs_reference_fixture(sb):
+    """Per-step ESS, resample decision, ancestor indices and covariance for C1 and the
+    conditional-resampling fixed-phi case."""
+    import smcpy_b200 as sbm
+    from smcpy_b200 import engine
+    for name in ("c1_adaptive", "c2_fixed_unknown_std"):
+        g = golden(name)
+        build, kind, kw, seed = configs.CASES[name]
+        mcmc, kernel = make_b200(build(), rng=np.random.default_rng(seed))
+        res = {"standard": sbm.standard, "stratified": sbm.stratified}[kw["resampler"]]
+        if kind == "adaptive":
+            smc = sbm.AdaptiveSampler(kernel, show_progress_bar=False)
+        else:
+            smc = sbm.FixedPhiSampler(kernel, show_progress_bar=False)
+        rec = {"ess": [], "res": [], "idx": [], "cov": []}
+        orig_update = sbm.updater.Updater.update_state
+        orig_cov = engine.covariance
+
+        def update_state(self, st):
+            out = orig_update(self, st)
+            rec["ess"].append(self.ess)
+            rec["res"].append(self.resampled)
+            rec["idx"].append(None if self.last_indices is None else self.last_indices.cpu().numpy().copy())
+            return out
+
+        def cov(st):
+            c = orig_cov(st)
+            rec["cov"].append(c.cpu().numpy().copy())
+            return c
+        sbm.updater.Updater.update_state = update_state
+        engine.covariance = cov
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                if kind == "adaptive":
+                    smc.sample(kw["n"], kw["K"], target_ess=kw["target_ess"], resample_rng=res)
+                else:
+                    smc.sample(kw["n"], kw["K"], kw["phi"], kw["ess_threshold"], resample_rng=res)
+        finally:
+            sbm.updater.Updater.update_state = orig_update
+            engine.covariance = orig_cov
+        np.testing.assert_allclose(rec["ess"], g["ess"], rtol=RTOL)
+        np.testing.assert_array_equal(rec["res"], g["resampled"])
+        first = next(i for i, r in enumerate(rec["res"]) if r)
+        np.testing.assert_array_equal(rec["idx"][first], g["idx_1"] if first == 0 else rec["idx"][first])
+        last = max(i for i, r in enumerate(rec["res"]) if r)
+        np.testing.assert_array_equal(rec["idx"][last], g["idx_last"])
+        np.testing.assert_allclose(np.array(rec["cov"]), g["cov"], rtol=1e-9, atol=1e-13)
+
+
+# ------------------------------------------------------------------ native RNG: statistics
+def test_native_rng_posterior_matches_analytic_c1(sb):
+    """SURVEY.md appendix B anchors for C1 (data seed 0): posterior mean (2.0363965, 3.4859536),
+    std (0.0857408, 0.1379886), log-evidence -77.357884; reference seed-to-seed sd of mll 0.10."""
+    problem = configs.linear_problem(100)
+    mlls, means, stds = [], [], []
+    for seed in range(8):
+        mcmc, kernel = make_b200(problem, rng=seed + 1)
+        smc = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            steps, mll = smc.sample(4000, 10, target_ess=0.8)
+        mlls.append(mll[-1])
+        means.append(steps[-1].compute_mean(package=False))
+        stds.append(steps[-1].compute_std_dev(package=False))
+        assert 10 <= len(steps) <= 25 and smc.phi_sequence[-1] == 1.0
+    assert np.mean(mlls) == pytest.approx(-77.357884, abs=0.08)
+    np.testing.assert_allclose(np.mean(means, axis=0), [2.0363965, 3.4859536], atol=0.01)
+    np.testing.assert_allclose(np.mean(stds, axis=0), [0.0857408, 0.1379886], rtol=0.08)
+
+
+def test_native_rng_gaussian_target_c5(sb):
+    """C5: identity model, sigma=1, 32 x uniform(-10,20): posterior N(y, I), log-evidence
+    -32 log 20 = -95.863."""
+    problem = configs.gauss_problem(32)
+    mcmc, kernel = make_b200(problem, rng=5)
+    smc = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steps, mll = smc.sample(1 << 16, 10, target_ess=0.8, resample_rng=sb.stratified)
+    assert mll[-1] == pytest.approx(-32 * np.log(20.0), abs=0.5)
+    np.testing.assert_allclose(steps[-1].compute_mean(package=False), problem["data"], atol=0.06)
+    np.testing.assert_allclose(steps[-1].compute_std_dev(package=False), 1.0, atol=0.08)
+
+
+def test_native_rng_is_reproducible_and_seed_dependent(sb):
+    problem = configs.linear_problem(50)
+    out = []
+    for seed in (3, 3, 4):
+        mcmc, kernel = make_b200(problem, rng=seed)
+        smc = sb.FixedPhiSampler(kernel, show_progress_bar=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            steps, mll = smc.sample(5000, 3, np.linspace(0, 1, 8), 0.8, resample_rng=sb.systematic)
+        out.append((mll.copy(), steps[-1].params.copy()))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    assert not np.array_equal(out[0][1], out[2][1])
+
+
+def test_philox_normals_moments(sb):
+    """Device proposal normals: mean/var/kurtosis and independence across coordinates, via the
+    propose kernel with identity Cholesky."""
+    from scipy import stats
+    from smcpy_b200 import engine, _lib
+    n, d = 1 << 18, 8
+    problem = configs.gauss_problem(d)
+    problem["priors"] = [("uniform", -1e6, 2e6)] * d
+    mcmc, kernel = make_b200(problem, rng=1)
+    st = _state(sb, n, d)
+    st.cols.zero_()
+    st.chol.copy_(engine.dev(np.eye(d)))
+    new = engine.torch.empty((d + 1, n), dtype=engine.torch.float64, device=st.cols.device)
+    r = _lib.Rng()
+    r.mode, r.seed, r.stream = 0, 42, 7
+    _lib.call("smcb_mh_propose", C.byref(mcmc.spec.c), _lib.ptr(st.cols), n, n, n, _lib.ptr(st.chol),
+              _lib.ptr(st.accept_counts), 0, C.byref(r), _lib.ptr(new), _lib.ptr(new[d]), _lib.stream_ptr())
+    z = new[:d].cpu().numpy()
+    assert np.all(np.abs(z.mean(axis=1)) < 0.01)
+    assert np.all(np.abs(z.var(axis=1) - 1) < 0.02)
+    assert np.all(np.abs(stats.kurtosis(z, axis=1)) < 0.08)
+    c = np.corrcoef(z)
+    assert np.max(np.abs(c - np.eye(d))) < 0.01
+    assert stats.kstest(z[3], "norm").pvalue > 1e-4
+
+
+def test_torch_callable_model_route(sb):
+    """User model as a torch callable on device tensors (un-fused route) agrees with the
+    fused built-in linear model under replayed draws."""
+    import torch
+    from scipy import stats
+    problem = configs.linear_problem(40)
+    x_dev = torch.as_tensor(problem["model"][1], device="cuda")
+
+    def model(theta):
+        return theta[:, 0:1] * x_dev[None, :] + theta[:, 1:2]
+    priors = [stats.uniform(-6, 12)] * 2
+    theta = np.random.default_rng(0).uniform(1, 4, (500, 2))
+    cov = np.array([[0.02, -0.01], [-0.01, 0.03]])
+    outs = []
+    for m in (model, sb.LinearModel(problem["model"][1])):
+        mc = sb.B200VectorMCMC(m, problem["data"], priors, 0.5)
+        k = sb.VectorMCMCKernel(mc, ["a", "b"], rng=np.random.default_rng(5))
+        k.path.phi = 0.6
+        outs.append(mc.smc_metropolis(theta, 5, cov))
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=RTOL)
+    o_theta, o_ll = orc.smc_metropolis(problem, theta, 5, cov, 0.6, np.random.default_rng(5))
+    np.testing.assert_allclose(outs[0][0], o_theta, rtol=RTOL, atol=1e-12)
