@@ -95,8 +95,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const doubl
                                                                      unsigned long long* state,
                                                                      unsigned int* counter) {
     __shared__ double sh_warp[kScanThreads / 32];
+    __shared__ double sh_wmax[kScanThreads / 32];
     __shared__ unsigned int sh_tile;
-    __shared__ double sh_prefix;
+    __shared__ double sh_prefix, sh_prefix_incl;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     // tiles are handed out in launch order so every predecessor is already resident
@@ -130,6 +131,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const doubl
         if (lane >= o) x += y;
     }
     if (lane == 31) sh_warp[wid] = x;
+    double xprev = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) xprev = 0.0;
     __syncthreads();
     double warp_off = 0.0, tile_agg = 0.0;
 #pragma unroll
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const doubl
         if (k < wid) warp_off += s;
         tile_agg += s;
     }
-    const double thread_excl = warp_off + (x - tsum);
+    const double thread_excl = warp_off + xprev;
 
     // cross-tile carry by decoupled look-back on fixed-point aggregates
     if (wid == 0) {
@@ -165,18 +168,41 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const doubl
             }
             if (lane == 0) st_state(state + tile, ((excl + agg_fx) << 2) | kFlagPrefix);
         }
-        if (lane == 0) sh_prefix = (double)excl * kFixInv;
+        if (lane == 0) {
+            sh_prefix = (double)excl * kFixInv;
+            sh_prefix_incl = (double)(excl + agg_fx) * kFixInv;
+        }
     }
     __syncthreads();
+    // candidate values, clamped into [tile prefix, next tile prefix] so tiles are ordered
     const double off = sh_prefix + thread_excl;
+    const double hi = sh_prefix_incl;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) v[j] = fmin(off + v[j], hi);
+    // exact (associative) running maximum across threads makes the CDF monotone by construction
+    double m = v[kScanItems - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, m, o);
+        if (lane >= o) m = fmax(m, y);
+    }
+    if (lane == 31) sh_wmax[wid] = m;
+    double lower = __shfl_up_sync(0xffffffffu, m, 1);
+    if (lane == 0) lower = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kScanThreads / 32; ++k)
+        if (k < wid) lower = fmax(lower, sh_wmax[k]);
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) v[j] = fmax(v[j], lower);
     if (base + kScanItems <= n) {
         double2* q = reinterpret_cast<double2*>(cdf + base);
 #pragma unroll
-        for (int j = 0; j < kScanItems / 2; ++j) q[j] = make_double2(off + v[2 * j], off + v[2 * j + 1]);
+        for (int j = 0; j < kScanItems / 2; ++j) q[j] = make_double2(v[2 * j], v[2 * j + 1]);
     } else {
 #pragma unroll
         for (int j = 0; j < kScanItems; ++j)
-            if (base + j < n) cdf[base + j] = off + v[j];
+            if (base + j < n) cdf[base + j] = v[j];
     }
 }
 

@@ -177,7 +177,8 @@ def test_scans_large(sb, n):
     from smcpy_b200 import engine, _lib
     rng = np.random.default_rng(7)
     w = rng.exponential(1.0, n)
-    w[rng.integers(0, n, max(1, n // 10))] = 0.0
+    if n > 10:
+        w[rng.integers(0, n, n // 10)] = 0.0
     w /= w.sum()
     st = _state(sb, n, 1)
     st.w.copy_(engine.dev(w))
@@ -419,9 +420,12 @@ def test_sampler_internals_replay_vs_reference_fixture(sb):
         np.testing.assert_allclose(rec["ess"], g["ess"], rtol=RTOL)
         np.testing.assert_array_equal(rec["res"], g["resampled"])
         first = next(i for i, r in enumerate(rec["res"]) if r)
-        np.testing.assert_array_equal(rec["idx"][first], g["idx_1"] if first == 0 else rec["idx"][first])
-        last = max(i for i, r in enumerate(rec["res"]) if r)
-        np.testing.assert_array_equal(rec["idx"][last], g["idx_last"])
+        if first == 0:
+            np.testing.assert_array_equal(rec["idx"][0], g["idx_1"])
+        if rec["res"][-1]:                                   # fixture keeps the last step's entry
+            np.testing.assert_array_equal(rec["idx"][-1], g["idx_last"])
+        else:
+            assert g["idx_last"].shape == (0,)
         np.testing.assert_allclose(np.array(rec["cov"]), g["cov"], rtol=1e-9, atol=1e-13)
 
 
