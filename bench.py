@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""
+bench.py -- particle-MCMC steps/s of the SMC hot path on B200 (BASELINE.json metric).
+
+Workload (config C2, BASELINE.json configs[1]): linear model y = a x + b, FixedPhiSampler,
+2^20 particles PER GPU (weak scaling), 20 Metropolis steps per SMC step, 1000 data points,
+phi = linspace(0, 1, 20), ess_threshold 0.8, two uniform(-6, 12) priors, sigma = 0.5,
+native Philox RNG, `standard` (multinomial) resampling (the reference's default).
+
+One bench "step" = one complete sample() pass = 19 SMC steps x 20 Metropolis steps x N particles.
+
+  value : device-resident run (data already in HBM, particles drawn on the device), CUDA events
+  e2e   : the same through the public API with host numpy buffers: H2D of data inside the timed
+          region, D2H of the final particles + marginal log-likelihoods
+  roofline / fp64 : dominant kernel (fused Metropolis step), timed live with CUDA events
+  cpu_baseline    : the numpy oracle port of the reference on a bounded sample (rank 0, N=1)
+  --impl reference: the oracle port timed on the host cores (the reference is pure Python and is
+                    not present on the GPU box; oracle/ is pinned to it by tests/golden)
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1 << 20
+K_MCMC = 20
+M_DATA = 1000
+PHI = np.linspace(0, 1, 20)
+ESS_THRESHOLD = 0.8
+METRIC = "particle-MCMC steps/sec"
+UNIT = "particle-steps/s"
+
+
+def c2_problem():
+    from tests.golden import configs
+    return configs.linear_problem(M_DATA, sigma=0.5, data_seed=0)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                pw.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+_POOL_PROBLEM = None
+
+
+def _pool_ll(theta):
+    from oracle import smc_oracle as orc
+    return orc.log_likelihood(_POOL_PROBLEM, theta)
+
+
+def oracle_run(n, cores, seed=1):
+    """One FixedPhi C2 pass of the oracle (numpy restatement of the reference) at n particles.
+    cores > 1: the model/likelihood evaluation is split over a fork pool, the way the
+    reference's ParallelVectorMCMC distributes it over MPI ranks (parallel_vector_mcmc.py:36-47)."""
+    global _POOL_PROBLEM
+    from oracle import smc_oracle as orc
+    problem = c2_problem()
+    pool = None
+    orig = orc.log_likelihood
+    if cores > 1:
+        import multiprocessing as mp
+        _POOL_PROBLEM = problem
+        pool = mp.get_context("fork").Pool(cores)
+
+        def par_ll(prob, theta):
+            if theta.shape[0] < 4 * cores:
+                return orig(prob, theta)
+            return np.vstack(pool.map(_pool_ll, np.array_split(theta, cores)))
+        orc.log_likelihood = par_ll
+    try:
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            steps, mll = orc.fixed_phi_sample(problem, n, K_MCMC, PHI, ESS_THRESHOLD,
+                                              np.random.default_rng(seed), "standard")
+        dt = time.perf_counter() - t0
+    finally:
+        orc.log_likelihood = orig
+        if pool is not None:
+            pool.close()
+            pool.join()
+    return dt, n * K_MCMC * (len(PHI) - 1), float(mll[-1])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    use = min(cores, 32)
+    n = 4096
+    for _ in range(args.warmup):
+        oracle_run(512, use)
+    times, units = [], 0
+    for _ in range(args.steps):
+        dt, u, mll = oracle_run(n, use)
+        times.append(dt)
+        units = u
+    ms = 1e3 * float(np.mean(times))
+    value = units / (ms * 1e-3)
+    sample = "C2 workload at N=%d particles per step (same model/data/phi/K), numpy oracle port, " \
+             "likelihood evaluation over a %d-process fork pool" % (n, use)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C2 linear FixedPhiSampler (bounded sample N=%d)" % n, "num_mcmc_samples": K_MCMC,
+                      "data_points": M_DATA, "smc_steps": len(PHI) - 1},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": use, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def build_sampler(sb, problem_host, n_global, seed, on_device_spec=None):
+    """Public-API construction from HOST buffers (model grid, data, priors)."""
+    from scipy import stats
+    model = sb.LinearModel(problem_host["model"][1])
+    priors = [stats.uniform(-6.0, 12.0), stats.uniform(-6.0, 12.0)]
+    mcmc = sb.B200VectorMCMC(model, problem_host["data"], priors, 0.5)
+    if on_device_spec is not None:
+        mcmc._spec = on_device_spec                      # data already resident in HBM
+    kernel = sb.VectorMCMCKernel(mcmc, param_order=("a", "b"), rng=seed)
+    return sb.FixedPhiSampler(kernel, show_progress_bar=False), mcmc
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import smcpy_b200 as sb
+    from smcpy_b200 import _lib, engine
+
+    n_global = N_PER_GPU * world
+    problem = c2_problem()
+    units = n_global * K_MCMC * (len(PHI) - 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_pass(seed, spec=None, host_out=False):
+        smc, mcmc = build_sampler(sb, problem, n_global, seed, spec)
+        smc._result = sb.InMemoryStorage(retain=1)          # keep only the last step on the device
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            steps, mll = smc.sample(n_global, K_MCMC, PHI, ESS_THRESHOLD, resample_rng=sb.standard)
+        last = steps[-1]
+        if host_out:
+            return last.params, last.log_likes, last.log_weights, mll, mcmc
+        return last, mll, mcmc
+
+    # resident spec: data + grid uploaded once, outside the timed region
+    _, _, mc0 = one_pass(1)
+    spec = mc0.spec
+    for i in range(args.warmup):
+        flush.zero_()
+        one_pass(100 + i, spec)
+
+    # ---- timed: device-resident ------------------------------------------------------------
+    sampler_clk = ClockSampler(local)
+    barrier()
+    sampler_clk.start()
+    _lib.launch_count = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    mlls = []
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        last, mll, _ = one_pass(200 + i, spec)
+        ev[i][1].record()
+        mlls.append(float(mll[-1]))
+    barrier()
+    clocks = sampler_clk.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = _lib.launch_count
+    # separate, untimed pass with per-kernel CUDA events (creating ~900 events inside the timed
+    # region would perturb it): kernel durations for the roofline and their share of a step
+    engine.PROFILE = {}
+    pv = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    flush.zero_()
+    pv[0].record()
+    one_pass(250, spec)
+    pv[1].record()
+    torch.cuda.synchronize()
+    prof = {k: [a.elapsed_time(b) for a, b in v] for k, v in engine.PROFILE.items()}
+    prof_total_ms = pv[0].elapsed_time(pv[1])
+    engine.PROFILE = None
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = units / (ms_per_step * 1e-3)
+
+    # ---- timed: end to end through the public API with host buffers ---------------------------
+    for i in range(2):
+        one_pass(300 + i, None, host_out=True)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    e2e_ev[0].record()
+    d2h = 0
+    for i in range(args.steps):
+        flush.zero_()
+        p, ll, lw, mll, _ = one_pass(400 + i, None, host_out=True)
+        d2h = p.nbytes + ll.nbytes + lw.nbytes + mll.nbytes
+    e2e_ev[1].record()
+    barrier()
+    e2e_ms = e2e_ev[0].elapsed_time(e2e_ev[1])
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = units / (float(te.item()) / args.steps * 1e-3)
+    h2d = problem["data"].nbytes + problem["model"][1].nbytes
+    # per SMC step the host also reads the step's scalars (ESS, total weight, flags, counts)
+    d2h += (len(PHI) - 1) * (6 * 8 + 4 + 8 + 8 + 4 * 2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused Metropolis step) ------------------------------
+    peaks, peak_kind = measured_peaks()
+    mh = np.array(prof.get("mh_step", [0.0]))
+    mh_ms = float(mh.mean())
+    d = 2
+    alg_bytes = (16 * d + 32) * N_PER_GPU                       # 16d+32 B per particle-step
+    ach = alg_bytes / (mh_ms * 1e-3) / 1e9
+    flops_per_unit = 5.0 * M_DATA + 4 * d * d                   # fma + sub + fma per data point
+    fp64_ach = flops_per_unit * N_PER_GPU / (mh_ms * 1e-3) / 1e12
+    # FP64 FMA probe (no FP64 peak in MEASURED_PEAKS.json)
+    probe = torch.empty(148 * 8 * 256, dtype=torch.float64, device="cuda")
+    iters = 1 << 15
+    pe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    for _ in range(2):
+        _lib.call("smcb_fp64_probe", _lib.ptr(probe), 148 * 8, iters, _lib.stream_ptr())
+    pe[0].record()
+    _lib.call("smcb_fp64_probe", _lib.ptr(probe), 148 * 8, iters, _lib.stream_ptr())
+    pe[1].record()
+    torch.cuda.synchronize()
+    fp64_peak = 16.0 * iters * 148 * 8 * 256 / (pe[0].elapsed_time(pe[1]) * 1e-3) / 1e12
+    share = {k: float(np.sum(v)) / (ms_per_step) for k, v in prof.items()}   # kernel ms per pass / pass ms
+    roofline = {"kernel": "mh_kernel<linear,normal> (fused Metropolis step, M=1000 reduce in smem)",
+                "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "traffic": None, "avg_launch_ms": mh_ms, "launches_timed": int(mh.size),
+                "share_of_step": share.get("mh_step"),
+                "note": "C2's Metropolis kernel is FP64-pipe bound (SURVEY.md 8d: ~78 flop/B), see fp64",
+                "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
+                         "peak_source": "smcb_fp64_probe FMA microbenchmark, this run",
+                         "flops_per_particle_step": flops_per_unit}}
+    other = {"share_of_step": share}
+    if "reweight" in prof:                      # single-GPU entry points (fused calls) only
+        rw = float(np.mean(prof["reweight"]))
+        other["reweight"] = {"avg_ms": rw, "gbps": 48.0 * N_PER_GPU / rw / 1e6,
+                             "frac_hbm": 48.0 * N_PER_GPU / rw / 1e6 / peaks["hbm_gbs"], "alg_bytes_per_particle": 48}
+    if "cov" in prof:
+        other["cov"] = {"avg_ms": float(np.mean(prof["cov"])), "alg_bytes_per_particle": 16 * d}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C2: linear model FixedPhiSampler, 2^20 particles per GPU, 20 MCMC steps, "
+                                  "1000 data points, phi=linspace(0,1,20), ess_threshold=0.8",
+                      "particles_per_gpu": N_PER_GPU, "num_mcmc_samples": K_MCMC, "data_points": M_DATA,
+                      "smc_steps": len(PHI) - 1, "rng": "philox (native)", "resampler": "standard",
+                      "parallelism": "particles sharded x%d" % world,
+                      "l2": "flushed between timed steps (256 MiB memset)"},
+           "clocks": clocks,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+           "gpu_launches": int(launches),
+           "roofline": roofline, "kernels": other,
+           "mll_last": mlls[-1]}
+    if world == 1 and not args.no_cpu:
+        n_cpu = 8192
+        dt, u, mll = oracle_run(n_cpu, 1)
+        out["cpu_baseline"] = {"value": u / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": "C2 workload at N=%d particles (same model/data/phi/K), one pass of the "
+                                         "single-process numpy oracle port, %.1f s" % (n_cpu, dt), "mll_last": mll}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

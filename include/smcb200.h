@@ -117,6 +117,10 @@ int smcb_version(void);
 const char* smcb_last_error(void);
 size_t smcb_workspace_bytes(int64_t n, int32_t d);
 
+/* measurement aid: `blocks` x 256 threads each run 8 independent chains of `iters` FP64 FMAs
+ * (16 * iters flops per thread); out holds blocks*256 doubles. */
+int smcb_fp64_probe(double* out, int32_t blocks, int32_t iters, void* stream);
+
 /* ---- layout / plumbing ----------------------------------------------------------- */
 /* (N,d) row-major <-> SoA (d, stride); kernel_base.py:53-66 dict<->array conversions */
 int smcb_aos_to_soa(const double* aos, double* soa, int64_t n, int32_t d, int64_t stride, void* stream);
@@ -176,6 +180,10 @@ int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mode, void* w
  * clamped to n_cdf-1 (documented divergence from the reference's IndexError, quirk Q4) */
 int smcb_searchsorted(const double* cdf, int64_t n_cdf, const double* u, int64_t n_u,
                       int64_t* idx_out, void* stream);
+/* same against a shard of a global CDF: idx_k = #{j : *offset + cdf_j <= u_k} (multi-GPU:
+ * offset = sum of the weight totals of the lower ranks, device scalar) */
+int smcb_searchsorted_offset(const double* cdf, int64_t n_cdf, const double* offset, const double* u,
+                             int64_t n_u, int64_t* idx_out, void* stream);
 /* dst[c][k] = src[c][idx[k]] for n_cols SoA columns (updater.py:140-143) */
 int smcb_gather(const double* src, int64_t src_stride, double* dst, int64_t dst_stride,
                 const int64_t* idx, int64_t n_out, int32_t n_cols, void* stream);

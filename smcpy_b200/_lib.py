@@ -60,6 +60,7 @@ _PP = C.POINTER
 SIGNATURES = {
     "smcb_aos_to_soa": [_P, _P, _I64, _I32, _I64, _P],
     "smcb_soa_to_aos": [_P, _P, _I64, _I32, _I64, _P],
+    "smcb_fp64_probe": [_P, _I32, _I32, _P],
     "smcb_fill_f64": [_P, _I64, _D, _P],
     "smcb_reweight": [_I64, _P, _P, _P, _P, _I64, _PP(Path), _P, _P, _P, _P, _P],
     "smcb_path_eval": [_I64, _P, _P, _P, _PP(Path), _I32, _P, _P],
@@ -74,6 +75,7 @@ SIGNATURES = {
     "smcb_resample_uniforms": [_I32, _I64, _I64, _I64, _U64, _U64, _P, _P],
     "smcb_cdf_scan": [_P, _P, _I64, _I32, _P, _P],
     "smcb_searchsorted": [_P, _I64, _P, _I64, _P, _P],
+    "smcb_searchsorted_offset": [_P, _I64, _P, _P, _I64, _P, _P],
     "smcb_gather": [_P, _I64, _P, _I64, _P, _I64, _I32, _P],
     "smcb_count_unique": [_P, _I64, _I64, _P, _P, _P],
     "smcb_weighted_cov": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P, _P],
@@ -106,7 +108,11 @@ def _load():
             "CPU fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, argtypes in SIGNATURES.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError("libsmcb200.so is stale (missing %s): rebuild with "
+                              "`python -m smcpy_b200.build`" % name) from e
         fn.argtypes = argtypes
         fn.restype = C.c_int
     lib.smcb_version.restype = C.c_int
@@ -116,7 +122,18 @@ def _load():
     return lib
 
 
-lib = _load()
+class _LazyLib:
+    """Loads libsmcb200.so on first use, so that importing the package (e.g. to run
+    `python -m smcpy_b200.build`) does not need a built library."""
+    _handle = None
+
+    def __getattr__(self, name):
+        if _LazyLib._handle is None:
+            _LazyLib._handle = _load()
+        return getattr(_LazyLib._handle, name)
+
+
+lib = _LazyLib()
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
 LAUNCHES = {"smcb_reweight": 3, "smcb_cdf_scan": 2, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
             "smcb_weighted_sums1": 2, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0}

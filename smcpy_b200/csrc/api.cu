@@ -23,6 +23,28 @@ int check_launch(const char* what) {
 
 }  // namespace smcb
 
+// FP64 FMA throughput probe: 8 independent FMA chains per thread (measurement aid for the
+// FP64-pipe-bound kernels; MEASURED_PEAKS.json has no FP64 figure).
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters) {
+    const double t = 1e-9 * (double)(threadIdx.x + 1);
+    double a0 = t, a1 = 2 * t, a2 = 3 * t, a3 = 4 * t, a4 = 5 * t, a5 = 6 * t, a6 = 7 * t, a7 = 8 * t;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int smcb_fp64_probe(double* out, int32_t blocks, int32_t iters, void* stream) {
+    if (!out || blocks < 1 || iters < 1) {
+        smcb::set_error("smcb_fp64_probe: bad argument");
+        return SMCB_ERR_ARG;
+    }
+    fp64_probe_kernel<<<blocks, 256, 0, smcb::as_stream(stream)>>>(out, iters);
+    return smcb::check_launch("fp64_probe_kernel");
+}
+
 extern "C" int smcb_version(void) { return SMCB_VERSION; }
 
 extern "C" const char* smcb_last_error(void) { return smcb::g_err; }

@@ -13,6 +13,8 @@
 //
 // The same kernels with kInit = true evaluate log-priors and log-likelihood of incoming
 // particles (vector_mcmc.py:162-166, initializer.py:66-73).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace smcb {
@@ -140,40 +142,50 @@ __device__ __forceinline__ double normal_ll(double ssq, double sigma, int m) {
     return term1 + term2;
 }
 
-template <int DMAX>
-__device__ __forceinline__ double ll_linear_normal(const MhArgs& a, const double (&th)[DMAX], bool run,
-                                                   double2* sxy) {
+// Linear model + Normal likelihood for PPT particles per thread: every staged data point
+// (one broadcast LDS.128) feeds 3*PPT FP64 instructions, which keeps the shared-memory pipe
+// off the critical path (profiles/r01_mh_c2_ncu.md).
+template <int DMAX, int PPT>
+__device__ __forceinline__ void ll_linear_normal(const MhArgs& a, const double (&th)[PPT][DMAX], bool run_any,
+                                                 double2* sxy, double (&ll)[PPT]) {
     const int m = a.prob.n_data;
-    const double aa = th[0], bb = th[1];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    double s0[PPT], s1[PPT];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) s0[p] = s1[p] = 0.0;
     for (int base = 0; base < m; base += kChunk) {
         const int cnt = (m - base < kChunk) ? (m - base) : kChunk;
         __syncthreads();
-        for (int j = threadIdx.x; j < cnt; j += kMhThreads)
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x)
             sxy[j] = make_double2(a.prob.xgrid[base + j], a.prob.data[base + j]);
         __syncthreads();
-        if (run) {
+        if (run_any) {
             int j = 0;
-            for (; j + 4 <= cnt; j += 4) {
-                const double2 p0 = sxy[j], p1 = sxy[j + 1], p2 = sxy[j + 2], p3 = sxy[j + 3];
-                const double d0 = fma(aa, p0.x, bb) - p0.y;
-                const double d1 = fma(aa, p1.x, bb) - p1.y;
-                const double d2 = fma(aa, p2.x, bb) - p2.y;
-                const double d3 = fma(aa, p3.x, bb) - p3.y;
-                s0 = fma(d0, d0, s0);
-                s1 = fma(d1, d1, s1);
-                s2 = fma(d2, d2, s2);
-                s3 = fma(d3, d3, s3);
+#pragma unroll 4
+            for (; j + 2 <= cnt; j += 2) {
+                const double2 p0 = sxy[j], p1 = sxy[j + 1];
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    const double d0 = fma(th[p][0], p0.x, th[p][1]) - p0.y;
+                    const double d1 = fma(th[p][0], p1.x, th[p][1]) - p1.y;
+                    s0[p] = fma(d0, d0, s0[p]);
+                    s1[p] = fma(d1, d1, s1[p]);
+                }
             }
             for (; j < cnt; ++j) {
-                const double2 p = sxy[j];
-                const double dd = fma(aa, p.x, bb) - p.y;
-                s0 = fma(dd, dd, s0);
+                const double2 q = sxy[j];
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    const double dd = fma(th[p][0], q.x, th[p][1]) - q.y;
+                    s0[p] = fma(dd, dd, s0[p]);
+                }
             }
         }
     }
-    const double sigma = a.prob.sigma_is_param ? th[DMAX > 2 ? 2 : 0] : a.prob.sigma;
-    return normal_ll((s0 + s1) + (s2 + s3), sigma, m);
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const double sigma = a.prob.sigma_is_param ? th[p][DMAX > 2 ? 2 : 0] : a.prob.sigma;
+        ll[p] = normal_ll(s0[p] + s1[p], sigma, m);
+    }
 }
 
 template <int DMAX>
@@ -189,7 +201,7 @@ __device__ __forceinline__ double ll_spring_normal(const MhArgs& a, const double
     for (int base = 0; base < m; base += kChunk) {
         const int cnt = (m - base < kChunk) ? (m - base) : kChunk;
         __syncthreads();
-        for (int j = threadIdx.x; j < cnt; j += kMhThreads) sy[j] = a.prob.data[base + j];
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) sy[j] = a.prob.data[base + j];
         __syncthreads();
         if (run) {
             for (int j = 0; j < cnt; ++j) {
@@ -220,7 +232,7 @@ __device__ __forceinline__ double ll_identity_normal(const MhArgs& a, const doub
                                                      double* sy) {
     const int m = a.prob.n_data;          // == n_model_params <= DMAX
     __syncthreads();
-    for (int j = threadIdx.x; j < m; j += kMhThreads) sy[j] = a.prob.data[j];
+    for (int j = threadIdx.x; j < m; j += blockDim.x) sy[j] = a.prob.data[j];
     __syncthreads();
     double s0 = 0.0, s1 = 0.0;
     double sigma = a.prob.sigma;
@@ -241,8 +253,8 @@ __device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&
                                                 double* sdat, bool& not_pd) {
     const int F = a.prob.n_data, S = a.prob.n_snapshots;
     __syncthreads();
-    for (int j = threadIdx.x; j < S * F; j += kMhThreads) sdat[j] = a.prob.data[j];
-    for (int j = threadIdx.x; j < F; j += kMhThreads) sdat[S * F + j] = a.prob.xgrid[j];
+    for (int j = threadIdx.x; j < S * F; j += blockDim.x) sdat[j] = a.prob.data[j];
+    for (int j = threadIdx.x; j < F; j += blockDim.x) sdat[S * F + j] = a.prob.xgrid[j];
     __syncthreads();
     if (!run) return 0.0;
     const double* X = sdat + S * F;
@@ -292,9 +304,10 @@ __device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&
 }
 
 // mode: 0 = init (evaluate incoming particles), 1 = fused Metropolis step, 2 = propose only,
-//       3 = log-priors only
-template <int KIND, int DMAX, int MODE>
-__global__ void __launch_bounds__(kMhThreads) mh_kernel(const __grid_constant__ MhArgs a) {
+//       3 = log-priors only.  TPB threads per block, PPT particles per thread: thread t of
+// block b owns particles b*TPB*PPT + p*TPB + t (coalesced column accesses for every p).
+template <int KIND, int DMAX, int MODE, int TPB, int PPT>
+__global__ void __launch_bounds__(TPB) mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ double smem[];
     __shared__ double sh_scale;
     const int d = a.prob.n_params;
@@ -302,134 +315,167 @@ __global__ void __launch_bounds__(kMhThreads) mh_kernel(const __grid_constant__ 
     double* sdata = smem + ((d * d + 1) & ~1);   // 16-byte aligned data staging area
 
     if (MODE == 1 || MODE == 2) {
-        for (int e = threadIdx.x; e < d * d; e += kMhThreads) sL[e] = a.chol[e];
+        for (int e = threadIdx.x; e < d * d; e += TPB) sL[e] = a.chol[e];
         if (threadIdx.x == 0) sh_scale = cov_scale_sqrt(a.accept_counts, a.step, a.n_global);
     }
     __syncthreads();
 
-    const int64_t i = (int64_t)blockIdx.x * kMhThreads + threadIdx.x;
-    const bool valid = i < a.n;
-    const int64_t ii = valid ? i : 0;
-
-    double th[DMAX];
+    int64_t idx[PPT];
+    bool valid[PPT];
+    double th[PPT][DMAX];
+    double ll_old[PPT], lp_old[PPT], lp_new[PPT], ll_new[PPT];
+    bool prior_ok[PPT];
 #pragma unroll
-    for (int c = 0; c < DMAX; ++c) th[c] = (c < d) ? a.params[(int64_t)c * a.stride + ii] : 0.0;
-    double ll_old = 0.0, lp_old = 0.0;
-    if (MODE == 1) {
-        ll_old = a.ll[ii];
-        lp_old = a.lp[ii];
+    for (int p = 0; p < PPT; ++p) {
+        const int64_t i = ((int64_t)blockIdx.x * PPT + p) * TPB + threadIdx.x;
+        valid[p] = i < a.n;
+        idx[p] = valid[p] ? i : 0;
+#pragma unroll
+        for (int c = 0; c < DMAX; ++c) th[p][c] = (c < d) ? a.params[(int64_t)c * a.stride + idx[p]] : 0.0;
+        ll_old[p] = lp_old[p] = 0.0;
+        if (MODE == 1) {
+            ll_old[p] = a.ll[idx[p]];
+            lp_old[p] = a.lp[idx[p]];
+        }
     }
 
     if (MODE == 1 || MODE == 2) {
         // proposal: th += sqrt(s) * L z, rows from last to first so th is updated in place
         const double sc = sh_scale;
-        if (a.rng.mode == 1) {
-            const double* zt = a.rng.z + ii * d;
 #pragma unroll
-            for (int r = DMAX - 1; r >= 0; --r) {
-                if (r < d) {
-                    double acc = 0.0;
-                    for (int j = 0; j <= r; ++j) acc = fma(sL[r * d + j], zt[j], acc);
-                    th[r] += sc * acc;
+        for (int p = 0; p < PPT; ++p) {
+            if (a.rng.mode == 1) {
+                const double* zt = a.rng.z + idx[p] * d;
+#pragma unroll
+                for (int r = DMAX - 1; r >= 0; --r) {
+                    if (r < d) {
+                        double acc = 0.0;
+                        for (int j = 0; j <= r; ++j) acc = fma(sL[r * d + j], zt[j], acc);
+                        th[p][r] += sc * acc;
+                    }
                 }
-            }
-        } else {
-            float zf[DMAX];
-            const Philox rng(a.rng.seed);
-            const uint64_t pid = (uint64_t)(a.rng.id_offset + ii);
+            } else {
+                float zf[DMAX];
+                const Philox rng(a.rng.seed);
+                const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[p]);
 #pragma unroll
-            for (int c = 0; c < DMAX; c += 4) {
-                if (c < d) {
-                    const uint4 r = rng(pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
-                    double z0, z1, z2, z3;
-                    normal_pair(r.x, r.y, z0, z1);
-                    normal_pair(r.z, r.w, z2, z3);
-                    zf[c] = (float)z0;
-                    if (c + 1 < DMAX) zf[c + 1] = (float)z1;
-                    if (c + 2 < DMAX) zf[c + 2] = (float)z2;
-                    if (c + 3 < DMAX) zf[c + 3] = (float)z3;
+                for (int c = 0; c < DMAX; c += 4) {
+                    if (c < d) {
+                        const uint4 r = rng(pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
+                        double z0, z1, z2, z3;
+                        normal_pair(r.x, r.y, z0, z1);
+                        normal_pair(r.z, r.w, z2, z3);
+                        zf[c] = (float)z0;
+                        if (c + 1 < DMAX) zf[c + 1] = (float)z1;
+                        if (c + 2 < DMAX) zf[c + 2] = (float)z2;
+                        if (c + 3 < DMAX) zf[c + 3] = (float)z3;
+                    }
                 }
-            }
 #pragma unroll
-            for (int r = DMAX - 1; r >= 0; --r) {
-                if (r < d) {
-                    double acc = 0.0;
+                for (int r = DMAX - 1; r >= 0; --r) {
+                    if (r < d) {
+                        double acc = 0.0;
 #pragma unroll
-                    for (int j = 0; j <= r; ++j) acc = fma(sL[r * d + j], (double)zf[j], acc);
-                    th[r] += sc * acc;
+                        for (int j = 0; j <= r; ++j) acc = fma(sL[r * d + j], (double)zf[j], acc);
+                        th[p][r] += sc * acc;
+                    }
                 }
             }
         }
     }
 
-    double* lp_cols_row = ((MODE == 0 || MODE == 3) && a.lp_cols && valid) ? a.lp_cols + ii : nullptr;
-    const double lp_new = eval_priors<KIND, DMAX>(a, th, lp_cols_row, a.stride);
-    const bool prior_ok = lp_new != kNegInf;
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        double* lp_cols_row = ((MODE == 0 || MODE == 3) && a.lp_cols && valid[p]) ? a.lp_cols + idx[p] : nullptr;
+        lp_new[p] = eval_priors<KIND, DMAX>(a, th[p], lp_cols_row, a.stride);
+        prior_ok[p] = lp_new[p] != kNegInf;
+    }
 
     if (MODE == 3) {
-        if (valid) a.lp[i] = lp_new;
+#pragma unroll
+        for (int p = 0; p < PPT; ++p)
+            if (valid[p]) a.lp[idx[p]] = lp_new[p];
         return;
     }
     if (MODE == 2) {
-        if (valid) {
 #pragma unroll
-            for (int c = 0; c < DMAX; ++c)
-                if (c < d) a.new_params[(int64_t)c * a.stride + i] = th[c];
-            a.new_lp[i] = lp_new;
+        for (int p = 0; p < PPT; ++p) {
+            if (valid[p]) {
+#pragma unroll
+                for (int c = 0; c < DMAX; ++c)
+                    if (c < d) a.new_params[(int64_t)c * a.stride + idx[p]] = th[p][c];
+                a.new_lp[idx[p]] = lp_new[p];
+            }
         }
         return;
     }
 
-    const bool run = valid && prior_ok;     // rows with a -inf prior are not evaluated (quirk Q6)
-    bool not_pd = false;
-    double ll_new;
-    if (KIND == K_LINEAR_NORMAL) ll_new = ll_linear_normal<DMAX>(a, th, run, reinterpret_cast<double2*>(sdata));
-    else if (KIND == K_SPRING_NORMAL) ll_new = ll_spring_normal<DMAX>(a, th, run, sdata);
-    else if (KIND == K_IDENTITY_NORMAL) ll_new = ll_identity_normal<DMAX>(a, th, run, sdata);
-    else ll_new = ll_linear_mvn<DMAX>(a, th, run, sdata, not_pd);
-    if (!run) ll_new = 0.0;                 // placeholder (vector_mcmc.py:207)
+    // rows with a -inf prior are not evaluated (quirk Q6)
+    bool run[PPT], not_pd[PPT];
+    bool run_any = false;
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        run[p] = valid[p] && prior_ok[p];
+        not_pd[p] = false;
+        run_any = run_any || run[p];
+    }
+    if (KIND == K_LINEAR_NORMAL) {
+        ll_linear_normal<DMAX, PPT>(a, th, run_any, reinterpret_cast<double2*>(sdata), ll_new);
+    } else {
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            if (KIND == K_SPRING_NORMAL) ll_new[p] = ll_spring_normal<DMAX>(a, th[p], run[p], sdata);
+            else if (KIND == K_IDENTITY_NORMAL) ll_new[p] = ll_identity_normal<DMAX>(a, th[p], run[p], sdata);
+            else ll_new[p] = ll_linear_mvn<DMAX>(a, th[p], run[p], sdata, not_pd[p]);
+        }
+    }
     int flag = 0;
-    if (run && ll_new != ll_new) flag |= SMCB_FLAG_MODEL_NAN;
-    if (run && not_pd) flag |= SMCB_FLAG_COV_NOT_PD;
-
-    if (MODE == 0) {
-        if (valid) {
-            a.ll[i] = ll_new;
-            a.lp[i] = lp_new;
-            if (!prior_ok) flag |= SMCB_FLAG_PRIOR_OOB;
-        }
-        if (flag) atomicOr(a.flags, flag);
-        return;
-    }
-
-    // acceptance (vector_mcmc.py:131-151 with evaluate_log_posterior = path.logpdf)
-    bool accepted = false;
-    if (valid) {
-        const double t_old = path_target(ll_old, lp_old, lp_old, a.phi, a.pe, a.qe);
-        const double t_new = path_target(ll_new, lp_new, lp_new, a.phi, a.pe, a.qe);
-        const double ratio = exp(t_new - t_old);
-        double u;
-        if (a.rng.mode == 1) {
-            u = a.rng.u[i];
-        } else {
-            const Philox rng(a.rng.seed);
-            const uint4 r = rng((uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
-            u = u01_53(r.x, r.y);
-        }
-        const bool rejected = ratio < u;     // NaN compares false -> accept, as numpy does
-        accepted = !rejected && !(run && not_pd);
-        if (accepted) {
+    int n_acc = 0;
 #pragma unroll
-            for (int c = 0; c < DMAX; ++c)
-                if (c < d) a.params[(int64_t)c * a.stride + i] = th[c];
-            a.ll[i] = ll_new;
-            a.lp[i] = lp_new;
-            a.moved[i] = 1;
+    for (int p = 0; p < PPT; ++p) {
+        if (!run[p]) ll_new[p] = 0.0;       // placeholder (vector_mcmc.py:207)
+        if (run[p] && ll_new[p] != ll_new[p]) flag |= SMCB_FLAG_MODEL_NAN;
+        if (run[p] && not_pd[p]) flag |= SMCB_FLAG_COV_NOT_PD;
+        if (MODE == 0) {
+            if (valid[p]) {
+                a.ll[idx[p]] = ll_new[p];
+                a.lp[idx[p]] = lp_new[p];
+                if (!prior_ok[p]) flag |= SMCB_FLAG_PRIOR_OOB;
+            }
+            continue;
+        }
+        // acceptance (vector_mcmc.py:131-151 with evaluate_log_posterior = path.logpdf)
+        if (valid[p]) {
+            const int64_t i = idx[p];
+            const double t_old = path_target(ll_old[p], lp_old[p], lp_old[p], a.phi, a.pe, a.qe);
+            const double t_new = path_target(ll_new[p], lp_new[p], lp_new[p], a.phi, a.pe, a.qe);
+            const double ratio = exp(t_new - t_old);
+            double u;
+            if (a.rng.mode == 1) {
+                u = a.rng.u[i];
+            } else {
+                const Philox rng(a.rng.seed);
+                const uint4 r = rng((uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
+                u = u01_53(r.x, r.y);
+            }
+            const bool rejected = ratio < u;     // NaN compares false -> accept, as numpy does
+            if (!rejected && !(run[p] && not_pd[p])) {
+#pragma unroll
+                for (int c = 0; c < DMAX; ++c)
+                    if (c < d) a.params[(int64_t)c * a.stride + i] = th[p][c];
+                a.ll[i] = ll_new[p];
+                a.lp[i] = lp_new[p];
+                a.moved[i] = 1;
+                ++n_acc;
+            }
         }
     }
     if (flag) atomicOr(a.flags, flag);
-    const int n_acc = __syncthreads_count(accepted ? 1 : 0);
-    if (threadIdx.x == 0 && n_acc) atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
+    if (MODE == 0) return;
+    // accept count: warp shuffle reduction, one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
+    if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
 }
 
 // ---- un-fused pieces (torch-callable user models) ---------------------------------------------------
@@ -558,17 +604,31 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
     return (size_t)((d * d + 1) & ~1) * 8 + data + 16;
 }
 
+template <int KIND, int DMAX, int MODE, int TPB, int PPT>
+static int launch_cfg(const MhArgs& a, cudaStream_t s) {
+    const size_t smem = mh_smem_bytes(&a.prob);
+    const int64_t per_block = (int64_t)TPB * PPT;
+    const unsigned grid = (unsigned)((a.n + per_block - 1) / per_block);
+    mh_kernel<KIND, DMAX, MODE, TPB, PPT><<<grid, TPB, smem, s>>>(a);
+    return check_launch("mh_kernel");
+}
+
 template <int KIND, int DMAX, int MODE>
 static int launch_one(const MhArgs& a, cudaStream_t s) {
-    const size_t smem = mh_smem_bytes(&a.prob);
-    static bool attr = false;
-    if (!attr && smem > 48 * 1024) {
-        cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr = true;
+    if constexpr (KIND == K_LINEAR_NORMAL && (MODE == 0 || MODE == 1)) {
+        // several particles per thread amortise the shared-memory data reads; keep at least
+        // ~4 blocks per SM so small problems still fill the chip
+        static const int cfg = getenv("SMCB_LINEAR_CFG") ? atoi(getenv("SMCB_LINEAR_CFG")) : -1;   // tuning aid
+        if (cfg == 0) return launch_cfg<KIND, DMAX, MODE, kMhThreads, 1>(a, s);
+        if (cfg == 1) return launch_cfg<KIND, DMAX, MODE, 128, 2>(a, s);
+        if (cfg == 2) return launch_cfg<KIND, DMAX, MODE, 128, 4>(a, s);
+        if (cfg == 3) return launch_cfg<KIND, DMAX, MODE, 256, 4>(a, s);
+        if (cfg == 4) return launch_cfg<KIND, DMAX, MODE, 256, 2>(a, s);
+        if (a.n >= (int64_t)kNumSMs * 4 * 1024) return launch_cfg<KIND, DMAX, MODE, 256, 4>(a, s);
+        if (a.n >= (int64_t)kNumSMs * 4 * 512) return launch_cfg<KIND, DMAX, MODE, 128, 4>(a, s);
+        if (a.n >= (int64_t)kNumSMs * 4 * 256) return launch_cfg<KIND, DMAX, MODE, 128, 2>(a, s);
     }
-    const unsigned grid = (unsigned)((a.n + kMhThreads - 1) / kMhThreads);
-    mh_kernel<KIND, DMAX, MODE><<<grid, kMhThreads, smem, s>>>(a);
-    return check_launch("mh_kernel");
+    return launch_cfg<KIND, DMAX, MODE, kMhThreads, 1>(a, s);
 }
 
 template <int MODE>

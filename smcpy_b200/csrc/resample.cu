@@ -208,15 +208,18 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const doubl
 
 // ---- search -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) searchsorted_kernel(const double* __restrict__ cdf, int64_t n_cdf,
+                                                           const double* __restrict__ offset_ptr,
                                                            const double* __restrict__ u, int64_t n_u,
                                                            int64_t* __restrict__ idx) {
+    const double off = offset_ptr ? *offset_ptr : 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_u; k += stride) {
         const double x = u[k];
         int64_t lo = 0, hi = n_cdf;                 // first j with cdf_j > x
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
-            if (__ldg(cdf + mid) <= x) lo = mid + 1; else hi = mid;
+            const double c = offset_ptr ? __dadd_rn(off, __ldg(cdf + mid)) : __ldg(cdf + mid);
+            if (c <= x) lo = mid + 1; else hi = mid;
         }
         idx[k] = (lo < n_cdf) ? lo : (n_cdf - 1);   // clamp (quirk Q4)
     }
@@ -309,7 +312,14 @@ extern "C" int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mo
 extern "C" int smcb_searchsorted(const double* cdf, int64_t n_cdf, const double* u, int64_t n_u,
                                  int64_t* idx_out, void* stream) {
     SMCB_REQUIRE(cdf && u && idx_out && n_cdf > 0 && n_u > 0, "bad argument");
-    searchsorted_kernel<<<grid_for(n_u, 256, 1, 8), 256, 0, as_stream(stream)>>>(cdf, n_cdf, u, n_u, idx_out);
+    searchsorted_kernel<<<grid_for(n_u, 256, 1, 8), 256, 0, as_stream(stream)>>>(cdf, n_cdf, nullptr, u, n_u, idx_out);
+    return check_launch("searchsorted_kernel");
+}
+
+extern "C" int smcb_searchsorted_offset(const double* cdf, int64_t n_cdf, const double* offset, const double* u,
+                                        int64_t n_u, int64_t* idx_out, void* stream) {
+    SMCB_REQUIRE(cdf && offset && u && idx_out && n_cdf > 0 && n_u > 0, "bad argument");
+    searchsorted_kernel<<<grid_for(n_u, 256, 1, 8), 256, 0, as_stream(stream)>>>(cdf, n_cdf, offset, u, n_u, idx_out);
     return check_launch("searchsorted_kernel");
 }
 

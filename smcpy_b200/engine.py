@@ -289,8 +289,9 @@ def reweight(st, path):
     lw_in = None if st.uniform_weights else st.log_w
     s = stream_ptr()
     if world == 1:
-        call("smcb_reweight", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
-             C.byref(path), ptr(st.log_w_alt), ptr(st.w_alt), ptr(st.scalars), ptr(st.ws), s)
+        with _timed("reweight"):
+            call("smcb_reweight", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
+                 C.byref(path), ptr(st.log_w_alt), ptr(st.w_alt), ptr(st.scalars), ptr(st.ws), s)
     else:
         part = st.scalars[8:11]
         call("smcb_reweight_partials", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
@@ -325,8 +326,9 @@ def find_phi(st, spec, phi_old, target_ess, lam=1.0):
     lp = None if (st.lq is None and spec is not None) else st.lp
     lp_const = spec.lp_const if spec is not None else 0.0
     if world == 1:
-        call("smcb_ess_bisect", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
-             float(target_ess), st.n_global, ptr(st.bis), ptr(st.ws), s, launches=1 + bisect_iters(phi_old))
+        with _timed("bisect"):
+            call("smcb_ess_bisect", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
+                 float(target_ess), st.n_global, ptr(st.bis), ptr(st.ws), s, launches=1 + bisect_iters(phi_old))
     else:
         call("smcb_ess_bisect_begin", float(phi_old), ptr(st.bis), s)
         part = st.scalars[8:11]
@@ -438,8 +440,9 @@ def covariance(st):
     s = stream_ptr()
     d = st.d
     if world == 1:
-        call("smcb_weighted_cov", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.mean), ptr(st.cov),
-             ptr(st.sums), ptr(st.ws), s)
+        with _timed("cov"):
+            call("smcb_weighted_cov", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.mean), ptr(st.cov),
+                 ptr(st.sums), ptr(st.ws), s)
     else:
         call("smcb_weighted_sums1", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.sums), ptr(st.ws), s)
         _all_reduce_sum(st.sums[:1 + d])
@@ -476,6 +479,26 @@ def eval_incoming(st, spec, lp_cols=None):
         eval_incoming_callable(st, spec, lp_cols)
 
 
+# optional kernel timing (bench.py): name -> list of (start, end) CUDA events on the launch stream
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record()
+            PROFILE.setdefault(self.name, []).append((self.a, self.b))
+
+
 def mutate(st, spec, num_samples, path, rng, check_incoming=False):
     """VectorMCMC.smc_metropolis (vector_mcmc.py:46-62): `num_samples` fused Metropolis steps in
     place, proposal covariance rescaled from the global accept count after every step.
@@ -500,9 +523,10 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
         else:
             r.mode, r.seed, r.stream = 0, rng.seed, rng.next_stream()
         if spec.fused:
-            call("smcb_mh_step", C.byref(spec.c), C.byref(path), ptr(st.cols), st.n, st.n, st.n_global,
-                 ptr(st.ll), ptr(st.lp), ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), k, C.byref(r),
-                 ptr(st.flags), s)
+            with _timed("mh_step"):
+                call("smcb_mh_step", C.byref(spec.c), C.byref(path), ptr(st.cols), st.n, st.n, st.n_global,
+                     ptr(st.ll), ptr(st.lp), ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), k, C.byref(r),
+                     ptr(st.flags), s)
         else:
             from .callable_route import mh_step_callable
             mh_step_callable(st, spec, path, k, r)

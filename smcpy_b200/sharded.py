@@ -1,0 +1,97 @@
+"""
+Multi-GPU resampling: particles are sharded in contiguous blocks, one process per GPU
+(replaces the MPI scatter/allgather of model evaluations in
+smcpy/mcmc/parallel_vector_mcmc.py:36-47 by sharding the whole particle loop).
+
+Per resample:
+  1. local inclusive scan of the (globally normalised) weights           [smcb_cdf_scan]
+  2. all-gather of the per-rank weight totals -> segment offsets O_r     [NCCL, G doubles]
+  3. every rank draws the uniforms of its own output slots                [smcb_resample_uniforms]
+     and routes each to the rank whose CDF segment [O_r, O_r+1) holds it  [all-to-all, 8 B/slot]
+  4. the owner searches its local CDF (+ offset) and gathers the rows     [smcb_searchsorted_offset,
+                                                                           smcb_gather]
+  5. rows travel back to the requesting rank                              [all-to-all, 8(d+2) B/slot]
+Stratified / systematic uniforms are already sorted, so step 3 is a split of a contiguous range;
+multinomial uniforms are sorted first (particles are exchangeable, so slot order is immaterial).
+Collectives are NCCL over NVLink; every count that decides a split is exchanged explicitly.
+"""
+
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, engine
+from ._lib import call, ptr, stream_ptr
+
+
+def segment_offsets(totals):
+    """O_0 = 0, O_r = W_0 + ... + W_{r-1} summed in rank order (identical on every rank)."""
+    off = torch.zeros(totals.shape[0] + 1, dtype=torch.float64, device=totals.device)
+    off[1:] = torch.cumsum(totals, dim=0)
+    return off
+
+
+def route_counts(dest, world):
+    """Rows this rank sends to each destination (dest is a sorted int64 tensor)."""
+    return torch.bincount(dest, minlength=world)[:world]
+
+
+def exchange_counts(send_counts):
+    """all-to-all of the per-destination counts -> per-source counts (works on any backend)."""
+    recv = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv, send_counts)
+    return recv
+
+
+def resample_sharded(st, kernel, resample_rng, warn_threshold):
+    rank, world = engine.dist_info()
+    rng = kernel.rng
+    kind = getattr(resample_rng, "kind", None)
+    if isinstance(rng, np.random.Generator) or kind is None:
+        raise NotImplementedError("multi-GPU resampling needs the native Philox generator and a built-in "
+                                  "resampler (replay parity mode is single-GPU)")
+    n, d = st.n, st.d
+    s = stream_ptr()
+    dv = st.cols.device
+    # 1-2: local CDF and segment offsets
+    call("smcb_cdf_scan", ptr(st.w), ptr(st.cdf), n, _lib.SCAN_LOOKBACK, ptr(st.ws), s)
+    totals = engine._all_gather_rows(st.cdf[n - 1:n]).reshape(-1)
+    off = segment_offsets(totals)
+    # 3: uniforms of my output slots, routed to the owning rank
+    call("smcb_resample_uniforms", int(kind), st.n_global, st.id_offset, n, rng.seed, rng.next_stream(),
+         ptr(st.u), s)
+    u = st.u
+    if kind == _lib.RESAMPLE_STANDARD:
+        u = torch.sort(u).values
+    bounds = torch.cat([off[1:world], torch.full((1,), float("inf"), dtype=torch.float64, device=dv)])
+    dest = torch.empty(n, dtype=torch.int64, device=dv)
+    call("smcb_searchsorted", ptr(bounds), world, ptr(u), n, ptr(dest), s)
+    send_counts = route_counts(dest, world)
+    recv_counts = exchange_counts(send_counts)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()          # host sync: split sizes
+    n_req = int(sum(rc))
+    u_in = torch.empty(max(n_req, 1), dtype=torch.float64, device=dv)
+    dist.all_to_all_single(u_in[:n_req], u.contiguous(), output_split_sizes=rc, input_split_sizes=sc)
+    # 4: owner-side search + gather (rows in AoS for the exchange)
+    rows_out = torch.empty((max(n_req, 1), d + 2), dtype=torch.float64, device=dv)
+    n_unique = torch.zeros(1, dtype=torch.int64, device=dv)
+    if n_req > 0:
+        idx = torch.empty(n_req, dtype=torch.int64, device=dv)
+        call("smcb_searchsorted_offset", ptr(st.cdf), n, ptr(off[rank:rank + 1]), ptr(u_in), n_req, ptr(idx), s)
+        soa = torch.empty((d + 2, n_req), dtype=torch.float64, device=dv)
+        call("smcb_gather", ptr(st.cols), n, ptr(soa), n_req, ptr(idx), n_req, d + 2, s)
+        call("smcb_soa_to_aos", ptr(soa), ptr(rows_out), n_req, d + 2, n_req, s)
+        call("smcb_count_unique", ptr(idx), n_req, n, ptr(st.counts), ptr(st.ws), s)
+        n_unique = st.counts[0:1].clone()
+    # 5: rows back to the requesters
+    rows_in = torch.empty((n, d + 2), dtype=torch.float64, device=dv)
+    dist.all_to_all_single(rows_in, rows_out[:n_req], output_split_sizes=sc, input_split_sizes=rc)
+    call("smcb_aos_to_soa", ptr(rows_in), ptr(st.cols_alt), n, d + 2, n, s)
+    st.cols, st.cols_alt = st.cols_alt, st.cols
+    st.set_uniform_weights()
+    engine._all_reduce_sum(n_unique)
+    if int(n_unique.item()) <= max(1, warn_threshold * st.n_global):
+        warnings.warn(f"Resampled to less than {warn_threshold * 100}% of particles; ", UserWarning)
+    return None

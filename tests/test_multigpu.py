@@ -1,0 +1,140 @@
+"""
+Multi-process tests.
+  * world_size-2 gloo tests on CPU (run everywhere): the host-side bookkeeping of the sharded
+    resampler (segment offsets, routing counts, all-to-all split exchange, row conservation).
+  * world_size-2 NCCL test on GPUs (marked gpu, skipped with < 2 devices): a sharded
+    FixedPhiSampler run agrees statistically with the single-GPU run and conserves particles.
+"""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from smcpy_b200 import engine, sharded
+    assert engine.dist_info() == (rank, world)
+    n_global = 1001
+    lo, hi = engine.shard_bounds(n_global, rank, world)
+    n = hi - lo
+    rng = np.random.default_rng(5)
+    w_all = rng.exponential(1.0, n_global)
+    w_all /= w_all.sum()
+    w = torch.tensor(w_all[lo:hi])
+    # 2: rank totals -> identical segment offsets on every rank
+    tot = torch.empty(world, dtype=torch.float64)
+    dist.all_gather_into_tensor(tot, torch.cumsum(w, 0)[-1:].clone())
+    off = sharded.segment_offsets(tot)
+    assert off[0] == 0 and abs(float(off[-1]) - 1.0) < 1e-12
+    # 3: stratified uniforms of my slots, routed by segment
+    u = (torch.arange(lo, hi, dtype=torch.float64) + torch.tensor(np.random.default_rng(rank).uniform(0, 1, n))) / n_global
+    bounds = torch.cat([off[1:world], torch.tensor([float("inf")], dtype=torch.float64)])
+    dest = torch.searchsorted(bounds, u, right=True)
+    send = sharded.route_counts(dest, world)
+    recv = sharded.exchange_counts(send)
+    assert int(send.sum()) == n
+    u_in = torch.empty(int(recv.sum()), dtype=torch.float64)
+    dist.all_to_all_single(u_in, u.contiguous(), output_split_sizes=recv.tolist(), input_split_sizes=send.tolist())
+    # every request that reached me lies in my CDF segment
+    assert bool(((u_in >= off[rank]) & (u_in < bounds[rank])).all())
+    # 4-5: answer with (global ancestor id) rows and send them back
+    cdf = torch.cumsum(w, 0)
+    idx = torch.clamp(torch.searchsorted(cdf + off[rank], u_in, right=True), max=n - 1)
+    rows = (idx + lo).to(torch.float64).reshape(-1, 1).repeat(1, 3)
+    back = torch.empty((n, 3), dtype=torch.float64)
+    dist.all_to_all_single(back, rows.contiguous(), output_split_sizes=send.tolist(), input_split_sizes=recv.tolist())
+    # compare with the single-process answer on the full arrays
+    want = np.minimum(np.searchsorted(np.cumsum(w_all), u.numpy(), side="right"), n_global - 1)
+    got = back[:, 0].numpy().astype(np.int64)
+    mism = int((got != want).sum())
+    tot_req = torch.tensor([float(recv.sum())])
+    dist.all_reduce(tot_req)
+    out.put((rank, n, mism, float(tot_req.item())))
+    dist.destroy_process_group()
+
+
+def test_sharded_resampling_bookkeeping_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sum(r[1] for r in res) == 1001
+    for rank, n, mism, tot_req in res:
+        assert tot_req == 1001.0                 # every slot is answered exactly once
+        assert mism <= 1                         # sharded offsets may move an edge by one ulp
+
+
+def _nccl_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import warnings
+    import smcpy_b200 as sb
+    from tests.golden import configs
+    from tests.helpers import make_b200
+    res = {}
+    for resampler in (sb.stratified, sb.standard, sb.systematic):
+        problem = configs.linear_problem(100)
+        mcmc, kernel = make_b200(problem, rng=7)
+        smc = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            steps, mll = smc.sample(20000, 8, target_ess=0.8, resample_rng=resampler)
+        last = steps[-1]
+        res[resampler.__name__] = (float(mll[-1]), last.compute_mean(package=False), last.num_particles,
+                                   len(steps), float(last.compute_ess()))
+    out.put((rank, res))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_sampler_two_gpus_nccl():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for name in ("stratified", "standard", "systematic"):
+        a, b = res[0][name], res[1][name]
+        assert a[0] == b[0] and a[3] == b[3]                  # identical scalars on every rank
+        np.testing.assert_array_equal(a[1], b[1])
+        assert a[2] + b[2] == 20000                           # particles conserved
+        assert a[0] == pytest.approx(-77.357884, abs=0.3)     # SURVEY appendix B anchors
+        np.testing.assert_allclose(a[1], [2.0363965, 3.4859536], atol=0.01)
