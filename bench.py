@@ -358,6 +358,20 @@ def run_gpu(args):
 
 
 def main():
+    # keep stdout clean for the ONE JSON line: libraries (e.g. NCCL's version banner) write to
+    # fd 1, so route fd 1 to stderr while running and print the result on the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    import builtins
+    _print = builtins.print
+
+    def emit(*a, **k):
+        k.setdefault("file", real_stdout)
+        _print(*a, **k)
+        real_stdout.flush()
+    builtins.print = emit
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

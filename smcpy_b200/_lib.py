@@ -11,7 +11,7 @@ import os
 import torch
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libsmcb200.so")
+LIB_PATH = os.environ.get("SMCB_LIB", os.path.join(PKG, "libsmcb200.so"))   # SMCB_LIB: tuning aid
 
 MAX_PARAMS = 32
 MAX_PRIORS = 32

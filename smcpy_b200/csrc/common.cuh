@@ -201,14 +201,16 @@ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
     const uint64_t x = ((uint64_t)hi << 32) | lo;
     return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
-// two standard normals from two 32-bit words (Box-Muller in fp32; proposals only need a
-// symmetric, well-distributed z -- see DESIGN.md "RNG")
+// two standard normals from two 32-bit words: Box-Muller in fp32 with the hardware
+// approximations (lg2 / sin / cos MUFU).  Proposals only need a symmetric, well-distributed z
+// (the Metropolis ratio does not involve the proposal density) -- see DESIGN.md "RNG".
 __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, double& z0, double& z1) {
     const float u1 = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
-    const float u2 = (float)(w1 >> 8) * (2.0f / 16777216.0f);            // [0,2)
-    const float r = sqrtf(-2.0f * logf(u1));
+    const float th = ((float)(int32_t)w1) * (3.14159265358979f / 2147483648.0f);   // [-pi, pi)
+    const float x = -2.0f * __logf(u1);       // > 0 since u1 < 1
+    const float r = x * rsqrtf(x);
     float s, c;
-    sincospif(u2, &s, &c);
+    __sincosf(th, &s, &c);
     z0 = (double)(r * c);
     z1 = (double)(r * s);
 }

@@ -6,13 +6,14 @@
 //   model + log-likelihood where the prior is finite             (:205-214, log_likelihoods.py)
 //   tempered acceptance ratio exp(target(x') - target(x))        (:131-146, paths.py:81-84)
 //   reject iff ratio < u, select                                 (:148-151, :176-181)
-// in one pass over structure-of-arrays particles: thread i owns particle i, reads its d
-// parameters + ll + lp (coalesced column loads), keeps proposal, model outputs and residuals in
-// registers, stages the shared data vector in shared memory, and writes back only accepted
-// rows.  Algorithmic HBM bytes per particle-step: 2 * 8 * (d + 2).
+// in one pass over structure-of-arrays particles.  Persistent blocks (a multiple of the SM
+// count) stage the Cholesky factor and the shared data vector in shared memory once, then loop
+// over tiles of TPB*PPT particles: thread t owns particles tile*TPB*PPT + p*TPB + t (coalesced
+// column loads), keeps proposal, model outputs and residuals in registers, and writes back only
+// accepted rows.  Algorithmic HBM bytes per particle-step: 2 * 8 * (d + 2).
 //
-// The same kernels with kInit = true evaluate log-priors and log-likelihood of incoming
-// particles (vector_mcmc.py:162-166, initializer.py:66-73).
+// The same kernels in other modes evaluate log-priors and log-likelihood of incoming
+// particles (vector_mcmc.py:162-166, initializer.py:66-73), priors only, or the proposal only.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -24,12 +25,17 @@ constexpr int kChunk = 1024;          // data points staged per shared-memory ch
 
 enum Kind { K_LINEAR_NORMAL = 0, K_SPRING_NORMAL = 1, K_IDENTITY_NORMAL = 2, K_LINEAR_MVN = 3 };
 
-// per-column view of the prior table (host-built from smcb_problem_t::priors)
+// per-column view of the prior table (host-built from smcb_problem_t::priors).  Scalar priors
+// share one branch-free support test:  t = x - a;  lo <= t <= hi.
+//   scipy uniform(loc, scale): a = loc, [0, scale] -- the reference tests (x-loc)/scale in [0,1];
+//     with t = fl(x-loc) that is exactly 0 <= t <= scale (DESIGN.md "priors"), no division;
+//   ImproperUniform(lo, hi):   a = 0 (t = x exactly), [lo, hi];
+//   columns of a matrix prior: a = 0, [-inf, inf].
 struct ColPriors {
-    int8_t kind[SMCB_MAX_PARAMS];        // 0 = column belongs to a matrix prior
-    int8_t prior_of_col[SMCB_MAX_PARAMS];
-    double a[SMCB_MAX_PARAMS], b[SMCB_MAX_PARAMS], logp[SMCB_MAX_PARAMS];
-    int32_t n_cov;                        // number of IMPROPER_COV priors (<= 2)
+    int8_t prior_of_col[SMCB_MAX_PARAMS];   // -1: column belongs to a matrix prior
+    double a[SMCB_MAX_PARAMS], lo[SMCB_MAX_PARAMS], hi[SMCB_MAX_PARAMS], logp[SMCB_MAX_PARAMS];
+    double logp_total;                      // sum of logp in column order
+    int32_t n_cov;                          // number of IMPROPER_COV priors (<= 2)
     int32_t cov_c0[2], cov_ncols[2], cov_prior[2];
 };
 
@@ -48,7 +54,7 @@ struct MhArgs {
     double phi, pe, qe;
     smcb_rng_t rng;
     int32_t* flags;
-    double* lp_cols;      // init only (optional)
+    double* lp_cols;      // init / priors only (optional)
     double* new_params;   // propose only
     double* new_lp;       // propose only
 };
@@ -66,27 +72,28 @@ __device__ __forceinline__ double cov_scale_sqrt(const unsigned long long* count
 }
 
 // ---- priors -----------------------------------------------------------------------------------
-// scipy uniform: support test on (x-loc)/scale in [0,1]; with t = fl(x-loc) this is exactly
-// 0 <= t <= scale (DESIGN.md "priors"), no division needed.
-template <int KIND, int DMAX>
+template <int KIND, int DMAX, bool EXACT>
 __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th)[DMAX], double* lp_cols_row,
                                               int64_t col_stride) {
     const int d = a.prob.n_params;
-    double lps = 0.0;
+    bool ok = true;
 #pragma unroll
     for (int c = 0; c < DMAX; ++c) {
-        if (c < d) {
-            const int kind = a.cp.kind[c];
-            if (kind == SMCB_PRIOR_UNIFORM) {
-                const double t = th[c] - a.cp.a[c];
-                const double v = (t >= 0.0 && t <= a.cp.b[c]) ? a.cp.logp[c] : kNegInf;
-                lps += v;
-                if (lp_cols_row) lp_cols_row[(int64_t)a.cp.prior_of_col[c] * col_stride] = v;
-            } else if (kind == SMCB_PRIOR_IMPROPER_UNIFORM) {
-                const double v = (th[c] >= a.cp.a[c] && th[c] <= a.cp.b[c]) ? 0.0 : kNegInf;
-                lps += v;
-                if (lp_cols_row) lp_cols_row[(int64_t)a.cp.prior_of_col[c] * col_stride] = v;
-            }
+        if (EXACT || c < d) {
+            const double t = th[c] - a.cp.a[c];
+            ok = ok && (t >= a.cp.lo[c]) && (t <= a.cp.hi[c]);
+        }
+    }
+    double lps = ok ? a.cp.logp_total : kNegInf;
+    if (lp_cols_row) {                      // un-summed per-prior values (host-facing API only)
+        for (int c = 0; c < d; ++c) {
+            if (a.cp.prior_of_col[c] < 0) continue;
+            double x = 0.0;
+#pragma unroll
+            for (int k = 0; k < DMAX; ++k) x = (k == c) ? th[k] : x;
+            const double t = x - a.cp.a[c];
+            lp_cols_row[(int64_t)a.cp.prior_of_col[c] * col_stride] =
+                (t >= a.cp.lo[c] && t <= a.cp.hi[c]) ? a.cp.logp[c] : kNegInf;
         }
     }
     // matrix priors: packed upper-triangular columns must form a Cholesky-PD matrix.
@@ -131,8 +138,8 @@ __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th
 }
 
 // ---- models + likelihoods ------------------------------------------------------------------------
-// All threads of the block call these (they stage data through shared memory); `run` says
-// whether this thread's particle needs the evaluation.
+// All threads of the block call these.  When the data vector fits one chunk it is staged once
+// per block (`resident`); otherwise it is re-staged chunk by chunk for every tile.
 
 __device__ __forceinline__ double normal_ll(double ssq, double sigma, int m) {
     // log_likelihoods.py:42-49: term1 = -log(2 pi var) * (M/2); term2 = -1/2 * ssqe / var
@@ -142,22 +149,39 @@ __device__ __forceinline__ double normal_ll(double ssq, double sigma, int m) {
     return term1 + term2;
 }
 
+template <int KIND>
+__device__ __forceinline__ void stage_data(const MhArgs& a, double* sdata, int base, int cnt) {
+    if (KIND == K_LINEAR_NORMAL) {
+        double2* sxy = reinterpret_cast<double2*>(sdata);
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x)
+            sxy[j] = make_double2(a.prob.xgrid[base + j], a.prob.data[base + j]);
+    } else if (KIND == K_LINEAR_MVN) {
+        const int F = a.prob.n_data, S = a.prob.n_snapshots;
+        for (int j = threadIdx.x; j < S * F; j += blockDim.x) sdata[j] = a.prob.data[j];
+        for (int j = threadIdx.x; j < F; j += blockDim.x) sdata[S * F + j] = a.prob.xgrid[j];
+    } else {
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) sdata[j] = a.prob.data[base + j];
+    }
+}
+
 // Linear model + Normal likelihood for PPT particles per thread: every staged data point
 // (one broadcast LDS.128) feeds 3*PPT FP64 instructions, which keeps the shared-memory pipe
-// off the critical path (profiles/r01_mh_c2_ncu.md).
+// off the critical path (profiles/r01_mh_kernels.md).
 template <int DMAX, int PPT>
 __device__ __forceinline__ void ll_linear_normal(const MhArgs& a, const double (&th)[PPT][DMAX], bool run_any,
-                                                 double2* sxy, double (&ll)[PPT]) {
+                                                 bool resident, double* sdata, double (&ll)[PPT]) {
+    const double2* sxy = reinterpret_cast<const double2*>(sdata);
     const int m = a.prob.n_data;
     double s0[PPT], s1[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) s0[p] = s1[p] = 0.0;
     for (int base = 0; base < m; base += kChunk) {
         const int cnt = (m - base < kChunk) ? (m - base) : kChunk;
-        __syncthreads();
-        for (int j = threadIdx.x; j < cnt; j += blockDim.x)
-            sxy[j] = make_double2(a.prob.xgrid[base + j], a.prob.data[base + j]);
-        __syncthreads();
+        if (!resident) {
+            __syncthreads();
+            stage_data<K_LINEAR_NORMAL>(a, sdata, base, cnt);
+            __syncthreads();
+        }
         if (run_any) {
             int j = 0;
 #pragma unroll 4
@@ -190,7 +214,7 @@ __device__ __forceinline__ void ll_linear_normal(const MhArgs& a, const double (
 
 template <int DMAX>
 __device__ __forceinline__ double ll_spring_normal(const MhArgs& a, const double (&th)[DMAX], bool run,
-                                                   double* sy) {
+                                                   bool resident, double* sy) {
     const int m = a.prob.n_data;
     const double K = th[0], g = th[1];
     double x = a.prob.model_args[0], v = a.prob.model_args[1];
@@ -200,9 +224,11 @@ __device__ __forceinline__ double ll_spring_normal(const MhArgs& a, const double
     double ssq = 0.0;
     for (int base = 0; base < m; base += kChunk) {
         const int cnt = (m - base < kChunk) ? (m - base) : kChunk;
-        __syncthreads();
-        for (int j = threadIdx.x; j < cnt; j += blockDim.x) sy[j] = a.prob.data[base + j];
-        __syncthreads();
+        if (!resident) {
+            __syncthreads();
+            stage_data<K_SPRING_NORMAL>(a, sy, base, cnt);
+            __syncthreads();
+        }
         if (run) {
             for (int j = 0; j < cnt; ++j) {
                 if (base + j > 0) {
@@ -227,35 +253,27 @@ __device__ __forceinline__ double ll_spring_normal(const MhArgs& a, const double
     return normal_ll(ssq, sigma, m);
 }
 
-template <int DMAX>
+template <int DMAX, bool EXACT>
 __device__ __forceinline__ double ll_identity_normal(const MhArgs& a, const double (&th)[DMAX], bool run,
-                                                     double* sy) {
+                                                     const double* sy) {
     const int m = a.prob.n_data;          // == n_model_params <= DMAX
-    __syncthreads();
-    for (int j = threadIdx.x; j < m; j += blockDim.x) sy[j] = a.prob.data[j];
-    __syncthreads();
     double s0 = 0.0, s1 = 0.0;
-    double sigma = a.prob.sigma;
     if (run) {
 #pragma unroll
         for (int j = 0; j < DMAX; j += 2) {
-            if (j < m) { const double dd = th[j] - sy[j]; s0 = fma(dd, dd, s0); }
-            if (j + 1 < m) { const double dd = th[j + 1] - sy[j + 1]; s1 = fma(dd, dd, s1); }
+            if (EXACT || j < m) { const double dd = th[j] - sy[j]; s0 = fma(dd, dd, s0); }
+            if (j + 1 < DMAX && (EXACT || j + 1 < m)) { const double dd = th[j + 1] - sy[j + 1]; s1 = fma(dd, dd, s1); }
         }
     }
-    return normal_ll(s0 + s1, sigma, m);
+    return normal_ll(s0 + s1, a.prob.sigma, m);
 }
 
 // MVNormal (log_likelihoods.py:150-192) with one Cholesky per particle:
 //   sum_s [ -F/2 log 2pi - 1/2 log det C - 1/2 e_s^T C^-1 e_s ],  e_s = model - data_s
 template <int DMAX>
 __device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&th)[DMAX], bool run,
-                                                double* sdat, bool& not_pd) {
+                                                const double* sdat, bool& not_pd) {
     const int F = a.prob.n_data, S = a.prob.n_snapshots;
-    __syncthreads();
-    for (int j = threadIdx.x; j < S * F; j += blockDim.x) sdat[j] = a.prob.data[j];
-    for (int j = threadIdx.x; j < F; j += blockDim.x) sdat[S * F + j] = a.prob.xgrid[j];
-    __syncthreads();
     if (!run) return 0.0;
     const double* X = sdat + S * F;
     double c[3][3];
@@ -303,176 +321,203 @@ __device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&
     return (double)S * (term1 - 0.5 * logdet) - 0.5 * quad;
 }
 
-// mode: 0 = init (evaluate incoming particles), 1 = fused Metropolis step, 2 = propose only,
-//       3 = log-priors only.  TPB threads per block, PPT particles per thread: thread t of
-// block b owns particles b*TPB*PPT + p*TPB + t (coalesced column accesses for every p).
-template <int KIND, int DMAX, int MODE, int TPB, int PPT>
-__global__ void __launch_bounds__(TPB) mh_kernel(const __grid_constant__ MhArgs a) {
-    extern __shared__ double smem[];
-    __shared__ double sh_scale;
-    const int d = a.prob.n_params;
-    double* sL = smem;                       // d*d lower Cholesky factor
-    double* sdata = smem + ((d * d + 1) & ~1);   // 16-byte aligned data staging area
+// register budget per thread -> minimum resident blocks per SM (keeps ptxas from trading
+// occupancy for unrolling: profiles/r01_mh_kernels.md)
+__host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt) {
+    const int regs = dmax >= 32 ? 128 : (dmax >= 16 ? 96 : (ppt >= 4 ? 84 : 64));
+    return 65536 / (tpb * regs) > 0 ? 65536 / (tpb * regs) : 1;
+}
 
+// mode: 0 = init (evaluate incoming particles), 1 = fused Metropolis step, 2 = propose only,
+//       3 = log-priors only.  EXACT: n_params == DMAX (drops every per-column bounds check).
+template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT>
+__global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT))
+mh_kernel(const __grid_constant__ MhArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double sh_scale;
+    const int d = EXACT ? DMAX : a.prob.n_params;
+    // Cholesky factor transposed and zero-padded to DMAX: sLt[j * DMAX + r] = L[r][j], so column j
+    // is contiguous (LDS.128) and the unrolled update needs no bounds checks
+    double* sLt = smem;
+    double* sdata = smem + DMAX * DMAX;      // 16-byte aligned data staging area
+
+    const bool resident = (KIND == K_IDENTITY_NORMAL) || (KIND == K_LINEAR_MVN) || (a.prob.n_data <= kChunk);
     if (MODE == 1 || MODE == 2) {
-        for (int e = threadIdx.x; e < d * d; e += TPB) sL[e] = a.chol[e];
+        for (int e = threadIdx.x; e < DMAX * DMAX; e += TPB) {
+            const int j = e / DMAX, r = e - j * DMAX;
+            sLt[e] = (r < d && j <= r) ? a.chol[r * d + j] : 0.0;
+        }
         if (threadIdx.x == 0) sh_scale = cov_scale_sqrt(a.accept_counts, a.step, a.n_global);
     }
+    if ((MODE == 0 || MODE == 1) && resident) stage_data<KIND>(a, sdata, 0, a.prob.n_data);
     __syncthreads();
+    const double sc = (MODE == 1 || MODE == 2) ? sh_scale : 0.0;
 
-    int64_t idx[PPT];
-    bool valid[PPT];
-    double th[PPT][DMAX];
-    double ll_old[PPT], lp_old[PPT], lp_new[PPT], ll_new[PPT];
-    bool prior_ok[PPT];
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        const int64_t i = ((int64_t)blockIdx.x * PPT + p) * TPB + threadIdx.x;
-        valid[p] = i < a.n;
-        idx[p] = valid[p] ? i : 0;
-#pragma unroll
-        for (int c = 0; c < DMAX; ++c) th[p][c] = (c < d) ? a.params[(int64_t)c * a.stride + idx[p]] : 0.0;
-        ll_old[p] = lp_old[p] = 0.0;
-        if (MODE == 1) {
-            ll_old[p] = a.ll[idx[p]];
-            lp_old[p] = a.lp[idx[p]];
-        }
-    }
-
-    if (MODE == 1 || MODE == 2) {
-        // proposal: th += sqrt(s) * L z, rows from last to first so th is updated in place
-        const double sc = sh_scale;
-#pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            if (a.rng.mode == 1) {
-                const double* zt = a.rng.z + idx[p] * d;
-#pragma unroll
-                for (int r = DMAX - 1; r >= 0; --r) {
-                    if (r < d) {
-                        double acc = 0.0;
-                        for (int j = 0; j <= r; ++j) acc = fma(sL[r * d + j], zt[j], acc);
-                        th[p][r] += sc * acc;
-                    }
-                }
-            } else {
-                float zf[DMAX];
-                const Philox rng(a.rng.seed);
-                const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[p]);
-#pragma unroll
-                for (int c = 0; c < DMAX; c += 4) {
-                    if (c < d) {
-                        const uint4 r = rng(pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
-                        double z0, z1, z2, z3;
-                        normal_pair(r.x, r.y, z0, z1);
-                        normal_pair(r.z, r.w, z2, z3);
-                        zf[c] = (float)z0;
-                        if (c + 1 < DMAX) zf[c + 1] = (float)z1;
-                        if (c + 2 < DMAX) zf[c + 2] = (float)z2;
-                        if (c + 3 < DMAX) zf[c + 3] = (float)z3;
-                    }
-                }
-#pragma unroll
-                for (int r = DMAX - 1; r >= 0; --r) {
-                    if (r < d) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int j = 0; j <= r; ++j) acc = fma(sL[r * d + j], (double)zf[j], acc);
-                        th[p][r] += sc * acc;
-                    }
-                }
-            }
-        }
-    }
-
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        double* lp_cols_row = ((MODE == 0 || MODE == 3) && a.lp_cols && valid[p]) ? a.lp_cols + idx[p] : nullptr;
-        lp_new[p] = eval_priors<KIND, DMAX>(a, th[p], lp_cols_row, a.stride);
-        prior_ok[p] = lp_new[p] != kNegInf;
-    }
-
-    if (MODE == 3) {
-#pragma unroll
-        for (int p = 0; p < PPT; ++p)
-            if (valid[p]) a.lp[idx[p]] = lp_new[p];
-        return;
-    }
-    if (MODE == 2) {
-#pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            if (valid[p]) {
-#pragma unroll
-                for (int c = 0; c < DMAX; ++c)
-                    if (c < d) a.new_params[(int64_t)c * a.stride + idx[p]] = th[p][c];
-                a.new_lp[idx[p]] = lp_new[p];
-            }
-        }
-        return;
-    }
-
-    // rows with a -inf prior are not evaluated (quirk Q6)
-    bool run[PPT], not_pd[PPT];
-    bool run_any = false;
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        run[p] = valid[p] && prior_ok[p];
-        not_pd[p] = false;
-        run_any = run_any || run[p];
-    }
-    if (KIND == K_LINEAR_NORMAL) {
-        ll_linear_normal<DMAX, PPT>(a, th, run_any, reinterpret_cast<double2*>(sdata), ll_new);
-    } else {
-#pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            if (KIND == K_SPRING_NORMAL) ll_new[p] = ll_spring_normal<DMAX>(a, th[p], run[p], sdata);
-            else if (KIND == K_IDENTITY_NORMAL) ll_new[p] = ll_identity_normal<DMAX>(a, th[p], run[p], sdata);
-            else ll_new[p] = ll_linear_mvn<DMAX>(a, th[p], run[p], sdata, not_pd[p]);
-        }
-    }
+    const int64_t per_tile = (int64_t)TPB * PPT;
+    const int64_t n_tiles = (a.n + per_tile - 1) / per_tile;
     int flag = 0;
     int n_acc = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t idx[PPT];
+        bool valid[PPT];
+        double th[PPT][DMAX];
+        double ll_old[PPT], lp_old[PPT], lp_new[PPT], ll_new[PPT];
+        bool prior_ok[PPT];
 #pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        if (!run[p]) ll_new[p] = 0.0;       // placeholder (vector_mcmc.py:207)
-        if (run[p] && ll_new[p] != ll_new[p]) flag |= SMCB_FLAG_MODEL_NAN;
-        if (run[p] && not_pd[p]) flag |= SMCB_FLAG_COV_NOT_PD;
-        if (MODE == 0) {
-            if (valid[p]) {
-                a.ll[idx[p]] = ll_new[p];
-                a.lp[idx[p]] = lp_new[p];
-                if (!prior_ok[p]) flag |= SMCB_FLAG_PRIOR_OOB;
+        for (int p = 0; p < PPT; ++p) {
+            const int64_t i = tile * per_tile + (int64_t)p * TPB + threadIdx.x;
+            valid[p] = i < a.n;
+            idx[p] = valid[p] ? i : 0;
+            const double* pc = a.params + idx[p];
+#pragma unroll
+            for (int c = 0; c < DMAX; ++c) {
+                th[p][c] = (EXACT || c < d) ? *pc : 0.0;
+                pc += a.stride;
+            }
+            ll_old[p] = lp_old[p] = 0.0;
+            if (MODE == 1) {
+                ll_old[p] = a.ll[idx[p]];
+                lp_old[p] = a.lp[idx[p]];
+            }
+        }
+
+        if (MODE == 1 || MODE == 2) {
+            // proposal x' = x + sqrt(s) L z, column-outer: z_j updates rows j..d-1, which are
+            // independent accumulators (the parameter registers themselves)
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                const Philox rng(a.rng.seed);
+                const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[p]);
+                const double* zt = (a.rng.mode == 1) ? a.rng.z + idx[p] * d : nullptr;
+#pragma unroll
+                for (int c = 0; c < DMAX; c += 4) {
+                    if (EXACT || c < d) {
+                        double z4[4];
+                        if (a.rng.mode == 1) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) z4[q] = (c + q < d) ? zt[c + q] : 0.0;
+                        } else {
+                            const uint4 r = rng(pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
+                            normal_pair(r.x, r.y, z4[0], z4[1]);
+                            normal_pair(r.z, r.w, z4[2], z4[3]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = c + q;
+                            if (j < DMAX) {
+                                const double zs = sc * z4[q];
+                                if (DMAX == 1) {
+                                    th[p][0] = fma(sLt[0], zs, th[p][0]);
+                                } else {
+#pragma unroll
+                                    for (int r2 = (j & ~1); r2 < DMAX; r2 += 2) {   // above the diagonal: 0
+                                        const double2 l2 = *reinterpret_cast<const double2*>(&sLt[j * DMAX + r2]);
+                                        th[p][r2] = fma(l2.x, zs, th[p][r2]);
+                                        if (r2 + 1 < DMAX) th[p][r2 + 1] = fma(l2.y, zs, th[p][r2 + 1]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            double* lp_cols_row =
+                ((MODE == 0 || MODE == 3) && a.lp_cols && valid[p]) ? a.lp_cols + idx[p] : nullptr;
+            lp_new[p] = eval_priors<KIND, DMAX, EXACT>(a, th[p], lp_cols_row, a.stride);
+            prior_ok[p] = lp_new[p] != kNegInf;
+        }
+
+        if (MODE == 3) {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p)
+                if (valid[p]) a.lp[idx[p]] = lp_new[p];
+            continue;
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                if (valid[p]) {
+                    double* pc = a.new_params + idx[p];
+#pragma unroll
+                    for (int c = 0; c < DMAX; ++c) {
+                        if (EXACT || c < d) *pc = th[p][c];
+                        pc += a.stride;
+                    }
+                    a.new_lp[idx[p]] = lp_new[p];
+                }
             }
             continue;
         }
-        // acceptance (vector_mcmc.py:131-151 with evaluate_log_posterior = path.logpdf)
-        if (valid[p]) {
-            const int64_t i = idx[p];
-            const double t_old = path_target(ll_old[p], lp_old[p], lp_old[p], a.phi, a.pe, a.qe);
-            const double t_new = path_target(ll_new[p], lp_new[p], lp_new[p], a.phi, a.pe, a.qe);
-            const double ratio = exp(t_new - t_old);
-            double u;
-            if (a.rng.mode == 1) {
-                u = a.rng.u[i];
-            } else {
-                const Philox rng(a.rng.seed);
-                const uint4 r = rng((uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
-                u = u01_53(r.x, r.y);
-            }
-            const bool rejected = ratio < u;     // NaN compares false -> accept, as numpy does
-            if (!rejected && !(run[p] && not_pd[p])) {
+
+        // rows with a -inf prior are not evaluated (quirk Q6)
+        bool run[PPT], not_pd[PPT];
+        bool run_any = false;
 #pragma unroll
-                for (int c = 0; c < DMAX; ++c)
-                    if (c < d) a.params[(int64_t)c * a.stride + i] = th[p][c];
-                a.ll[i] = ll_new[p];
-                a.lp[i] = lp_new[p];
-                a.moved[i] = 1;
-                ++n_acc;
+        for (int p = 0; p < PPT; ++p) {
+            run[p] = valid[p] && prior_ok[p];
+            not_pd[p] = false;
+            run_any = run_any || run[p];
+        }
+        if (KIND == K_LINEAR_NORMAL) {
+            ll_linear_normal<DMAX, PPT>(a, th, run_any, resident, sdata, ll_new);
+        } else {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                if (KIND == K_SPRING_NORMAL) ll_new[p] = ll_spring_normal<DMAX>(a, th[p], run[p], resident, sdata);
+                else if (KIND == K_IDENTITY_NORMAL) ll_new[p] = ll_identity_normal<DMAX, EXACT>(a, th[p], run[p], sdata);
+                else ll_new[p] = ll_linear_mvn<DMAX>(a, th[p], run[p], sdata, not_pd[p]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            if (!run[p]) ll_new[p] = 0.0;       // placeholder (vector_mcmc.py:207)
+            if (run[p] && ll_new[p] != ll_new[p]) flag |= SMCB_FLAG_MODEL_NAN;
+            if (run[p] && not_pd[p]) flag |= SMCB_FLAG_COV_NOT_PD;
+            if (MODE == 0) {
+                if (valid[p]) {
+                    a.ll[idx[p]] = ll_new[p];
+                    a.lp[idx[p]] = lp_new[p];
+                    if (!prior_ok[p]) flag |= SMCB_FLAG_PRIOR_OOB;
+                }
+                continue;
+            }
+            // acceptance (vector_mcmc.py:131-151 with evaluate_log_posterior = path.logpdf)
+            if (valid[p]) {
+                const int64_t i = idx[p];
+                const double t_old = path_target(ll_old[p], lp_old[p], lp_old[p], a.phi, a.pe, a.qe);
+                const double t_new = path_target(ll_new[p], lp_new[p], lp_new[p], a.phi, a.pe, a.qe);
+                const double ratio = exp(t_new - t_old);
+                double u;
+                if (a.rng.mode == 1) {
+                    u = a.rng.u[i];
+                } else {
+                    const Philox rng(a.rng.seed);
+                    const uint4 r = rng((uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
+                    u = u01_53(r.x, r.y);
+                }
+                const bool rejected = ratio < u;     // NaN compares false -> accept, as numpy does
+                if (!rejected && !(run[p] && not_pd[p])) {
+                    double* pc = a.params + i;
+#pragma unroll
+                    for (int c = 0; c < DMAX; ++c) {
+                        if (EXACT || c < d) *pc = th[p][c];
+                        pc += a.stride;
+                    }
+                    a.ll[i] = ll_new[p];
+                    a.lp[i] = lp_new[p];
+                    a.moved[i] = 1;
+                    ++n_acc;
+                }
             }
         }
     }
     if (flag) atomicOr(a.flags, flag);
-    if (MODE == 0) return;
-    // accept count: warp shuffle reduction, one atomic per warp
+    if (MODE != 1) return;
+    // accept count: warp shuffle reduction, one atomic per warp per launch
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
     if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
@@ -560,8 +605,8 @@ __global__ void __launch_bounds__(256) sample_priors_kernel(ColPriors cp, int d,
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
         for (int c = 0; c < d; c += 2) {
             const uint4 r = rng((uint64_t)(id_offset + i), (uint32_t)(c >> 1), stream_id);
-            params[(int64_t)c * stride + i] = cp.a[c] + cp.b[c] * u01_53(r.x, r.y);
-            if (c + 1 < d) params[(int64_t)(c + 1) * stride + i] = cp.a[c + 1] + cp.b[c + 1] * u01_53(r.z, r.w);
+            params[(int64_t)c * stride + i] = cp.a[c] + cp.hi[c] * u01_53(r.x, r.y);
+            if (c + 1 < d) params[(int64_t)(c + 1) * stride + i] = cp.a[c + 1] + cp.hi[c + 1] * u01_53(r.z, r.w);
         }
     }
 }
@@ -569,16 +614,30 @@ __global__ void __launch_bounds__(256) sample_priors_kernel(ColPriors cp, int d,
 // ---- host side ------------------------------------------------------------------------------------------
 static int build_col_priors(const smcb_problem_t* p, ColPriors* cp) {
     memset(cp, 0, sizeof(*cp));
+    const double inf = __builtin_huge_val();
+    for (int c = 0; c < SMCB_MAX_PARAMS; ++c) {
+        cp->prior_of_col[c] = -1;
+        cp->lo[c] = -inf;
+        cp->hi[c] = inf;
+    }
     int col = 0;
+    double total = 0.0;
     for (int q = 0; q < p->n_priors; ++q) {
         const smcb_prior_t& pr = p->priors[q];
         if (pr.kind == SMCB_PRIOR_UNIFORM || pr.kind == SMCB_PRIOR_IMPROPER_UNIFORM) {
             if (col >= SMCB_MAX_PARAMS) return -1;
-            cp->kind[col] = (int8_t)pr.kind;
             cp->prior_of_col[col] = (int8_t)q;
-            cp->a[col] = pr.a;
-            cp->b[col] = pr.b;
+            if (pr.kind == SMCB_PRIOR_UNIFORM) {
+                cp->a[col] = pr.a;
+                cp->lo[col] = 0.0;
+                cp->hi[col] = pr.b;
+            } else {
+                cp->a[col] = 0.0;
+                cp->lo[col] = pr.a;
+                cp->hi[col] = pr.b;
+            }
             cp->logp[col] = pr.logp_in;
+            total += pr.logp_in;
             col += 1;
         } else if (pr.kind == SMCB_PRIOR_IMPROPER_COV) {
             if (cp->n_cov >= 2 || pr.ncols < 1 || pr.ncols > 3) return -1;
@@ -587,10 +646,12 @@ static int build_col_priors(const smcb_problem_t* p, ColPriors* cp) {
             cp->cov_prior[cp->n_cov] = q;
             cp->n_cov += 1;
             col += pr.ncols * (pr.ncols + 1) / 2;
+            if (col > SMCB_MAX_PARAMS) return -1;
         } else {
             return -1;
         }
     }
+    cp->logp_total = total;
     return col;
 }
 
@@ -601,29 +662,55 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
     else if (p->model_id == SMCB_MODEL_LINEAR) data = (size_t)kChunk * 16;
     else if (p->model_id == SMCB_MODEL_SPRING_MASS) data = (size_t)kChunk * 8;
     else data = (size_t)SMCB_MAX_PARAMS * 8;
-    return (size_t)((d * d + 1) & ~1) * 8 + data + 16;
+    (void)d;
+    return data + 16;      // + DMAX*DMAX doubles for the Cholesky factor, added per instantiation
+}
+
+template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT>
+static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
+    const size_t smem = mh_smem_bytes(&a.prob) + (size_t)DMAX * DMAX * sizeof(double);
+    // persistent grid: resident blocks per SM (occupancy query, cached) x SM count
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT>, TPB,
+                                                          smem) != cudaSuccess || nb < 1)
+            nb = 1;
+        blocks_per_sm = nb;
+    }
+    const int64_t per_tile = (int64_t)TPB * PPT;
+    const int64_t n_tiles = (a.n + per_tile - 1) / per_tile;
+    // persistent blocks (stage L / data once, loop over tiles) for the bandwidth-bound identity
+    // model; one tile per block for the FP64-bound models, where the hardware block scheduler
+    // balances the tail better than a static tile loop (SMCB_PERSIST overrides: tuning aid)
+    static const int persist_env = getenv("SMCB_PERSIST") ? atoi(getenv("SMCB_PERSIST")) : -1;
+    const bool persist = persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL);
+    const int64_t cap = persist ? (int64_t)kNumSMs * blocks_per_sm : n_tiles;
+    const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
+    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT><<<grid, TPB, smem, s>>>(a);
+    return check_launch("mh_kernel");
 }
 
 template <int KIND, int DMAX, int MODE, int TPB, int PPT>
 static int launch_cfg(const MhArgs& a, cudaStream_t s) {
-    const size_t smem = mh_smem_bytes(&a.prob);
-    const int64_t per_block = (int64_t)TPB * PPT;
-    const unsigned grid = (unsigned)((a.n + per_block - 1) / per_block);
-    mh_kernel<KIND, DMAX, MODE, TPB, PPT><<<grid, TPB, smem, s>>>(a);
-    return check_launch("mh_kernel");
+    // exact-width instantiations (no per-column bounds checks) where they pay
+    constexpr bool kHasExact = (KIND == K_IDENTITY_NORMAL && DMAX >= 8) || (KIND != K_LINEAR_MVN && DMAX == 2);
+    if constexpr (kHasExact) {
+        if (a.prob.n_params == DMAX) return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true>(a, s);
+    }
+    return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, false>(a, s);
 }
 
 template <int KIND, int DMAX, int MODE>
 static int launch_one(const MhArgs& a, cudaStream_t s) {
     if constexpr (KIND == K_LINEAR_NORMAL && (MODE == 0 || MODE == 1)) {
         // several particles per thread amortise the shared-memory data reads; keep at least
-        // ~4 blocks per SM so small problems still fill the chip
+        // ~4 tiles per SM so small problems still fill the chip
         static const int cfg = getenv("SMCB_LINEAR_CFG") ? atoi(getenv("SMCB_LINEAR_CFG")) : -1;   // tuning aid
         if (cfg == 0) return launch_cfg<KIND, DMAX, MODE, kMhThreads, 1>(a, s);
         if (cfg == 1) return launch_cfg<KIND, DMAX, MODE, 128, 2>(a, s);
         if (cfg == 2) return launch_cfg<KIND, DMAX, MODE, 128, 4>(a, s);
         if (cfg == 3) return launch_cfg<KIND, DMAX, MODE, 256, 4>(a, s);
-        if (cfg == 4) return launch_cfg<KIND, DMAX, MODE, 256, 2>(a, s);
         if (a.n >= (int64_t)kNumSMs * 4 * 1024) return launch_cfg<KIND, DMAX, MODE, 256, 4>(a, s);
         if (a.n >= (int64_t)kNumSMs * 4 * 512) return launch_cfg<KIND, DMAX, MODE, 128, 4>(a, s);
         if (a.n >= (int64_t)kNumSMs * 4 * 256) return launch_cfg<KIND, DMAX, MODE, 128, 2>(a, s);
@@ -850,9 +937,9 @@ extern "C" int smcb_sample_priors(const smcb_problem_t* prob, double* params, in
         set_error("Num prior distributions != num input params");
         return SMCB_ERR_ARG;
     }
-    for (int c = 0; c < cols; ++c) {
-        if (cp.kind[c] != SMCB_PRIOR_UNIFORM) {
-            set_error("device prior sampling supports scipy-uniform priors only (column %d)", c);
+    for (int q = 0; q < prob->n_priors; ++q) {
+        if (prob->priors[q].kind != SMCB_PRIOR_UNIFORM) {
+            set_error("device prior sampling supports scipy-uniform priors only (prior %d)", q);
             return SMCB_ERR_UNSUPPORTED;
         }
     }
