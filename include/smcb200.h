@@ -112,6 +112,20 @@ typedef struct smcb_rng {
     const double* u;     /* replay: device (N) */
 } smcb_rng_t;
 
+/* cross-GPU accept-count exchange fused into the Metropolis kernel (multi-GPU only).  Each rank
+ * owns a symmetric `slots` buffer of SMCB_MAX_MCMC_STEPS x SMCB_MAX_RANKS uint64 mapped by
+ * every peer.  The last block of step k stores (gen << 32 | local count) into slot [k][rank] of
+ * EVERY rank over NVLink; the prologue of step k+1 waits until all `world` slots of step k carry
+ * `gen` and sums them -- no separate collective launch.  `gen` increases with every mutate call. */
+#define SMCB_MAX_RANKS 8
+typedef struct smcb_xchg {
+    int32_t world, rank;
+    uint64_t gen;
+    uint64_t* peer_slots[SMCB_MAX_RANKS];   /* device pointers to each rank's slots buffer */
+    int64_t* global_counts;                 /* device, SMCB_MAX_MCMC_STEPS: summed counts (local cache) */
+    uint32_t* ticket;                       /* device, zero-initialised block ticket */
+} smcb_xchg_t;
+
 /* ---- library --------------------------------------------------------------------- */
 int smcb_version(void);
 const char* smcb_last_error(void);
@@ -225,6 +239,12 @@ int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path, double* pa
                  int64_t n, int64_t n_global, double* ll, double* lp, uint8_t* moved,
                  const double* chol, int64_t* accept_counts, int32_t step, const smcb_rng_t* rng,
                  int32_t* flags, void* stream);
+/* same step with the cross-GPU accept-count exchange fused in (x->world > 1); accept_counts
+ * then holds the LOCAL counts, x->global_counts the global ones. */
+int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride,
+                      int64_t n, int64_t n_global, double* ll, double* lp, uint8_t* moved,
+                      const double* chol, int64_t* accept_counts, int32_t step, const smcb_rng_t* rng,
+                      int32_t* flags, const smcb_xchg_t* x, void* stream);
 /* fraction of particles that moved (mutator.py:69-71): count of non-zero bytes */
 int smcb_count_moved(const uint8_t* moved, int64_t n, int64_t* count_out, void* ws, void* stream);
 /* initial particles from uniform priors on the device (vector_mcmc.py:91-96) */

@@ -44,6 +44,14 @@ class Path(C.Structure):
     _fields_ = [("phi", C.c_double), ("phi_prev", C.c_double), ("lam", C.c_double)]
 
 
+MAX_RANKS = 8
+
+
+class Xchg(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("gen", C.c_uint64),
+                ("peer_slots", C.c_void_p * MAX_RANKS), ("global_counts", C.c_void_p), ("ticket", C.c_void_p)]
+
+
 class Rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("seed", C.c_uint64), ("stream", C.c_uint64),
                 ("id_offset", C.c_int64), ("z", C.c_void_p), ("u", C.c_void_p)]
@@ -88,6 +96,8 @@ SIGNATURES = {
     "smcb_log_priors": [_PP(Problem), _P, _I64, _I64, _P, _P, _P],
     "smcb_mh_step": [_PP(Problem), _PP(Path), _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I32,
                      _PP(Rng), _P, _P],
+    "smcb_mh_step_xchg": [_PP(Problem), _PP(Path), _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I32,
+                          _PP(Rng), _P, _PP(Xchg), _P],
     "smcb_count_moved": [_P, _I64, _P, _P, _P],
     "smcb_sample_priors": [_PP(Problem), _P, _I64, _I64, _U64, _U64, _I64, _P],
     "smcb_mh_propose": [_PP(Problem), _P, _I64, _I64, _I64, _P, _P, _I32, _PP(Rng), _P, _P, _P],

@@ -93,36 +93,51 @@ __device__ __forceinline__ Lse lse_merge(const Lse& a, const Lse& b) {
     r.s2 = a.s2 * (ea * ea) + b.s2 * (eb * eb);
     return r;
 }
-__device__ __forceinline__ Lse warp_lse(Lse v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        Lse t;
-        t.m = __shfl_xor_sync(0xffffffffu, v.m, o);
-        t.s1 = __shfl_xor_sync(0xffffffffu, v.s1, o);
-        t.s2 = __shfl_xor_sync(0xffffffffu, v.s2, o);
-        // order the operands by lane so both partners compute the identical value
-        const bool low = (threadIdx.x & o) == 0;
-        v = low ? lse_merge(v, t) : lse_merge(t, v);
-    }
-    return v;
-}
-// block merge, result valid in thread 0. sh >= 96 doubles.
-__device__ __forceinline__ Lse block_lse(Lse v, double* sh) {
+// Block merge, max first: the block maximum is an exact fmax reduction, every thread then
+// rescales its own sums with ONE independent exp, and the sums are plain ordered reductions
+// (a tree of pairwise lse_merge calls would chain ~20 dependent exps).  Result valid in
+// thread 0; sh >= 32 doubles.
+__device__ __forceinline__ double block_max_all(double v, double* sh) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    v = warp_lse(v);
+    v = warp_max(v);
     __syncthreads();
-    if (lane == 0) {
-        sh[wid] = v.m;
-        sh[32 + wid] = v.s1;
-        sh[64 + wid] = v.s2;
-    }
+    if (lane == 0) sh[wid] = v;
     __syncthreads();
     const int nw = (blockDim.x + 31) >> 5;
-    if (wid == 0) {
-        v = (lane < nw) ? Lse{sh[lane], sh[32 + lane], sh[64 + lane]} : lse_empty();
-        v = warp_lse(v);
+    double m = kNegInf;
+    for (int k = 0; k < nw; ++k) m = fmax(m, sh[k]);      // same value in every thread
+    return m;
+}
+__device__ __forceinline__ Lse block_lse(Lse v, double* sh) {
+    const double bm = block_max_all(v.m, sh);
+    const double e = (v.m == kNegInf) ? 0.0 : exp(v.m - bm);
+    Lse r;
+    r.m = bm;
+    r.s1 = block_sum(v.s1 * e, sh);
+    r.s2 = block_sum(v.s2 * (e * e), sh);
+    return r;
+}
+// Merge of n partial triples stored as (m, s1, s2) rows by ONE warp (all 32 lanes call):
+// lane l handles rows l, l+32, ... in order.  Deterministic; result in every lane.
+__device__ __forceinline__ Lse warp_merge_partials(const volatile double* parts, int n) {
+    const int lane = threadIdx.x & 31;
+    double m = kNegInf;
+    for (int b = lane; b < n; b += 32) m = fmax(m, parts[3 * b]);
+    m = warp_max(m);
+    double s1 = 0.0, s2 = 0.0;
+    if (m != kNegInf) {
+        for (int b = lane; b < n; b += 32) {
+            const double mb = parts[3 * b];
+            const double e = (mb == kNegInf) ? 0.0 : exp(mb - m);
+            s1 += parts[3 * b + 1] * e;
+            s2 += parts[3 * b + 2] * (e * e);
+        }
     }
-    return v;
+    Lse r;
+    r.m = m;
+    r.s1 = warp_sum(s1);
+    r.s2 = warp_sum(s2);
+    return r;
 }
 // add one value with a running max (rescale only when the max moves)
 __device__ __forceinline__ void lse_push4(Lse& acc, double v0, double v1, double v2, double v3) {

@@ -57,6 +57,7 @@ struct MhArgs {
     double* lp_cols;      // init / priors only (optional)
     double* new_params;   // propose only
     double* new_lp;       // propose only
+    smcb_xchg_t x;        // world <= 1: no cross-GPU exchange
 };
 
 // covariance scale after the first `step` Metropolis steps (vector_mcmc.py:55-60):
@@ -65,6 +66,42 @@ __device__ __forceinline__ double cov_scale_sqrt(const unsigned long long* count
     double s = 1.0;
     for (int k = 0; k < step; ++k) {
         const double acc = (double)counts[k];
+        if (acc < n_global * 0.3) s = s * 1 / 5;
+        if (acc > n_global * 0.7) s = s * 2;
+    }
+    return sqrt(s);
+}
+
+// ---- cross-GPU accept-count exchange (fused collective over NVLink peer memory) ----------------
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// global accept count of step j: local cache if already summed, else wait for every rank's slot
+__device__ __forceinline__ double xchg_global_count(const smcb_xchg_t& x, int j, bool latest) {
+    if (!latest) return (double)x.global_counts[j];
+    const unsigned long long* mine =
+        reinterpret_cast<const unsigned long long*>(x.peer_slots[x.rank]) + (size_t)j * SMCB_MAX_RANKS;
+    unsigned long long total = 0;
+    for (int r = 0; r < x.world; ++r) {
+        unsigned long long v = ld_sys(mine + r);
+        while ((v >> 32) != x.gen) {
+            __nanosleep(64);
+            v = ld_sys(mine + r);
+        }
+        total += v & 0xffffffffull;
+    }
+    x.global_counts[j] = (long long)total;     // every block writes the same value
+    return (double)total;
+}
+__device__ __forceinline__ double cov_scale_sqrt_xchg(const smcb_xchg_t& x, int step, double n_global) {
+    double s = 1.0;
+    for (int k = 0; k < step; ++k) {
+        const double acc = xchg_global_count(x, k, k == step - 1);
         if (acc < n_global * 0.3) s = s * 1 / 5;
         if (acc > n_global * 0.7) s = s * 2;
     }
@@ -347,7 +384,9 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             const int j = e / DMAX, r = e - j * DMAX;
             sLt[e] = (r < d && j <= r) ? a.chol[r * d + j] : 0.0;
         }
-        if (threadIdx.x == 0) sh_scale = cov_scale_sqrt(a.accept_counts, a.step, a.n_global);
+        if (threadIdx.x == 0)
+            sh_scale = (a.x.world > 1) ? cov_scale_sqrt_xchg(a.x, a.step, a.n_global)
+                                       : cov_scale_sqrt(a.accept_counts, a.step, a.n_global);
     }
     if ((MODE == 0 || MODE == 1) && resident) stage_data<KIND>(a, sdata, 0, a.prob.n_data);
     __syncthreads();
@@ -521,6 +560,24 @@ mh_kernel(const __grid_constant__ MhArgs a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
     if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
+    if (a.x.world > 1) {
+        // the last block of the grid publishes this rank's count to every peer (P2P stores)
+        __shared__ bool is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(a.x.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (is_last && threadIdx.x < a.x.world) {
+            __threadfence();
+            const unsigned long long local = atomicAdd(a.accept_counts + a.step, 0ull);
+            const unsigned long long word = (a.x.gen << 32) | (local & 0xffffffffull);
+            st_sys(reinterpret_cast<unsigned long long*>(a.x.peer_slots[threadIdx.x]) +
+                       (size_t)a.step * SMCB_MAX_RANKS + a.x.rank,
+                   word);
+            __threadfence_system();
+            if (threadIdx.x == 0) *a.x.ticket = 0u;
+        }
+    }
 }
 
 // ---- un-fused pieces (torch-callable user models) ---------------------------------------------------
@@ -848,6 +905,32 @@ extern "C" int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path,
     a.lp = lp;
     a.moved = moved;
     a.flags = flags;
+    return dispatch<1>(a, as_stream(stream));
+}
+
+extern "C" int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* path, double* params,
+                                 int64_t stride, int64_t n, int64_t n_global, double* ll, double* lp,
+                                 uint8_t* moved, const double* chol, int64_t* accept_counts, int32_t step,
+                                 const smcb_rng_t* rng, int32_t* flags, const smcb_xchg_t* x, void* stream) {
+    MhArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = validate_problem(prob, &a.cp);
+    if (rc) return rc;
+    SMCB_REQUIRE(path && params && ll && lp && moved && chol && accept_counts && rng && flags && x, "NULL argument");
+    SMCB_REQUIRE(n > 0 && stride >= n && n_global >= n, "bad sizes");
+    SMCB_REQUIRE(step >= 0 && step < SMCB_MAX_MCMC_STEPS, "step out of range");
+    SMCB_REQUIRE(rng->mode == 0 || (rng->z && rng->u), "replay mode needs z and u tapes");
+    SMCB_REQUIRE(x->world >= 1 && x->world <= SMCB_MAX_RANKS && x->rank >= 0 && x->rank < x->world, "bad ranks");
+    SMCB_REQUIRE(x->world == 1 || (x->global_counts && x->ticket && x->gen > 0 && x->gen < (1ull << 32)),
+                 "exchange buffers required");
+    for (int r = 0; r < x->world && x->world > 1; ++r) SMCB_REQUIRE(x->peer_slots[r] != nullptr, "peer slot pointer is NULL");
+    fill_step_args(a, prob, path, stride, n, n_global, chol, accept_counts, step, rng);
+    a.params = params;
+    a.ll = ll;
+    a.lp = lp;
+    a.moved = moved;
+    a.flags = flags;
+    a.x = *x;
     return dispatch<1>(a, as_stream(stream));
 }
 

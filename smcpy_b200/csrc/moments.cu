@@ -39,13 +39,17 @@ __global__ void __launch_bounds__(kMomThreads) wsums1_kernel(const double* __res
     }
 }
 
-// out[j] = sum over blocks (in block order) of partials[b][j]
-__global__ void reduce_partials_kernel(const double* partials, int n_blocks, int n_vals, double* out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// out[j] = sum over blocks of partials[b][j]: one warp per output value, lane l adds blocks
+// l, l+32, ... in order, then a fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const double* partials, int n_blocks, int n_vals,
+                                                              double* out) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (j >= n_vals) return;
     double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += partials[(int64_t)b * n_vals + j];
-    out[j] = s;
+    for (int b = lane; b < n_blocks; b += 32) s += partials[(int64_t)b * n_vals + j];
+    s = warp_sum(s);
+    if (lane == 0) out[j] = s;
 }
 
 __global__ void mean_from_sums_kernel(const double* sums, int d, double* mean) {
@@ -244,7 +248,7 @@ extern "C" int smcb_weighted_sums1(const double* params, int64_t stride, const d
     else if (d <= 2) wsums1_kernel<2><<<dim3(grid, 1), kMomThreads, 0, s>>>(params, stride, w, n, d, partials);
     else if (d <= 4) wsums1_kernel<4><<<dim3(grid, 1), kMomThreads, 0, s>>>(params, stride, w, n, d, partials);
     else wsums1_kernel<8><<<dim3(grid, (d + 7) / 8), kMomThreads, 0, s>>>(params, stride, w, n, d, partials);
-    reduce_partials_kernel<<<(1 + d + 63) / 64, 64, 0, s>>>(partials, grid, 1 + d, sums_out);
+    reduce_partials_kernel<<<(1 + d + 3) / 4, 128, 0, s>>>(partials, grid, 1 + d, sums_out);
     return check_launch("wsums1_kernel");
 }
 
@@ -272,7 +276,7 @@ extern "C" int smcb_weighted_sums2(const double* params, int64_t stride, const d
     wsums2_kernel<<<grid, kMomThreads, smem, s>>>(params, stride, w, n, d, mean, partials);
     // packed block sums live after the per-block partials
     double* packed = partials + (int64_t)grid * nbu * 16;
-    reduce_partials_kernel<<<(nbu * 16 + 63) / 64, 64, 0, s>>>(partials, grid, nbu * 16, packed);
+    reduce_partials_kernel<<<(nbu * 16 + 3) / 4, 128, 0, s>>>(partials, grid, nbu * 16, packed);
     sums2_unpack_kernel<<<(d * d + 63) / 64, 64, 0, s>>>(packed, d, sums_out);
     return check_launch("wsums2_kernel");
 }

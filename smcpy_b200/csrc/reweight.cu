@@ -6,12 +6,16 @@
 //
 // Bytes per particle (algorithmic): partial pass reads ll, lp, log_w (24 B; 16 B when the
 // weights are uniform), finalize pass reads them again and writes log_w, w (16 B).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace smcb {
 
 constexpr int kRwThreads = 256;
 constexpr int kRwItems = 4;
+constexpr int kRwBlocksPerSM = 4;   // LSE passes: few fat blocks keep the finalizer's merge short
 
 struct RwIn {
     const double* ll;
@@ -73,14 +77,9 @@ __device__ __forceinline__ bool lse_partials_body(const RwIn& in, int64_t n, dou
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    // warp 0: lane l merges partials l, l+32, ... in order, then a fixed shuffle tree
+    // warp 0 merges the block partials (max first, then independent rescales, fixed order)
     if (threadIdx.x < 32) {
-        Lse a = lse_empty();
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) {
-            const volatile double* p = partials + 3 * b;
-            a = lse_merge(a, Lse{p[0], p[1], p[2]});
-        }
-        a = warp_lse(a);
+        const Lse a = warp_merge_partials(partials, (int)gridDim.x);
         if (threadIdx.x == 0) {
             out3[0] = a.m;
             out3[1] = a.s1;
@@ -242,6 +241,53 @@ __global__ void bisect_update_kernel(const double* parts, int n_parts, double ph
     bisect_advance(st, a, phi_old, target, n_global);
 }
 
+// The whole search in ONE cooperative launch (single GPU): persistent blocks, a grid-wide
+// barrier after each evaluation; every block merges the same block partials in the same order
+// and advances an identical copy of the scipy state machine, so no block ever disagrees about
+// the next evaluation point.  Partials are double-buffered by iteration parity and read with
+// volatile (L2) loads.
+__global__ void __launch_bounds__(kRwThreads) ess_bisect_coop_kernel(RwIn in, int64_t n, double phi_old,
+                                                                    double lambda, double target, double n_global,
+                                                                    double* st_out, double* partials, int max_iters) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[96];
+    __shared__ double st[16];
+    if (threadIdx.x == 0) {
+        st[0] = 1.0; st[1] = 0.0; st[2] = 0.0; st[3] = phi_old; st[4] = 1.0 - phi_old;
+        st[5] = 0.0; st[6] = 1.0; st[7] = 0.0; st[8] = 0.0; st[9] = 0.0;
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < max_iters; ++it) {
+        if (st[2] != 0.0) break;                       // identical in every block
+        const double x = st[6];
+        in.c.phi = x;
+        in.c.pe = fmin(1.0, x / lambda);
+        in.c.qe = fmax(0.0, (lambda - x) / lambda);
+        Lse acc = lse_empty();
+        int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n; i += 4 * stride)
+            lse_push4(acc, inc_value(in, i), inc_value(in, i + stride), inc_value(in, i + 2 * stride),
+                      inc_value(in, i + 3 * stride));
+        for (; i < n; i += stride) lse_push4(acc, inc_value(in, i), kNegInf, kNegInf, kNegInf);
+        acc = block_lse(acc, sh);
+        double* buf = partials + (size_t)(it & 1) * 3 * gridDim.x;
+        if (threadIdx.x == 0) {
+            buf[3 * blockIdx.x + 0] = acc.m;
+            buf[3 * blockIdx.x + 1] = acc.s1;
+            buf[3 * blockIdx.x + 2] = acc.s2;
+        }
+        grid.sync();
+        if (threadIdx.x < 32) {
+            const Lse m = warp_merge_partials(buf, (int)gridDim.x);
+            if (threadIdx.x == 0) bisect_advance(st, m, phi_old, target, n_global);
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 10) st_out[threadIdx.x] = st[threadIdx.x];
+}
+
 static RwIn make_in(const double* ll, const double* lp, const double* lq, const double* lw,
                     int64_t n_global, const smcb_path_t* path) {
     RwIn in;
@@ -272,7 +318,7 @@ extern "C" int smcb_reweight_partials(int64_t n, const double* ll, const double*
                                       double* partial_out, void* ws, void* stream) {
     SMCB_REQUIRE(n > 0 && ll && lp && path && partial_out && ws, "bad argument");
     RwIn in = make_in(ll, lp, lq, log_w_in, n_global, path);
-    const int grid = grid_for(n, kRwThreads, kRwItems, 8);
+    const int grid = grid_for(n, kRwThreads, kRwItems, kRwBlocksPerSM);
     char* w = (char*)ws;
     rw_partials_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(
         in, n, (double*)(w + kWsPartials), (unsigned int*)(w + kWsTickets), partial_out);
@@ -326,7 +372,7 @@ extern "C" int smcb_ess_partial(int64_t n, const double* ll, const double* lp, c
     smcb_path_t p{phi_old, phi_old, lambda};
     RwIn in = make_in(ll, lp, lq, nullptr, 1, &p);
     in.lp_const = lp_const;
-    const int grid = grid_for(n, kRwThreads, kRwItems, 8);
+    const int grid = grid_for(n, kRwThreads, kRwItems, kRwBlocksPerSM);
     char* w = (char*)ws;
     ess_eval_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(
         in, n, phi_old, lambda, 0.0, 0.0, const_cast<double*>(state), (double*)(w + kWsPartials),
@@ -355,14 +401,38 @@ extern "C" int smcb_ess_bisect(int64_t n, const double* ll, const double* lp, co
                                int64_t n_global, double* state, void* ws, void* stream) {
     SMCB_REQUIRE(n > 0 && ll && state && ws, "bad argument");
     SMCB_REQUIRE(phi_old >= 0.0 && phi_old < 1.0, "phi_old must be in [0, 1)");
-    int rc = smcb_ess_bisect_begin(phi_old, state, stream);
-    if (rc) return rc;
     smcb_path_t p{phi_old, phi_old, lambda};
     RwIn in = make_in(ll, lp, lq, nullptr, 1, &p);
     in.lp_const = lp_const;
-    const int grid = grid_for(n, kRwThreads, kRwItems, 8);
     char* w = (char*)ws;
-    const int iters = bisect_iters(phi_old);
+    int iters = bisect_iters(phi_old);
+    static int coop_blocks = -1;       // co-resident blocks of the cooperative kernel (0: unsupported)
+    if (coop_blocks < 0) {
+        int dev = 0, coop = 0, per_sm = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ess_bisect_coop_kernel, kRwThreads, 0);
+        coop_blocks = (coop && per_sm > 0) ? sms * (per_sm < 2 ? per_sm : 2) : 0;
+        if (getenv("SMCB_NO_COOP")) coop_blocks = 0;        // tuning aid: launch-chain version
+    }
+    if (coop_blocks > 0) {
+        int grid = grid_for(n, kRwThreads, kRwItems, 2);
+        if (grid > coop_blocks) grid = coop_blocks;
+        double* partials = (double*)(w + kWsPartials);
+        double ng = (double)n_global;
+        void* args[] = {&in, &n, &phi_old, &lambda, &target_ess, &ng, &state, &partials, &iters};
+        const cudaError_t e = cudaLaunchCooperativeKernel((const void*)ess_bisect_coop_kernel, dim3(grid),
+                                                          dim3(kRwThreads), args, 0, as_stream(stream));
+        if (e != cudaSuccess) {
+            set_error("ess_bisect_coop_kernel: %s", cudaGetErrorString(e));
+            return SMCB_ERR_CUDA;
+        }
+        return SMCB_OK;
+    }
+    int rc = smcb_ess_bisect_begin(phi_old, state, stream);
+    if (rc) return rc;
+    const int grid = grid_for(n, kRwThreads, kRwItems, kRwBlocksPerSM);
     for (int it = 0; it < iters; ++it) {
         ess_eval_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(
             in, n, phi_old, lambda, target_ess, (double)n_global, state, (double*)(w + kWsPartials),

@@ -46,6 +46,59 @@ class Runtime:
         return self._ws
 
 
+class AcceptExchange:
+    """Symmetric-memory buffers for the accept-count exchange fused into the Metropolis kernel
+    (smcb_xchg_t).  One per process; falls back to NCCL all-reduce (None) if symmetric memory
+    cannot be set up."""
+    _inst = None
+    _failed = False
+
+    def __init__(self):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        rank, world = dist_info()
+        dv = Runtime.get().device
+        self.slots = symm_mem.empty(_lib.MAX_MCMC_STEPS * _lib.MAX_RANKS, dtype=torch.int64, device=dv)
+        self.slots.zero_()
+        self.handle = symm_mem.rendezvous(self.slots, dist.group.WORLD)
+        self.global_counts = torch.zeros(_lib.MAX_MCMC_STEPS, dtype=torch.int64, device=dv)
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=dv)
+        self.gen = 0
+        x = _lib.Xchg()
+        x.world, x.rank = world, rank
+        for r in range(world):
+            x.peer_slots[r] = int(self.handle.buffer_ptrs[r])
+        x.global_counts = self.global_counts.data_ptr()
+        x.ticket = self.ticket.data_ptr()
+        self.x = x
+        torch.cuda.synchronize()
+        dist.barrier()                       # every rank's slots are zeroed before anyone publishes
+
+    @classmethod
+    def get(cls):
+        import os
+        if cls._failed or os.environ.get("SMCB_NO_XCHG"):
+            return None
+        _, world = dist_info()
+        if world < 2 or world > _lib.MAX_RANKS:
+            return None
+        if cls._inst is None:
+            try:
+                cls._inst = AcceptExchange()
+            except Exception as e:            # pragma: no cover - depends on the box
+                warnings.warn("symmetric-memory accept-count exchange unavailable (%s); using NCCL all-reduce" % e)
+                cls._failed = True
+                return None
+        return cls._inst
+
+    def next_gen(self):
+        self.gen += 1
+        if self.gen >= (1 << 32) - 1:
+            raise RuntimeError("accept-count exchange generation overflow")
+        self.x.gen = self.gen
+        return self.x
+
+
 def dist_info():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -328,7 +381,7 @@ def find_phi(st, spec, phi_old, target_ess, lam=1.0):
     if world == 1:
         with _timed("bisect"):
             call("smcb_ess_bisect", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
-                 float(target_ess), st.n_global, ptr(st.bis), ptr(st.ws), s, launches=1 + bisect_iters(phi_old))
+                 float(target_ess), st.n_global, ptr(st.bis), ptr(st.ws), s, launches=1)
     else:
         call("smcb_ess_bisect_begin", float(phi_old), ptr(st.bis), s)
         part = st.scalars[8:11]
@@ -399,6 +452,11 @@ def resample(st, kernel, resample_rng, warn_threshold):
     n = st.n
     host_rng = isinstance(kernel.rng, np.random.Generator)
     kind = getattr(resample_rng, "kind", None)
+    with _timed("resample"):
+        return _resample_local(st, kernel, resample_rng, warn_threshold, n, host_rng, kind)
+
+
+def _resample_local(st, kernel, resample_rng, warn_threshold, n, host_rng, kind):
     if host_rng or kind is None:
         u1 = np.asarray(resample_rng(kernel, n), dtype=np.float64)
         idx = resample_indices(st, dev(u1), _lib.SCAN_SEQUENTIAL)
@@ -514,6 +572,8 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
     r = _lib.Rng()
     r.id_offset = st.id_offset
     keep = []
+    xchg = AcceptExchange.get() if (world > 1 and spec.fused) else None
+    xs = xchg.next_gen() if xchg is not None else None
     for k in range(num_samples):
         if host_rng:
             z = dev(rng.normal(0, 1, (st.n, st.d)))
@@ -522,7 +582,13 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
             r.mode, r.z, r.u = 1, z.data_ptr(), u.data_ptr()
         else:
             r.mode, r.seed, r.stream = 0, rng.seed, rng.next_stream()
-        if spec.fused:
+        if spec.fused and xs is not None:
+            with _timed("mh_step"):
+                call("smcb_mh_step_xchg", C.byref(spec.c), C.byref(path), ptr(st.cols), st.n, st.n, st.n_global,
+                     ptr(st.ll), ptr(st.lp), ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), k, C.byref(r),
+                     ptr(st.flags), C.byref(xs), s)
+            continue
+        elif spec.fused:
             with _timed("mh_step"):
                 call("smcb_mh_step", C.byref(spec.c), C.byref(path), ptr(st.cols), st.n, st.n, st.n_global,
                      ptr(st.ll), ptr(st.lp), ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), k, C.byref(r),

@@ -35,6 +35,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(L.Prior) == 32
     assert ctypes.sizeof(L.Path) == 24
     assert ctypes.sizeof(L.Rng) == 48
+    assert ctypes.sizeof(L.Xchg) == 8 + 8 + 8 * 8 + 8 + 8
     # 8 ints + sigma + 8 args + 2 ptrs + 6 doubles + 6 ints + priors
     assert ctypes.sizeof(L.Problem) == 32 + 8 + 64 + 16 + 48 + 24 + 32 * 32
 
