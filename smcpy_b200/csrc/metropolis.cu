@@ -367,11 +367,14 @@ __host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt) {
 
 // mode: 0 = init (evaluate incoming particles), 1 = fused Metropolis step, 2 = propose only,
 //       3 = log-priors only.  EXACT: n_params == DMAX (drops every per-column bounds check).
-template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT>
+//       TMA: the next tile's d+2 column segments are bulk-copied (cp.async.bulk + mbarrier) into
+//       a shared-memory stage by one elected thread while the block computes the current tile.
+template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false>
 __global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double sh_scale;
+    __shared__ __align__(8) uint64_t mbar;
     const int d = EXACT ? DMAX : a.prob.n_params;
     // Cholesky factor transposed and zero-padded to DMAX: sLt[j * DMAX + r] = L[r][j], so column j
     // is contiguous (LDS.128) and the unrolled update needs no bounds checks
@@ -396,27 +399,59 @@ mh_kernel(const __grid_constant__ MhArgs a) {
     const int64_t n_tiles = (a.n + per_tile - 1) / per_tile;
     int flag = 0;
     int n_acc = 0;
+    // TMA stage: (d + 2) column segments of TPB doubles, after the data staging area
+    double* stage = sdata + 64;
+    uint32_t tma_phase = 0;
+    auto tma_issue = [&](int64_t tile) {          // one elected thread
+        const int64_t base = tile * per_tile;
+        const uint32_t cnt = (uint32_t)((a.n - base < per_tile) ? (a.n - base) : per_tile);
+        const uint32_t bytes = cnt * 8u;
+        fence_proxy_async();                       // generic-proxy reads of the stage are done
+        mbar_expect_tx(&mbar, bytes * (uint32_t)(d + 2));
+        for (int c = 0; c < d; ++c) tma_load_1d(stage + c * TPB, a.params + (int64_t)c * a.stride + base, bytes, &mbar);
+        tma_load_1d(stage + d * TPB, a.ll + base, bytes, &mbar);
+        tma_load_1d(stage + (d + 1) * TPB, a.lp + base, bytes, &mbar);
+    };
+    if (TMA) {
+        if (threadIdx.x == 0) mbar_init(&mbar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) tma_issue(blockIdx.x);
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int64_t idx[PPT];
         bool valid[PPT];
         double th[PPT][DMAX];
         double ll_old[PPT], lp_old[PPT], lp_new[PPT], ll_new[PPT];
         bool prior_ok[PPT];
+        if (TMA) {
+            const int64_t i = tile * per_tile + threadIdx.x;
+            valid[0] = i < a.n;
+            idx[0] = valid[0] ? i : 0;
+            mbar_wait(&mbar, tma_phase);
+            tma_phase ^= 1u;
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            const int64_t i = tile * per_tile + (int64_t)p * TPB + threadIdx.x;
-            valid[p] = i < a.n;
-            idx[p] = valid[p] ? i : 0;
-            const double* pc = a.params + idx[p];
+            for (int c = 0; c < DMAX; ++c) th[0][c] = (EXACT || c < d) ? stage[c * TPB + threadIdx.x] : 0.0;
+            ll_old[0] = stage[d * TPB + threadIdx.x];
+            lp_old[0] = stage[(d + 1) * TPB + threadIdx.x];
+            __syncthreads();                       // the whole block has drained the stage
+            if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) tma_issue(tile + gridDim.x);
+        } else {
 #pragma unroll
-            for (int c = 0; c < DMAX; ++c) {
-                th[p][c] = (EXACT || c < d) ? *pc : 0.0;
-                pc += a.stride;
-            }
-            ll_old[p] = lp_old[p] = 0.0;
-            if (MODE == 1) {
-                ll_old[p] = a.ll[idx[p]];
-                lp_old[p] = a.lp[idx[p]];
+            for (int p = 0; p < PPT; ++p) {
+                const int64_t i = tile * per_tile + (int64_t)p * TPB + threadIdx.x;
+                valid[p] = i < a.n;
+                idx[p] = valid[p] ? i : 0;
+                const double* pc = a.params + idx[p];
+#pragma unroll
+                for (int c = 0; c < DMAX; ++c) {
+                    th[p][c] = (EXACT || c < d) ? *pc : 0.0;
+                    pc += a.stride;
+                }
+                ll_old[p] = lp_old[p] = 0.0;
+                if (MODE == 1) {
+                    ll_old[p] = a.ll[idx[p]];
+                    lp_old[p] = a.lp[idx[p]];
+                }
             }
         }
 
@@ -723,14 +758,23 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
     return data + 16;      // + DMAX*DMAX doubles for the Cholesky factor, added per instantiation
 }
 
-template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT>
+template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false>
 static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
-    const size_t smem = mh_smem_bytes(&a.prob) + (size_t)DMAX * DMAX * sizeof(double);
+    const size_t smem = mh_smem_bytes(&a.prob) + (size_t)DMAX * DMAX * sizeof(double) +
+                        (TMA ? (size_t)(64 + (DMAX + 2) * TPB) * sizeof(double) : 0);
+    if (TMA) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            attr = true;
+        }
+    }
     // persistent grid: resident blocks per SM (occupancy query, cached) x SM count
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT>, TPB,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA>, TPB,
                                                           smem) != cudaSuccess || nb < 1)
             nb = 1;
         blocks_per_sm = nb;
@@ -744,7 +788,7 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     const bool persist = persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL);
     const int64_t cap = persist ? (int64_t)kNumSMs * blocks_per_sm : n_tiles;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT><<<grid, TPB, smem, s>>>(a);
+    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA><<<grid, TPB, smem, s>>>(a);
     return check_launch("mh_kernel");
 }
 
@@ -753,7 +797,18 @@ static int launch_cfg(const MhArgs& a, cudaStream_t s) {
     // exact-width instantiations (no per-column bounds checks) where they pay
     constexpr bool kHasExact = (KIND == K_IDENTITY_NORMAL && DMAX >= 8) || (KIND != K_LINEAR_MVN && DMAX == 2);
     if constexpr (kHasExact) {
-        if (a.prob.n_params == DMAX) return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true>(a, s);
+        if (a.prob.n_params == DMAX) {
+            // TMA-staged variant for the bandwidth-bound wide identity kernels: needs 16-byte
+            // aligned column segments (even n and stride) and enough tiles to pipeline
+            if constexpr (KIND == K_IDENTITY_NORMAL && MODE == 1 && DMAX >= 16 && PPT == 1) {
+                static const bool no_tma = getenv("SMCB_NO_TMA") != nullptr;     // tuning aid
+                const bool aligned = ((((uintptr_t)a.params | (uintptr_t)a.ll | (uintptr_t)a.lp) & 15) == 0) &&
+                                     (a.stride % 2 == 0) && (a.n % 2 == 0);
+                if (!no_tma && aligned && a.n >= (int64_t)kNumSMs * 8 * TPB)
+                    return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true, true>(a, s);
+            }
+            return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true>(a, s);
+        }
     }
     return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, false>(a, s);
 }

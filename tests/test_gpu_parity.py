@@ -528,3 +528,22 @@ def test_torch_callable_model_route(sb):
     np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=RTOL)
     o_theta, o_ll = orc.smc_metropolis(problem, theta, 5, cov, 0.6, np.random.default_rng(5))
     np.testing.assert_allclose(outs[0][0], o_theta, rtol=RTOL, atol=1e-12)
+
+
+def test_wide_identity_kernel_tma_path_vs_oracle(sb):
+    """2^18 particles x d=32 takes the persistent, TMA-staged (cp.async.bulk + mbarrier) variant
+    of the fused Metropolis kernel; replayed draws against the oracle, 1e-10."""
+    problem = configs.gauss_problem(32)
+    n, K = 1 << 18, 2
+    rng0 = np.random.default_rng(3)
+    theta = problem["data"][None, :] + rng0.normal(0, 1.0, (n, 32))
+    cov = np.eye(32) * 0.04 + 0.01
+    o_rng = np.random.default_rng(77)
+    accepts = []
+    o_theta, o_ll = orc.smc_metropolis(problem, theta, K, cov, 0.8, o_rng, trace=accepts)
+    mc, kernel = make_b200(problem, rng=np.random.default_rng(77))
+    kernel.path.phi = 0.8
+    g_theta, g_ll = mc.smc_metropolis(theta, K, cov)
+    np.testing.assert_allclose(g_theta, o_theta, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(g_ll, o_ll, rtol=RTOL)
+    assert 0.05 * n < accepts[0] < 0.95 * n
