@@ -5,6 +5,8 @@
 //     mean = sum(w x) / sum(w);   C = sum(w (x-mean)(x-mean)^T) * (1 / sum(w)).
 // np.linalg.cholesky of the result (smcpy/mcmc/vector_mcmc.py:225).
 // Algorithmic bytes per particle: pass 1 reads d+1 doubles, pass 2 reads d+1 doubles.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace smcb {
@@ -134,6 +136,122 @@ __global__ void __launch_bounds__(kMomThreads) wsums2_kernel(const double* __res
         for (int sl = 0; sl < nslices; ++sl) s += red[sl * nbu * 16 + e];
         partials[(int64_t)blockIdx.x * (nbu * 16) + e] = s;
     }
+}
+
+// ---- pass 2 for d > 8: FP64 tensor cores (DMMA m8n8k4) + TMA-prefetched tiles ----------------------
+// sum_p w_p (x_p - m)(x_p - m)^T is a SYRK: C (d x d) += XW (d x 4) * XC^T (4 x d) for every
+// group of 4 particles.  One mma.sync.m8n8k4.f64 does 256 FMAs from two 8-byte fragment loads
+// per lane, so shared-memory bandwidth is no longer the limit (a 4x4 register-blocked SYRK
+// needs 8 loads per 16 FMAs and is smem-bound at ~1/3 of the FP64 rate, profiles/r01_cov.md).
+// Per CTA: the raw tile (d columns + weights, 128 particles) is bulk-copied by TMA
+// (cp.async.bulk + mbarrier); all threads centre and weight it into xc / xw; the raw stage is
+// re-armed with the next tile at once; each of the 8 warps then takes 4 of the tile's 32
+// k-steps over all upper-triangular 8x8 blocks, accumulating in registers across tiles.
+constexpr int kWP = 128;            // particles per tile
+constexpr int kWLd = 132;           // row length: == 4 (mod 16) doubles -> conflict-free fragment loads
+constexpr int kDmmaWarps = 8;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int NB8>
+__global__ void __launch_bounds__(kDmmaWarps * 32, 2)
+wsums2_dmma_kernel(const double* __restrict__ params, int64_t pstride, const double* __restrict__ w, int64_t n,
+                   int d, const double* __restrict__ mean, double* partials /* [grid][NBU8*64] */) {
+    constexpr int NBU8 = NB8 * (NB8 + 1) / 2;
+    constexpr int DP = NB8 * 8;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    double* raw = smem;                          // [DP + 1][kWP]  (last row: weights)
+    double* xc = raw + (DP + 1) * kWP;           // [DP][kWLd] centred
+    double* xw = xc + DP * kWLd;                 // [DP][kWLd] centred * weight
+    double* smean = xw + DP * kWLd;              // [DP]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int frow = lane >> 2, fk = lane & 3;   // fragment row / k index of this lane
+
+    double acc[NBU8][2];
+#pragma unroll
+    for (int q = 0; q < NBU8; ++q) acc[q][0] = acc[q][1] = 0.0;
+
+    for (int c = tid; c < DP; c += blockDim.x) smean[c] = (c < d) ? mean[c] : 0.0;
+    const int64_t n_tiles = (n + kWP - 1) / kWP;
+    auto issue = [&](int64_t tile) {             // one elected thread
+        const int64_t base = tile * kWP;
+        const uint32_t cnt = (uint32_t)((n - base < kWP) ? (n - base) : kWP);
+        const uint32_t bytes = cnt * 8u;
+        fence_proxy_async();
+        mbar_expect_tx(&mbar, bytes * (uint32_t)(d + 1));
+        for (int c = 0; c < d; ++c) tma_load_1d(raw + c * kWP, params + (int64_t)c * pstride + base, bytes, &mbar);
+        tma_load_1d(raw + DP * kWP, w + base, bytes, &mbar);
+    };
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0 && (int64_t)blockIdx.x < n_tiles) issue(blockIdx.x);
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * kWP;
+        const int cnt = (int)((n - base < kWP) ? (n - base) : kWP);
+        mbar_wait(&mbar, phase);
+        phase ^= 1u;
+        for (int e = tid; e < DP * kWP; e += blockDim.x) {
+            const int c = e / kWP, p = e - c * kWP;
+            double v = 0.0, vw = 0.0;
+            if (c < d && p < cnt) {
+                v = raw[c * kWP + p] - smean[c];
+                vw = __dmul_rn(v, raw[DP * kWP + p]);
+            }
+            xc[c * kWLd + p] = v;
+            xw[c * kWLd + p] = vw;
+        }
+        __syncthreads();                          // raw drained, xc / xw complete
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x);
+#pragma unroll
+        for (int ks = 0; ks < kWP / 4 / kDmmaWarps; ++ks) {
+            const int p0 = (wid + ks * kDmmaWarps) * 4 + fk;
+            double fa[NB8], fb[NB8];
+#pragma unroll
+            for (int I = 0; I < NB8; ++I) {
+                fa[I] = xw[(I * 8 + frow) * kWLd + p0];
+                fb[I] = xc[(I * 8 + frow) * kWLd + p0];
+            }
+            int q = 0;
+#pragma unroll
+            for (int I = 0; I < NB8; ++I)
+#pragma unroll
+                for (int J = I; J < NB8; ++J) {
+                    dmma_m8n8k4(acc[q][0], acc[q][1], fa[I], fb[J]);
+                    ++q;
+                }
+        }
+        __syncthreads();                          // xc / xw free for the next tile
+    }
+    // warps -> CTA partial in warp order (deterministic); reuse xc as [warp][NBU8*64]
+    double* red = xc;
+#pragma unroll
+    for (int q = 0; q < NBU8; ++q) {
+        red[(wid * NBU8 + q) * 64 + frow * 8 + fk * 2 + 0] = acc[q][0];
+        red[(wid * NBU8 + q) * 64 + frow * 8 + fk * 2 + 1] = acc[q][1];
+    }
+    __syncthreads();
+    for (int e = tid; e < NBU8 * 64; e += blockDim.x) {
+        double sum = 0.0;
+        for (int wq = 0; wq < kDmmaWarps; ++wq) sum += red[wq * NBU8 * 64 + e];
+        partials[(int64_t)blockIdx.x * (NBU8 * 64) + e] = sum;
+    }
+}
+
+// expand the 8x8-block-packed upper triangle to a full symmetric d x d matrix
+__global__ void sums2_unpack8_kernel(const double* packed, int d, int nb8, double* full) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d * d) return;
+    int i = e / d, j = e - i * d;
+    if (i > j) { const int tmp = i; i = j; j = tmp; }
+    const int bi = i >> 3, bj = j >> 3;
+    const int blk = bi * nb8 - bi * (bi - 1) / 2 + (bj - bi);
+    full[e] = packed[blk * 64 + (i & 7) * 8 + (j & 7)];
 }
 
 // expand the block-packed upper triangle to a full symmetric d x d matrix
@@ -269,11 +387,38 @@ extern "C" int smcb_weighted_sums2(const double* params, int64_t stride, const d
     }
     const int nb = (d + 3) / 4, nbu = nb * (nb + 1) / 2;
     double* partials = (double*)((char*)ws + kWsPartials);
-    int grid = sums2_grid(n);
-    const int maxb = (int)(kWsPartialsBytes / sizeof(double) / (nbu * 16 + 0)) - 1;
-    if (grid > maxb) grid = maxb;
     cudaStream_t s = as_stream(stream);
-    wsums2_kernel<<<grid, kMomThreads, smem, s>>>(params, stride, w, n, d, mean, partials);
+    int grid;
+    static const bool no_dmma = getenv("SMCB_NO_DMMA") != nullptr;      // tuning aid
+    const bool aligned = ((((uintptr_t)params | (uintptr_t)w) & 15) == 0) && (stride % 2 == 0) && (n % 2 == 0);
+    if (!no_dmma && d > 8 && aligned && n >= (int64_t)kNumSMs * kWP) {
+        const int nb8 = (d + 7) / 8, nbu8 = nb8 * (nb8 + 1) / 2, dp = nb8 * 8;
+        const size_t smem_w = (size_t)((dp + 1) * kWP + 2 * dp * kWLd + dp) * sizeof(double);
+        grid = kNumSMs * 2;
+        if (nb8 == 2) {
+            static bool at = false;
+            if (!at) { cudaFuncSetAttribute(wsums2_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); at = true; }
+            wsums2_dmma_kernel<2><<<grid, kDmmaWarps * 32, smem_w, s>>>(params, stride, w, n, d, mean, partials);
+        } else if (nb8 == 3) {
+            static bool at = false;
+            if (!at) { cudaFuncSetAttribute(wsums2_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); at = true; }
+            wsums2_dmma_kernel<3><<<grid, kDmmaWarps * 32, smem_w, s>>>(params, stride, w, n, d, mean, partials);
+        } else {
+            static bool at = false;
+            if (!at) { cudaFuncSetAttribute(wsums2_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); at = true; }
+            wsums2_dmma_kernel<4><<<grid, kDmmaWarps * 32, smem_w, s>>>(params, stride, w, n, d, mean, partials);
+        }
+        double* packed8 = partials + (int64_t)grid * nbu8 * 64;
+        reduce_partials_kernel<<<(nbu8 * 64 + 3) / 4, 128, 0, s>>>(partials, grid, nbu8 * 64, packed8);
+        sums2_unpack8_kernel<<<(d * d + 63) / 64, 64, 0, s>>>(packed8, d, nb8, sums_out);
+        return check_launch("wsums2_dmma_kernel");
+    }
+    grid = sums2_grid(n);
+    {
+        const int maxb = (int)(kWsPartialsBytes / sizeof(double) / (nbu * 16 + 0)) - 1;
+        if (grid > maxb) grid = maxb;
+        wsums2_kernel<<<grid, kMomThreads, smem, s>>>(params, stride, w, n, d, mean, partials);
+    }
     // packed block sums live after the per-block partials
     double* packed = partials + (int64_t)grid * nbu * 16;
     reduce_partials_kernel<<<(nbu * 16 + 3) / 4, 128, 0, s>>>(partials, grid, nbu * 16, packed);

@@ -122,13 +122,28 @@ __global__ void __launch_bounds__(kRwThreads) rw_finalize_kernel(RwIn in, int64_
                                                                  double* log_w, double* w) {
     const double m = sc[0], ls = sc[5];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {          // four independent load/exp/store chains
+        double v[4], lw[4], wi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = rw_value(in, i + k * stride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            lw[k] = (v[k] - m) - ls;
+            wi[k] = exp(lw[k]);
+            if (!(wi[k] > 0.0)) lw[k] = (wi[k] != wi[k]) ? wi[k] : kNegInf;   // underflow / -inf / NaN
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            log_w[i + k * stride] = lw[k];
+            w[i + k * stride] = wi[k];
+        }
+    }
+    for (; i < n; i += stride) {
         const double v = rw_value(in, i);
         double lw = (v - m) - ls;
         double wi = exp(lw);
-        if (!(wi > 0.0)) {           // underflow or -inf (NaN when every weight is -inf)
-            lw = (wi != wi) ? wi : kNegInf;
-        }
+        if (!(wi > 0.0)) lw = (wi != wi) ? wi : kNegInf;
         log_w[i] = lw;
         w[i] = wi;
     }
