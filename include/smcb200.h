@@ -65,6 +65,15 @@ enum {
     SMCB_SCAN_LOOKBACK = 1     /* single-pass decoupled look-back, deterministic (fast mode) */
 };
 
+/* initial-particle proposal q(x) of GeometricPath(proposal=...): independent components
+ * (smcpy/proposals.py:4-34 MultivarIndependent over scipy.stats distributions) */
+enum { SMCB_PROPOSAL_NORMAL = 1 /* norm(loc=a, scale=b) */, SMCB_PROPOSAL_UNIFORM = 2 /* uniform(loc=a, scale=b) */ };
+typedef struct smcb_proposal_col {
+    int32_t kind;    /* SMCB_PROPOSAL_* */
+    int32_t pad;
+    double a, b;     /* loc, scale */
+} smcb_proposal_col_t;
+
 typedef struct smcb_prior {
     int32_t kind;    /* SMCB_PRIOR_* */
     int32_t ncols;   /* IMPROPER_COV: matrix size; else 1 */
@@ -91,6 +100,9 @@ typedef struct smcb_problem {
     double cov_fixed[SMCB_MAX_COV_ARGS];      /* MVNormal packed upper-tri, fixed values */
     int32_t cov_param_col[SMCB_MAX_COV_ARGS]; /* -1 = fixed, else parameter column */
     smcb_prior_t priors[SMCB_MAX_PRIORS];
+    int32_t has_proposal;    /* 1: the path has a proposal; one entry per parameter column below */
+    int32_t pad;
+    smcb_proposal_col_t proposal[SMCB_MAX_PARAMS];
 } smcb_problem_t;
 
 /* GeometricPath state (smcpy/paths.py:64-112): exponents are derived inside the
@@ -223,9 +235,11 @@ int smcb_cholesky(const double* cov, int32_t d, double* chol_out, int32_t* flags
 /* ---- (d) vectorised Metropolis ------------------------------------------------------ */
 /* log-priors + log-likelihood of incoming particles
  * (vector_mcmc.py:162-166 _initialize_probabilities, initializer.py:66-73).
- * lp_cols_out (optional, n_priors x stride) = un-summed log priors (vector_mcmc.py:98-111). */
+ * lp_cols_out (optional, n_priors x stride) = un-summed log priors (vector_mcmc.py:98-111).
+ * lq_out (required iff prob->has_proposal) = proposal log-pdf (paths.py:107-112). */
 int smcb_mh_init(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
-                 double* ll_out, double* lp_out, double* lp_cols_out, int32_t* flags, void* stream);
+                 double* ll_out, double* lp_out, double* lp_cols_out, double* lq_out, int32_t* flags,
+                 void* stream);
 /* log-priors only: lp_out[n] summed (vector_mcmc_kernel.py:33-36), lp_cols_out optional
  * (n_priors x stride) un-summed (vector_mcmc.py:98-111) */
 int smcb_log_priors(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
@@ -234,15 +248,16 @@ int smcb_log_priors(const smcb_problem_t* prob, const double* params, int64_t st
  * proposal x + sqrt(s) L z, priors, model, likelihood, tempered ratio, accept/reject, in place.
  * accept_counts (device, int64[SMCB_MAX_MCMC_STEPS]): slot `step` receives this step's number
  * of accepted particles; slots < step (already all-reduced across GPUs by the caller) give
- * the covariance scale s (x1/5 below 30 %, x2 above 70 %). `moved` (n bytes) |= accepted. */
+ * the covariance scale s (x1/5 below 30 %, x2 above 70 %). `moved` (n bytes) |= accepted.
+ * lq (required iff prob->has_proposal): resident proposal log-pdf column, updated in place. */
 int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride,
-                 int64_t n, int64_t n_global, double* ll, double* lp, uint8_t* moved,
+                 int64_t n, int64_t n_global, double* ll, double* lp, double* lq, uint8_t* moved,
                  const double* chol, int64_t* accept_counts, int32_t step, const smcb_rng_t* rng,
                  int32_t* flags, void* stream);
 /* same step with the cross-GPU accept-count exchange fused in (x->world > 1); accept_counts
  * then holds the LOCAL counts, x->global_counts the global ones. */
 int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride,
-                      int64_t n, int64_t n_global, double* ll, double* lp, uint8_t* moved,
+                      int64_t n, int64_t n_global, double* ll, double* lp, double* lq, uint8_t* moved,
                       const double* chol, int64_t* accept_counts, int32_t step, const smcb_rng_t* rng,
                       int32_t* flags, const smcb_xchg_t* x, void* stream);
 /* fraction of particles that moved (mutator.py:69-71): count of non-zero bytes */

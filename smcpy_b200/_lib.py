@@ -31,13 +31,21 @@ class Prior(C.Structure):
                 ("logp_in", C.c_double)]
 
 
+PROPOSAL_NORMAL, PROPOSAL_UNIFORM = 1, 2
+
+
+class ProposalCol(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("a", C.c_double), ("b", C.c_double)]
+
+
 class Problem(C.Structure):
     _fields_ = [("model_id", C.c_int32), ("loglike_id", C.c_int32), ("n_params", C.c_int32),
                 ("n_model_params", C.c_int32), ("n_data", C.c_int32), ("n_snapshots", C.c_int32),
                 ("sigma_is_param", C.c_int32), ("n_priors", C.c_int32), ("sigma", C.c_double),
                 ("model_args", C.c_double * 8), ("data", C.c_void_p), ("xgrid", C.c_void_p),
                 ("cov_fixed", C.c_double * MAX_COV_ARGS), ("cov_param_col", C.c_int32 * MAX_COV_ARGS),
-                ("priors", Prior * MAX_PRIORS)]
+                ("priors", Prior * MAX_PRIORS), ("has_proposal", C.c_int32), ("pad", C.c_int32),
+                ("proposal", ProposalCol * MAX_PARAMS)]
 
 
 class Path(C.Structure):
@@ -92,11 +100,11 @@ SIGNATURES = {
     "smcb_weighted_sums2": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P],
     "smcb_cov_from_sums": [_P, _P, _I32, _P, _P],
     "smcb_cholesky": [_P, _I32, _P, _P, _P],
-    "smcb_mh_init": [_PP(Problem), _P, _I64, _I64, _P, _P, _P, _P, _P],
+    "smcb_mh_init": [_PP(Problem), _P, _I64, _I64, _P, _P, _P, _P, _P, _P],
     "smcb_log_priors": [_PP(Problem), _P, _I64, _I64, _P, _P, _P],
-    "smcb_mh_step": [_PP(Problem), _PP(Path), _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I32,
+    "smcb_mh_step": [_PP(Problem), _PP(Path), _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I32,
                      _PP(Rng), _P, _P],
-    "smcb_mh_step_xchg": [_PP(Problem), _PP(Path), _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I32,
+    "smcb_mh_step_xchg": [_PP(Problem), _PP(Path), _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I32,
                           _PP(Rng), _P, _PP(Xchg), _P],
     "smcb_count_moved": [_P, _I64, _P, _P, _P],
     "smcb_sample_priors": [_PP(Problem), _P, _I64, _I64, _U64, _U64, _I64, _P],

@@ -47,6 +47,7 @@ struct MhArgs {
     double n_global;
     double* ll;
     double* lp;
+    double* lq;           // proposal log-pdf column (nullptr: no proposal, lq := lp)
     uint8_t* moved;
     const double* chol;
     unsigned long long* accept_counts;
@@ -172,6 +173,26 @@ __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th
         if (lp_cols_row) lp_cols_row[(int64_t)a.cp.cov_prior[q] * col_stride] = v;
     }
     return lps;
+}
+
+// proposal log-pdf log q(x) = sum of independent components (smcpy/proposals.py:27-30 over
+// scipy.stats frozen norm / uniform: norm.logpdf = -y^2/2 - log(sqrt(2 pi)) - log(scale))
+template <int DMAX, bool EXACT>
+__device__ __forceinline__ double eval_proposal(const MhArgs& a, const double (&th)[DMAX]) {
+    const int d = a.prob.n_params;
+    double lq = 0.0;
+#pragma unroll
+    for (int c = 0; c < DMAX; ++c) {
+        if (EXACT || c < d) {
+            const smcb_proposal_col_t& q = a.prob.proposal[c];
+            const double y = (th[c] - q.a) / q.b;
+            double v;
+            if (q.kind == SMCB_PROPOSAL_NORMAL) v = (-(y * y) / 2.0 - 0.91893853320467274178) - log(q.b);
+            else v = (y >= 0.0 && y <= 1.0) ? -log(q.b) : kNegInf;
+            lq += v;
+        }
+    }
+    return lq;
 }
 
 // ---- models + likelihoods ------------------------------------------------------------------------
@@ -369,7 +390,8 @@ __host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt) {
 //       3 = log-priors only.  EXACT: n_params == DMAX (drops every per-column bounds check).
 //       TMA: the next tile's d+2 column segments are bulk-copied (cp.async.bulk + mbarrier) into
 //       a shared-memory stage by one elected thread while the block computes the current tile.
-template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false>
+//       PROP: the path has a proposal q: its log-pdf is a third resident column next to ll, lp.
+template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false>
 __global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -422,6 +444,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         bool valid[PPT];
         double th[PPT][DMAX];
         double ll_old[PPT], lp_old[PPT], lp_new[PPT], ll_new[PPT];
+        double lq_old[PPT], lq_new[PPT];
         bool prior_ok[PPT];
         if (TMA) {
             const int64_t i = tile * per_tile + threadIdx.x;
@@ -454,6 +477,8 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                 }
             }
         }
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) lq_old[p] = (PROP && MODE == 1) ? a.lq[idx[p]] : 0.0;
 
         if (MODE == 1 || MODE == 2) {
             // proposal x' = x + sqrt(s) L z, column-outer: z_j updates rows j..d-1, which are
@@ -503,6 +528,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                 ((MODE == 0 || MODE == 3) && a.lp_cols && valid[p]) ? a.lp_cols + idx[p] : nullptr;
             lp_new[p] = eval_priors<KIND, DMAX, EXACT>(a, th[p], lp_cols_row, a.stride);
             prior_ok[p] = lp_new[p] != kNegInf;
+            lq_new[p] = PROP ? eval_proposal<DMAX, EXACT>(a, th[p]) : 0.0;
         }
 
         if (MODE == 3) {
@@ -527,12 +553,13 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             continue;
         }
 
-        // rows with a -inf prior are not evaluated (quirk Q6)
+        // proposals with a -inf prior are not evaluated (quirk Q6, vector_mcmc.py:205-214);
+        // incoming particles (MODE 0) always are (vector_mcmc.py:116-118 has no prior test)
         bool run[PPT], not_pd[PPT];
         bool run_any = false;
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
-            run[p] = valid[p] && prior_ok[p];
+            run[p] = valid[p] && (MODE == 0 || prior_ok[p]);
             not_pd[p] = false;
             run_any = run_any || run[p];
         }
@@ -549,12 +576,14 @@ mh_kernel(const __grid_constant__ MhArgs a) {
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
             if (!run[p]) ll_new[p] = 0.0;       // placeholder (vector_mcmc.py:207)
-            if (run[p] && ll_new[p] != ll_new[p]) flag |= SMCB_FLAG_MODEL_NAN;
-            if (run[p] && not_pd[p]) flag |= SMCB_FLAG_COV_NOT_PD;
+            // a particle outside the prior support may legitimately have no valid likelihood
+            if (run[p] && prior_ok[p] && ll_new[p] != ll_new[p]) flag |= SMCB_FLAG_MODEL_NAN;
+            if (run[p] && prior_ok[p] && not_pd[p]) flag |= SMCB_FLAG_COV_NOT_PD;
             if (MODE == 0) {
                 if (valid[p]) {
                     a.ll[idx[p]] = ll_new[p];
                     a.lp[idx[p]] = lp_new[p];
+                    if (PROP) a.lq[idx[p]] = lq_new[p];
                     if (!prior_ok[p]) flag |= SMCB_FLAG_PRIOR_OOB;
                 }
                 continue;
@@ -562,8 +591,8 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             // acceptance (vector_mcmc.py:131-151 with evaluate_log_posterior = path.logpdf)
             if (valid[p]) {
                 const int64_t i = idx[p];
-                const double t_old = path_target(ll_old[p], lp_old[p], lp_old[p], a.phi, a.pe, a.qe);
-                const double t_new = path_target(ll_new[p], lp_new[p], lp_new[p], a.phi, a.pe, a.qe);
+                const double t_old = path_target(ll_old[p], lp_old[p], PROP ? lq_old[p] : lp_old[p], a.phi, a.pe, a.qe);
+                const double t_new = path_target(ll_new[p], lp_new[p], PROP ? lq_new[p] : lp_new[p], a.phi, a.pe, a.qe);
                 const double ratio = exp(t_new - t_old);
                 double u;
                 if (a.rng.mode == 1) {
@@ -583,6 +612,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                     }
                     a.ll[i] = ll_new[p];
                     a.lp[i] = lp_new[p];
+                    if (PROP) a.lq[i] = lq_new[p];
                     a.moved[i] = 1;
                     ++n_acc;
                 }
@@ -758,14 +788,14 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
     return data + 16;      // + DMAX*DMAX doubles for the Cholesky factor, added per instantiation
 }
 
-template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false>
+template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false>
 static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     const size_t smem = mh_smem_bytes(&a.prob) + (size_t)DMAX * DMAX * sizeof(double) +
                         (TMA ? (size_t)(64 + (DMAX + 2) * TPB) * sizeof(double) : 0);
     if (TMA) {
         static bool attr = false;
         if (!attr) {
-            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA>,
+            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr = true;
         }
@@ -774,7 +804,7 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA>, TPB,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP>, TPB,
                                                           smem) != cudaSuccess || nb < 1)
             nb = 1;
         blocks_per_sm = nb;
@@ -788,7 +818,7 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     const bool persist = persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL);
     const int64_t cap = persist ? (int64_t)kNumSMs * blocks_per_sm : n_tiles;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA><<<grid, TPB, smem, s>>>(a);
+    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP><<<grid, TPB, smem, s>>>(a);
     return check_launch("mh_kernel");
 }
 
@@ -815,6 +845,10 @@ static int launch_cfg(const MhArgs& a, cudaStream_t s) {
 
 template <int KIND, int DMAX, int MODE>
 static int launch_one(const MhArgs& a, cudaStream_t s) {
+    if constexpr (MODE == 0 || MODE == 1) {
+        // paths with a proposal: generic 1-particle-per-thread variant with the log q column
+        if (a.prob.has_proposal) return launch_cfg2<KIND, DMAX, MODE, kMhThreads, 1, false, false, true>(a, s);
+    }
     if constexpr (KIND == K_LINEAR_NORMAL && (MODE == 0 || MODE == 1)) {
         // several particles per thread amortise the shared-memory data reads; keep at least
         // ~4 tiles per SM so small problems still fill the chip
@@ -883,6 +917,15 @@ static int validate_problem(const smcb_problem_t* p, ColPriors* cp) {
         return SMCB_ERR_ARG;
     }
     if (!p->data) { set_error("data pointer is NULL"); return SMCB_ERR_ARG; }
+    if (p->has_proposal) {
+        for (int c = 0; c < p->n_params; ++c) {
+            const smcb_proposal_col_t& q = p->proposal[c];
+            if ((q.kind != SMCB_PROPOSAL_NORMAL && q.kind != SMCB_PROPOSAL_UNIFORM) || !(q.b > 0.0)) {
+                set_error("proposal column %d: kind must be normal/uniform with scale > 0", c);
+                return SMCB_ERR_ARG;
+            }
+        }
+    }
     if (p->loglike_id == SMCB_LL_NORMAL) {
         const int extra = p->sigma_is_param ? 1 : 0;
         if (p->n_model_params + extra != p->n_params) { set_error("Normal: n_model_params + sigma != n_params"); return SMCB_ERR_ARG; }
@@ -906,7 +949,8 @@ static int validate_problem(const smcb_problem_t* p, ColPriors* cp) {
 using namespace smcb;
 
 extern "C" int smcb_mh_init(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
-                            double* ll_out, double* lp_out, double* lp_cols_out, int32_t* flags, void* stream) {
+                            double* ll_out, double* lp_out, double* lp_cols_out, double* lq_out, int32_t* flags,
+                            void* stream) {
     MhArgs a;
     memset(&a, 0, sizeof(a));
     int rc = validate_problem(prob, &a.cp);
@@ -917,7 +961,9 @@ extern "C" int smcb_mh_init(const smcb_problem_t* prob, const double* params, in
     a.stride = stride;
     a.n = n;
     a.ll = ll_out;
+    SMCB_REQUIRE(!prob->has_proposal || lq_out, "lq_out required when the problem has a proposal");
     a.lp = lp_out;
+    a.lq = lq_out;
     a.lp_cols = lp_cols_out;
     a.flags = flags;
     return dispatch<0>(a, as_stream(stream));
@@ -943,7 +989,8 @@ static void fill_step_args(MhArgs& a, const smcb_problem_t* prob, const smcb_pat
 }
 
 extern "C" int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride,
-                            int64_t n, int64_t n_global, double* ll, double* lp, uint8_t* moved, const double* chol,
+                            int64_t n, int64_t n_global, double* ll, double* lp, double* lq, uint8_t* moved,
+                            const double* chol,
                             int64_t* accept_counts, int32_t step, const smcb_rng_t* rng, int32_t* flags,
                             void* stream) {
     MhArgs a;
@@ -954,17 +1001,19 @@ extern "C" int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path,
     SMCB_REQUIRE(n > 0 && stride >= n && n_global >= n, "bad sizes");
     SMCB_REQUIRE(step >= 0 && step < SMCB_MAX_MCMC_STEPS, "step out of range");
     SMCB_REQUIRE(rng->mode == 0 || (rng->z && rng->u), "replay mode needs z and u tapes");
+    SMCB_REQUIRE(!prob->has_proposal || lq, "lq required when the problem has a proposal");
     fill_step_args(a, prob, path, stride, n, n_global, chol, accept_counts, step, rng);
     a.params = params;
     a.ll = ll;
     a.lp = lp;
+    a.lq = lq;
     a.moved = moved;
     a.flags = flags;
     return dispatch<1>(a, as_stream(stream));
 }
 
 extern "C" int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* path, double* params,
-                                 int64_t stride, int64_t n, int64_t n_global, double* ll, double* lp,
+                                 int64_t stride, int64_t n, int64_t n_global, double* ll, double* lp, double* lq,
                                  uint8_t* moved, const double* chol, int64_t* accept_counts, int32_t step,
                                  const smcb_rng_t* rng, int32_t* flags, const smcb_xchg_t* x, void* stream) {
     MhArgs a;
@@ -980,9 +1029,11 @@ extern "C" int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* 
                  "exchange buffers required");
     for (int r = 0; r < x->world && x->world > 1; ++r) SMCB_REQUIRE(x->peer_slots[r] != nullptr, "peer slot pointer is NULL");
     fill_step_args(a, prob, path, stride, n, n_global, chol, accept_counts, step, rng);
+    SMCB_REQUIRE(!prob->has_proposal || lq, "lq required when the problem has a proposal");
     a.params = params;
     a.ll = ll;
     a.lp = lp;
+    a.lq = lq;
     a.moved = moved;
     a.flags = flags;
     a.x = *x;

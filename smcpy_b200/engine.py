@@ -232,6 +232,25 @@ class ProblemSpec:
     def n_model_params(self):
         return int(self.c.n_model_params)
 
+    @property
+    def has_device_proposal(self):
+        return bool(self.c.has_proposal)
+
+    def set_proposal(self, proposal):
+        """Binds the path's proposal (GeometricPath(proposal=...)): fills the device log q table
+        when the proposal is describable, else leaves has_proposal = 0."""
+        from .proposals import describe_proposal
+        cols = describe_proposal(proposal) if proposal else None
+        self.c.has_proposal = 0
+        if cols is not None:
+            if len(cols) != self.d:
+                raise ValueError("proposal has %d components but there are %d parameters" % (len(cols), self.d))
+            if not self.fused:
+                raise NotImplementedError("proposals with torch-callable models are not on the device")
+            for i, (k, a, b) in enumerate(cols):
+                self.c.proposal[i] = _lib.ProposalCol(k, 0, a, b)
+            self.c.has_proposal = 1
+
 
 # ---------------------------------------------------------------------------------------------
 # particle state
@@ -239,18 +258,20 @@ class ProblemSpec:
 class DeviceState:
     """Working set of one particle shard."""
 
-    def __init__(self, n_local, n_global, d, id_offset=0):
+    def __init__(self, n_local, n_global, d, id_offset=0, with_lq=False):
         rt = Runtime.get()
         dv = rt.device
         self.n, self.n_global, self.d, self.id_offset = int(n_local), int(n_global), int(d), int(id_offset)
         f64 = torch.float64
-        self.cols = torch.empty((d + 2, self.n), dtype=f64, device=dv)
-        self.cols_alt = torch.empty((d + 2, self.n), dtype=f64, device=dv)
+        self.with_lq = bool(with_lq)            # third resident column: proposal log-pdf
+        rows = d + 3 if with_lq else d + 2
+        self.cols = torch.empty((rows, self.n), dtype=f64, device=dv)
+        self.cols_alt = torch.empty((rows, self.n), dtype=f64, device=dv)
         self.log_w = torch.empty(self.n, dtype=f64, device=dv)
         self.w = torch.empty(self.n, dtype=f64, device=dv)
         self.log_w_alt = torch.empty(self.n, dtype=f64, device=dv)
         self.w_alt = torch.empty(self.n, dtype=f64, device=dv)
-        self.lq = None
+        self._lq_host = None                    # host-evaluated proposal log-pdf (reweight only)
         self.cdf = torch.empty(self.n, dtype=f64, device=dv)
         self.u = torch.empty(self.n, dtype=f64, device=dv)
         self.idx = torch.empty(self.n, dtype=torch.int64, device=dv)
@@ -280,6 +301,14 @@ class DeviceState:
     def lp(self):
         return self.cols[self.d + 1]
 
+    @property
+    def lq(self):
+        return self.cols[self.d + 2] if self.with_lq else self._lq_host
+
+    @lq.setter
+    def lq(self, value):
+        self._lq_host = value
+
     def set_params_host(self, params):
         """(n, d) host array -> SoA columns."""
         a = dev(np.asarray(params, dtype=np.float64))
@@ -300,12 +329,12 @@ class DeviceState:
         call("smcb_fill_f64", ptr(self.w), self.n, w, stream_ptr())
         self.uniform_weights = True
 
-    def check_flags(self, where):
+    def check_flags(self, where, allow_oob=False):
         f = int(self.flags.item())
         if f == 0:
             return 0
         self.flags.zero_()
-        if f & _lib.FLAG_PRIOR_OOB:
+        if (f & _lib.FLAG_PRIOR_OOB) and not allow_oob:
             raise ValueError("Initial inputs are out of bounds; prior log prob = -inf (%s)" % where)
         if f & _lib.FLAG_MODEL_NAN:
             raise ValueError("nan in model output.")
@@ -435,7 +464,8 @@ def count_unique(st, idx):
 
 
 def gather_particles(st, idx):
-    call("smcb_gather", ptr(st.cols), st.n, ptr(st.cols_alt), st.n, ptr(idx), st.n, st.d + 2, stream_ptr())
+    call("smcb_gather", ptr(st.cols), st.n, ptr(st.cols_alt), st.n, ptr(idx), st.n, int(st.cols.shape[0]),
+         stream_ptr())
     st.cols, st.cols_alt = st.cols_alt, st.cols
     st.set_uniform_weights()
 
@@ -530,8 +560,10 @@ def cholesky(st, cov_dev=None):
 def eval_incoming(st, spec, lp_cols=None):
     """log-priors + log-likelihood of the particles in st.cols (vector_mcmc.py:162-166)."""
     if spec.fused:
+        if spec.has_device_proposal and not st.with_lq:
+            raise ValueError("particle state has no proposal log-pdf column")
         call("smcb_mh_init", C.byref(spec.c), ptr(st.cols), st.n, st.n, ptr(st.ll), ptr(st.lp), ptr(lp_cols),
-             ptr(st.flags), stream_ptr())
+             ptr(st.lq) if spec.has_device_proposal else None, ptr(st.flags), stream_ptr())
     else:
         from .callable_route import eval_incoming_callable
         eval_incoming_callable(st, spec, lp_cols)
@@ -572,6 +604,7 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
     r = _lib.Rng()
     r.id_offset = st.id_offset
     keep = []
+    lq = ptr(st.lq) if (spec.fused and spec.has_device_proposal) else None
     xchg = AcceptExchange.get() if (world > 1 and spec.fused) else None
     xs = xchg.next_gen() if xchg is not None else None
     for k in range(num_samples):
@@ -585,14 +618,14 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
         if spec.fused and xs is not None:
             with _timed("mh_step"):
                 call("smcb_mh_step_xchg", C.byref(spec.c), C.byref(path), ptr(st.cols), st.n, st.n, st.n_global,
-                     ptr(st.ll), ptr(st.lp), ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), k, C.byref(r),
-                     ptr(st.flags), C.byref(xs), s)
+                     ptr(st.ll), ptr(st.lp), lq, ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), k,
+                     C.byref(r), ptr(st.flags), C.byref(xs), s)
             continue
         elif spec.fused:
             with _timed("mh_step"):
                 call("smcb_mh_step", C.byref(spec.c), C.byref(path), ptr(st.cols), st.n, st.n, st.n_global,
-                     ptr(st.ll), ptr(st.lp), ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), k, C.byref(r),
-                     ptr(st.flags), s)
+                     ptr(st.ll), ptr(st.lp), lq, ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), k,
+                     C.byref(r), ptr(st.flags), s)
         else:
             from .callable_route import mh_step_callable
             mh_step_callable(st, spec, path, k, r)

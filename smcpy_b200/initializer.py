@@ -31,7 +31,7 @@ class Initializer:
         spec = kernel.spec
         rank, world = engine.dist_info()
         lo, hi = engine.shard_bounds(num_particles, rank, world)
-        st = engine.DeviceState(hi - lo, num_particles, spec.d, id_offset=lo)
+        st = engine.DeviceState(hi - lo, num_particles, spec.d, id_offset=lo, with_lq=spec.has_device_proposal)
         host_rng = isinstance(kernel.rng, np.random.Generator)
         if kernel.has_proposal() or host_rng:
             if kernel.has_proposal():
@@ -45,7 +45,9 @@ class Initializer:
             call("smcb_sample_priors", C.byref(spec.c), ptr(st.cols), st.n, st.n, rng.seed, rng.next_stream(),
                  st.id_offset, stream_ptr())
         engine.eval_incoming(st, spec)
-        st.check_flags("initialize_particles")
+        # the reference's Initializer does not test the priors (initializer.py:66-73): particles
+        # drawn from a proposal may lie outside the prior support and simply get zero weight
+        st.check_flags("initialize_particles", allow_oob=True)
         st.set_uniform_weights()
         lw0 = np.log(1 / num_particles)
         st.total_unnorm_log_weight = float(lw0 + np.log(1 + (num_particles - 1) * 1.0))   # _logsum of N equal terms

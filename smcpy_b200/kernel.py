@@ -56,6 +56,8 @@ class VectorMCMCKernel(KernelBase):
     def __init__(self, vector_mcmc_object, param_order, path=None, rng=None):
         super().__init__(vector_mcmc_object, param_order, path, rng)
         self._mcmc.evaluate_log_posterior = self.path.logpdf
+        if hasattr(self._mcmc, "bind_path"):
+            self._mcmc.bind_path(self.path)
         self.param_order = tuple(str(p) for p in param_order)
 
     def mutate_particles(self, param_dict, num_samples, cov):

@@ -22,9 +22,9 @@ class Mutator:
     def mutate_state(self, st, num_samples):
         """In place on a device working set; returns the mutation ratio (mutator.py:69-71)."""
         kernel = self._mcmc_kernel
-        if kernel.has_proposal():
-            raise NotImplementedError("mutation with GeometricPath(proposal=...) is not on the device yet "
-                                      "(SURVEY.md section 8f-2)")
+        if kernel.has_proposal() and not (kernel.spec.has_device_proposal and st.with_lq):
+            raise NotImplementedError("mutation under GeometricPath(proposal=...) needs a MultivarIndependent "
+                                      "of scipy norm / uniform components (device log q)")
         engine.covariance(st)
         engine.cholesky(st)
         p = kernel.path

@@ -70,7 +70,8 @@ class Particles:
 
     def to_state(self):
         """Fresh DeviceState holding copies of this step."""
-        st = engine.DeviceState(self._num_particles, self._n_global, self._d, self._id_offset)
+        st = engine.DeviceState(self._num_particles, self._n_global, self._d, self._id_offset,
+                                with_lq=(self._cols.shape[0] == self._d + 3))
         st.cols.copy_(self._cols)
         st.log_w.copy_(self._log_w)
         st.w.copy_(self._w)

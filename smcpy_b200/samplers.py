@@ -144,7 +144,7 @@ class AdaptiveSampler(SamplerBase):
 
     def _prepare_lq(self, st):
         kernel = self._mcmc_kernel
-        if kernel.has_proposal():
+        if kernel.has_proposal() and not st.with_lq:
             st.lq = engine.dev(np.asarray(kernel.path.proposal.logpdf(st.params_host()),
                                           dtype=np.float64).reshape(-1))
 

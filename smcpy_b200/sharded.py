@@ -53,6 +53,7 @@ def resample_sharded(st, kernel, resample_rng, warn_threshold):
         raise NotImplementedError("multi-GPU resampling needs the native Philox generator and a built-in "
                                   "resampler (replay parity mode is single-GPU)")
     n, d = st.n, st.d
+    ncol = int(st.cols.shape[0])            # d + 2 (+1 with a proposal log-pdf column)
     s = stream_ptr()
     dv = st.cols.device
     # 1-2: local CDF and segment offsets
@@ -75,20 +76,20 @@ def resample_sharded(st, kernel, resample_rng, warn_threshold):
     u_in = torch.empty(max(n_req, 1), dtype=torch.float64, device=dv)
     dist.all_to_all_single(u_in[:n_req], u.contiguous(), output_split_sizes=rc, input_split_sizes=sc)
     # 4: owner-side search + gather (rows in AoS for the exchange)
-    rows_out = torch.empty((max(n_req, 1), d + 2), dtype=torch.float64, device=dv)
+    rows_out = torch.empty((max(n_req, 1), ncol), dtype=torch.float64, device=dv)
     n_unique = torch.zeros(1, dtype=torch.int64, device=dv)
     if n_req > 0:
         idx = torch.empty(n_req, dtype=torch.int64, device=dv)
         call("smcb_searchsorted_offset", ptr(st.cdf), n, ptr(off[rank:rank + 1]), ptr(u_in), n_req, ptr(idx), s)
-        soa = torch.empty((d + 2, n_req), dtype=torch.float64, device=dv)
-        call("smcb_gather", ptr(st.cols), n, ptr(soa), n_req, ptr(idx), n_req, d + 2, s)
-        call("smcb_soa_to_aos", ptr(soa), ptr(rows_out), n_req, d + 2, n_req, s)
+        soa = torch.empty((ncol, n_req), dtype=torch.float64, device=dv)
+        call("smcb_gather", ptr(st.cols), n, ptr(soa), n_req, ptr(idx), n_req, ncol, s)
+        call("smcb_soa_to_aos", ptr(soa), ptr(rows_out), n_req, ncol, n_req, s)
         call("smcb_count_unique", ptr(idx), n_req, n, ptr(st.counts), ptr(st.ws), s)
         n_unique = st.counts[0:1].clone()
     # 5: rows back to the requesters
-    rows_in = torch.empty((n, d + 2), dtype=torch.float64, device=dv)
+    rows_in = torch.empty((n, ncol), dtype=torch.float64, device=dv)
     dist.all_to_all_single(rows_in, rows_out[:n_req], output_split_sizes=sc, input_split_sizes=rc)
-    call("smcb_aos_to_soa", ptr(rows_in), ptr(st.cols_alt), n, d + 2, n, s)
+    call("smcb_aos_to_soa", ptr(rows_in), ptr(st.cols_alt), n, ncol, n, s)
     st.cols, st.cols_alt = st.cols_alt, st.cols
     st.set_uniform_weights()
     engine._all_reduce_sum(n_unique)

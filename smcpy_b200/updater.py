@@ -50,7 +50,7 @@ class Updater:
         """In-place update of a device working set: reweight with the kernel path's
         (phi_prev -> phi), then resample if ESS < threshold * N."""
         kernel = self._mcmc_kernel
-        if kernel.has_proposal():
+        if kernel.has_proposal() and not st.with_lq:   # no device log q: evaluate it on the host
             st.lq = engine.dev(np.asarray(kernel.path.proposal.logpdf(st.params_host()),
                                           dtype=np.float64).reshape(-1))
         ess, _ = engine.reweight(st, kernel.device_path())

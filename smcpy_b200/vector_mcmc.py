@@ -81,6 +81,7 @@ class B200VectorMCMC:
         self._log_like_func = log_like_func(model, data, log_like_args)
         self._rng = np.random.default_rng()
         self._spec = None
+        self._proposal = None
 
     # -- reference surface ---------------------------------------------------------------------
     @property
@@ -99,7 +100,15 @@ class B200VectorMCMC:
         if self._spec is None:
             self._spec = engine.ProblemSpec(self._eval_model, self._data, self._priors, self._log_like_args,
                                             self._kind)
+            self._spec.set_proposal(self._proposal)
         return self._spec
+
+    def bind_path(self, path):
+        """Tells the MCMC object about the kernel's path: a describable proposal
+        (MultivarIndependent of scipy norm / uniform) gets a device log q column."""
+        self._proposal = getattr(path, "proposal", None)
+        if self._spec is not None:
+            self._spec.set_proposal(self._proposal)
 
     @staticmethod
     def evaluate_log_posterior(inputs, log_likelihood, log_priors):
@@ -130,13 +139,13 @@ class B200VectorMCMC:
         inputs = np.ascontiguousarray(np.asarray(inputs, dtype=np.float64))
         if inputs.ndim != 2 or inputs.shape[1] != self.spec.d:
             raise ValueError("Num prior distributions != num input params")
-        st = engine.DeviceState(inputs.shape[0], inputs.shape[0], self.spec.d)
+        st = engine.DeviceState(inputs.shape[0], inputs.shape[0], self.spec.d,
+                                with_lq=self.spec.has_device_proposal)
         st.set_params_host(inputs)
         return st
 
     def evaluate_log_likelihood(self, inputs):
-        """(N,1)  (vector_mcmc.py:116-118).  Rows outside the prior support keep 0 as in
-        _eval_log_like_if_prior_nonzero (:205-210)."""
+        """(N,1)  (vector_mcmc.py:116-118); every row is evaluated, whatever its prior."""
         st = self._load(inputs)
         engine.eval_incoming(st, self.spec)
         f = int(st.flags.item())
@@ -149,9 +158,12 @@ class B200VectorMCMC:
         assigns (vector_mcmc_kernel.py:10): recover the path object from it."""
         owner = getattr(self.evaluate_log_posterior, "__self__", None)
         if owner is not None and hasattr(owner, "phi") and hasattr(owner, "_lambda"):
-            if getattr(owner, "proposal", None):
-                raise NotImplementedError("GeometricPath(proposal=...) inside smc_metropolis is not on the "
-                                          "device yet (SURVEY.md section 8f-2)")
+            prop = getattr(owner, "proposal", None)
+            if prop is not self._proposal:
+                self.bind_path(owner)
+            if prop and not self.spec.has_device_proposal:
+                raise NotImplementedError("smc_metropolis with a path proposal needs a MultivarIndependent of "
+                                          "scipy norm / uniform components (device log q)")
             return engine.make_path(owner.phi, owner.phi, owner._lambda)
         return engine.make_path(1.0, 1.0, 1.0)       # plain posterior: ll + sum(log priors)
 

@@ -72,6 +72,14 @@ def gauss_problem(d, data_seed=5):
     }
 
 
+def proposal_problem(required_phi=1):
+    """C1 with an initial-particle proposal q = N(2,1) x N(3.5,1.5) (examples/proposal_example)."""
+    p = linear_problem(100)
+    p["proposal"] = [("normal", 2.0, 1.0), ("normal", 3.5, 1.5)]
+    p["required_phi"] = required_phi
+    return p
+
+
 # name -> (problem builder, sampler kind, sampler kwargs, rng seed)
 CASES = {
     "c1_adaptive": (lambda: linear_problem(100), "adaptive",
@@ -90,6 +98,10 @@ CASES = {
                   dict(n=400, K=4, target_ess=0.8, resampler="stratified"), 6),
     "c5_gauss32": (lambda: gauss_problem(32), "adaptive",
                    dict(n=200, K=3, target_ess=0.85, resampler="standard"), 7),
+    "c1_proposal": (lambda: proposal_problem(), "adaptive",
+                    dict(n=400, K=5, target_ess=0.8, resampler="standard"), 8),
+    "c1_proposal_reqphi": (lambda: proposal_problem([0.2, 0.6]), "adaptive",
+                           dict(n=400, K=4, target_ess=0.75, resampler="stratified"), 9),
 }
 
 

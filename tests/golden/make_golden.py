@@ -126,7 +126,11 @@ def run_case(name):
     model, priors, largs, ll_cls = ref_objects(problem)
     rng = np.random.default_rng(seed)
     mcmc = VectorMCMC(model, problem["data"], priors, largs, ll_cls)
-    kernel = VectorMCMCKernel(mcmc, param_order=problem["names"], rng=rng)
+    path = None
+    if problem.get("proposal"):
+        dists = [stats.norm(loc, sc) if k == "normal" else stats.uniform(loc, sc) for k, loc, sc in problem["proposal"]]
+        path = GeometricPath(proposal=MultivarIndependent(*dists), required_phi=problem.get("required_phi", 1))
+    kernel = VectorMCMCKernel(mcmc, param_order=problem["names"], rng=rng, path=path)
     init = None
     if "iw_seed" in kw:
         init = configs.mvn_init_params(kw["n"], kw["iw_seed"])
@@ -173,6 +177,8 @@ def run_case(name):
     }
     if init is not None:
         out["init_params"] = init
+    if kind == "adaptive":
+        out["req_phi_index"] = np.array(smc.req_phi_index, dtype=np.int64)
     if steps[0].params.size * len(steps) <= 40000:            # small cases: every step
         out["params_all"] = np.array([s.params for s in steps])
         out["log_likes_all"] = np.array([s.log_likes for s in steps])
@@ -299,6 +305,9 @@ def unit_vectors():
 
 if __name__ == "__main__":
     print("reference smcpy", smcpy.__version__, "numpy", np.__version__)
-    unit_vectors()
+    only = sys.argv[1:]
+    if not only:
+        unit_vectors()
     for name in configs.CASES:
-        run_case(name)
+        if not only or name in only:
+            run_case(name)

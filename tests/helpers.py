@@ -60,6 +60,11 @@ def make_b200(problem, rng=None, path=None):
     lk, largs = problem["loglike"]
     cls = sb.Normal if lk == "normal" else sb.MVNormal
     mcmc = sb.B200VectorMCMC(model, problem["data"], priors, largs, cls)
+    if path is None and problem.get("proposal"):
+        dists = [stats.norm(loc, sc) if k == "normal" else stats.uniform(loc, sc)
+                 for k, loc, sc in problem["proposal"]]
+        path = sb.GeometricPath(proposal=sb.MultivarIndependent(*dists),
+                                required_phi=problem.get("required_phi", 1))
     kernel = sb.VectorMCMCKernel(mcmc, param_order=problem["names"], rng=rng, path=path)
     return mcmc, kernel
 

@@ -37,7 +37,8 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(L.Rng) == 48
     assert ctypes.sizeof(L.Xchg) == 8 + 8 + 8 * 8 + 8 + 8
     # 8 ints + sigma + 8 args + 2 ptrs + 6 doubles + 6 ints + priors
-    assert ctypes.sizeof(L.Problem) == 32 + 8 + 64 + 16 + 48 + 24 + 32 * 32
+    assert ctypes.sizeof(L.ProposalCol) == 24
+    assert ctypes.sizeof(L.Problem) == 32 + 8 + 64 + 16 + 48 + 24 + 32 * 32 + 8 + 32 * 24
 
 
 def test_argument_errors_are_reported_without_a_gpu():
@@ -46,7 +47,7 @@ def test_argument_errors_are_reported_without_a_gpu():
         L.call("smcb_fill_f64", None, 0, 1.0, None)
     p = L.Problem()
     with pytest.raises(L.SmcbError):
-        L.call("smcb_mh_init", ctypes.byref(p), None, 0, 0, None, None, None, None, None)
+        L.call("smcb_mh_init", ctypes.byref(p), None, 0, 0, None, None, None, None, None, None)
 
 
 def test_no_cpu_fallback():

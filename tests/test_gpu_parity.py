@@ -338,7 +338,8 @@ def test_smc_metropolis_replay_vs_oracle(sb, name):
     phi = 0.37
     accepts = []
     o_rng = np.random.default_rng(99)
-    o_theta, o_ll = orc.smc_metropolis(problem, theta, K, cov, phi, o_rng, trace=accepts)
+    lam = orc.path_lambda(problem.get("required_phi", 1))[0]
+    o_theta, o_ll = orc.smc_metropolis(problem, theta, K, cov, phi, o_rng, lam=lam, trace=accepts)
     mc, kernel = make_b200(problem, rng=np.random.default_rng(99))
     kernel.path.phi = phi
     g_theta, g_ll = mc.smc_metropolis(theta, K, cov)
@@ -372,6 +373,8 @@ def test_full_sampler_replay_vs_reference_fixture(sb, name):
     np.testing.assert_allclose(steps[-1].log_weights, g["log_weights_last"], rtol=RTOL)
     np.testing.assert_allclose(np.array([s.compute_mean(package=False) for s in steps]), g["mean"], rtol=1e-9, atol=1e-12)
     np.testing.assert_array_equal(rng.uniform(0, 1, 4), g["rng_check"])       # tape exactly exhausted
+    if "req_phi_index" in g:
+        np.testing.assert_array_equal(smc.req_phi_index, g["req_phi_index"])
     assert steps[0].attrs["phi"] == 0 and steps[0].attrs["mutation_ratio"] == 0
     assert steps[-1].param_names == tuple(configs.CASES[name][0]()["names"])
 
