@@ -318,13 +318,18 @@ def run_gpu(args):
     roofline = {"kernel": "mh_kernel<linear,normal> (fused Metropolis step, M=1000 reduce in smem)",
                 "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
-                "traffic": None, "avg_launch_ms": mh_ms, "launches_timed": int(mh.size),
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the
+                # ncu --set full capture summarised in profiles/r01_mh_kernels.md (33.63 MB + 2 KB;
+                # the 2^20-particle state is L2 resident, accepted rows are written back lazily)
+                "traffic": 33.63e6, "traffic_source": "profiles/r01_mh_kernels.md (ncu, C2 PPT=4 capture)",
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": mh_ms, "launches_timed": int(mh.size),
                 "share_of_step": share.get("mh_step"),
                 "note": "C2's Metropolis kernel is FP64-pipe bound (SURVEY.md 8d: ~78 flop/B), see fp64",
                 "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
                          "peak_source": "smcb_fp64_probe FMA microbenchmark, this run",
                          "flops_per_particle_step": flops_per_unit}}
-    other = {"share_of_step": share}
+    other = {"share_of_step": share, "avg_ms": {k: float(np.mean(v)) for k, v in prof.items()},
+             "calls_per_step": {k: len(v) for k, v in prof.items()}}
     if "reweight" in prof:                      # single-GPU entry points (fused calls) only
         rw = float(np.mean(prof["reweight"]))
         other["reweight"] = {"avg_ms": rw, "gbps": 48.0 * N_PER_GPU / rw / 1e6,

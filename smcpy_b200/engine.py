@@ -375,13 +375,14 @@ def reweight(st, path):
             call("smcb_reweight", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
                  C.byref(path), ptr(st.log_w_alt), ptr(st.w_alt), ptr(st.scalars), ptr(st.ws), s)
     else:
-        part = st.scalars[8:11]
-        call("smcb_reweight_partials", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
-             C.byref(path), ptr(part), ptr(st.ws), s)
-        parts = _all_gather_rows(part)                       # rank-ordered (max, S1, S2)
-        call("smcb_lse_merge", ptr(parts), world, ptr(st.scalars), s)
-        call("smcb_reweight_finalize", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
-             C.byref(path), ptr(st.scalars), ptr(st.log_w_alt), ptr(st.w_alt), s)
+        with _timed("reweight"):
+            part = st.scalars[8:11]
+            call("smcb_reweight_partials", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
+                 C.byref(path), ptr(part), ptr(st.ws), s)
+            parts = _all_gather_rows(part)                       # rank-ordered (max, S1, S2)
+            call("smcb_lse_merge", ptr(parts), world, ptr(st.scalars), s)
+            call("smcb_reweight_finalize", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
+                 C.byref(path), ptr(st.scalars), ptr(st.log_w_alt), ptr(st.w_alt), s)
     st.log_w, st.log_w_alt = st.log_w_alt, st.log_w
     st.w, st.w_alt = st.w_alt, st.w
     st.uniform_weights = False
@@ -478,7 +479,8 @@ def resample(st, kernel, resample_rng, warn_threshold):
     _, world = dist_info()
     if world > 1:
         from .sharded import resample_sharded
-        return resample_sharded(st, kernel, resample_rng, warn_threshold)
+        with _timed("resample"):
+            return resample_sharded(st, kernel, resample_rng, warn_threshold)
     n = st.n
     host_rng = isinstance(kernel.rng, np.random.Generator)
     kind = getattr(resample_rng, "kind", None)
@@ -532,14 +534,15 @@ def covariance(st):
             call("smcb_weighted_cov", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.mean), ptr(st.cov),
                  ptr(st.sums), ptr(st.ws), s)
     else:
-        call("smcb_weighted_sums1", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.sums), ptr(st.ws), s)
-        _all_reduce_sum(st.sums[:1 + d])
-        call("smcb_mean_from_sums", ptr(st.sums), d, ptr(st.mean), s)
-        s2 = st.sums[1 + d:]
-        call("smcb_weighted_sums2", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.mean), ptr(s2),
-             ptr(st.ws), s)
-        _all_reduce_sum(s2)
-        call("smcb_cov_from_sums", ptr(st.sums), ptr(s2), d, ptr(st.cov), s)
+        with _timed("cov"):
+            call("smcb_weighted_sums1", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.sums), ptr(st.ws), s)
+            _all_reduce_sum(st.sums[:1 + d])
+            call("smcb_mean_from_sums", ptr(st.sums), d, ptr(st.mean), s)
+            s2 = st.sums[1 + d:]
+            call("smcb_weighted_sums2", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.mean), ptr(s2),
+                 ptr(st.ws), s)
+            _all_reduce_sum(s2)
+            call("smcb_cov_from_sums", ptr(st.sums), ptr(s2), d, ptr(st.cov), s)
     return st.cov
 
 
@@ -632,9 +635,18 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
         if world > 1:
             _all_reduce_sum(st.accept_counts[k:k + 1])
     call("smcb_count_moved", ptr(st.moved), st.n, ptr(st.counts[1:]), ptr(st.ws), s)
-    moved = st.counts[1:2].clone()
     if world > 1:
-        _all_reduce_sum(moved)
+        # one collective for the moved count and the error flags, so that every rank raises
+        # (or none does): [moved, flag bit 0..3 set on this rank]
+        pack = torch.zeros(5, dtype=torch.int64, device=st.cols.device)
+        pack[0] = st.counts[1]
+        pack[1:] = (st.flags.to(torch.int64) >> torch.arange(4, device=st.cols.device)) & 1
+        _all_reduce_sum(pack)
+        host = pack.cpu().numpy()
+        st.flags.fill_(int(sum((1 << b) for b in range(4) if host[1 + b] > 0)))
+        st.check_flags("smc_metropolis")
+        return float(host[0]) / st.n_global
+    moved = st.counts[1:2].clone()
     st.check_flags("smc_metropolis")                         # sync; raises on NaN
     return float(moved.item()) / st.n_global
 
