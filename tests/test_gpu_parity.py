@@ -550,3 +550,69 @@ def test_wide_identity_kernel_tma_path_vs_oracle(sb):
     np.testing.assert_allclose(g_theta, o_theta, rtol=RTOL, atol=1e-12)
     np.testing.assert_allclose(g_ll, o_ll, rtol=RTOL)
     assert 0.05 * n < accepts[0] < 0.95 * n
+
+
+# ------------------------------------------------------------------ host phi policies / step operators
+def test_max_step_and_fixed_time_samplers(sb):
+    """samplers.py:304-454: host phi policies on top of the device optimize_step."""
+    problem = configs.linear_problem(100)
+    mcmc, kernel = make_b200(problem, rng=11)
+    smc = sb.MaxStepSampler(kernel, max_steps=6, show_progress_bar=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steps, mll = smc.sample(3000, 5, target_ess=0.8)
+    assert len(steps) - 1 <= 6 and smc.phi_sequence[-1] == 1.0
+    assert np.all(np.diff(smc.phi_sequence) > 0)
+    mcmc, kernel = make_b200(problem, rng=12)
+    smc = sb.FixedTimeSampler(kernel, time=1e-3, show_progress_bar=False)     # budget already exhausted
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steps, mll = smc.sample(3000, 5, target_ess=0.8)
+    assert smc.phi_sequence[-1] == 1.0 and len(steps) <= 4
+    mcmc, kernel = make_b200(problem, rng=13)
+    smc = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steps, mll = smc.sample(3000, 5, target_ess=0.8, min_dphi=0.3)       # quirk Q10: floor may overshoot 1
+    assert len(steps) - 1 <= 4 and smc.phi_sequence[-1] >= 1.0
+
+
+def test_step_operators_api_parity(sb):
+    """Initializer / Updater / Mutator used object-by-object as in the reference
+    (initializer.py:66-78, updater.py:97-120, mutator.py:52-67) agree with the oracle step."""
+    from smcpy_b200.initializer import Initializer
+    from smcpy_b200.mutator import Mutator
+    from smcpy_b200.updater import Updater
+    problem = configs.linear_problem(60, data_seed=4)
+    n, K, phi = 700, 4, 0.02
+    o_rng = np.random.default_rng(21)
+    o0 = orc.initialize(problem, n, o_rng)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o1 = orc.smc_step(problem, o0, phi, 0.0, K, 0.9, o_rng)
+    mcmc, kernel = make_b200(problem, rng=np.random.default_rng(21))
+    p0 = Initializer(kernel).initialize_particles(n)
+    assert p0.attrs["phi"] == 0 and p0.attrs["mutation_ratio"] == 0
+    np.testing.assert_allclose(p0.params, o0.params, rtol=1e-15)
+    np.testing.assert_allclose(p0.log_likes, o0.log_likes, rtol=RTOL)
+    np.testing.assert_array_equal(p0.log_weights, np.full((n, 1), np.log(1 / n)))
+    kernel.path.phi = phi
+    upd = Updater(0.9, kernel, sb.standard)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        p1 = upd.update(p0)
+    assert upd.resampled == o1.resampled and upd.ess == pytest.approx(o1.ess, rel=RTOL)
+    assert p1.total_unnorm_log_weight == pytest.approx(o1.total_unnorm_log_weight, rel=RTOL)
+    p2 = Mutator(kernel).mutate(p1, K)
+    np.testing.assert_allclose(p2.params, o1.params, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(p2.log_likes, o1.log_likes, rtol=RTOL)
+    assert p2.attrs["mutation_ratio"] == o1.mutation_ratio and p2.attrs["phi"] == phi
+    q = p2.copy()
+    q.attrs["phi"] = -1
+    assert p2.attrs["phi"] == phi and q.num_particles == n
+    # a Particles object built from host arrays goes through the same operators
+    host = sb.Particles(p0.param_dict, p0.log_likes, p0.log_weights)
+    upd2 = Updater(0.0, kernel, sb.standard)                   # never resample
+    r = upd2.update(host)
+    assert not upd2.resampled
+    np.testing.assert_allclose(np.exp(r.log_weights).sum(), 1.0, rtol=1e-12)
