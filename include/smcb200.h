@@ -249,7 +249,9 @@ int smcb_log_priors(const smcb_problem_t* prob, const double* params, int64_t st
  * accept_counts (device, int64[SMCB_MAX_MCMC_STEPS]): slot `step` receives this step's number
  * of accepted particles; slots < step (already all-reduced across GPUs by the caller) give
  * the covariance scale s (x1/5 below 30 %, x2 above 70 %). `moved` (n bytes) |= accepted.
- * lq (required iff prob->has_proposal): resident proposal log-pdf column, updated in place. */
+ * lq (required iff prob->has_proposal): resident proposal log-pdf column, updated in place.
+ * flags: device int32[4], zero-initialised once: [0] SMCB_FLAG_* bits, [1] and [2] are the
+ * library's dynamic tile counter and ticket (left at zero by every launch). */
 int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride,
                  int64_t n, int64_t n_global, double* ll, double* lp, double* lq, uint8_t* moved,
                  const double* chol, int64_t* accept_counts, int32_t step, const smcb_rng_t* rng,

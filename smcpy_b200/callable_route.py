@@ -34,7 +34,7 @@ def _model_ll(st, spec, soa_params, lp, ll_out):
 def eval_incoming_callable(st, spec, lp_cols=None):
     call("smcb_log_priors", C.byref(spec.c), ptr(st.cols), st.n, st.n, ptr(st.lp), ptr(lp_cols), stream_ptr())
     if bool(torch.isinf(st.lp).any().item()):
-        st.flags.fill_(_lib.FLAG_PRIOR_OOB)
+        st.flags[0] = _lib.FLAG_PRIOR_OOB
     _model_ll(st, spec, st.params, st.lp, st.ll)
 
 

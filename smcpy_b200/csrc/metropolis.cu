@@ -391,7 +391,10 @@ __host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt) {
 //       TMA: the next tile's d+2 column segments are bulk-copied (cp.async.bulk + mbarrier) into
 //       a shared-memory stage by one elected thread while the block computes the current tile.
 //       PROP: the path has a proposal q: its log-pdf is a third resident column next to ll, lp.
-template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false>
+//       DYN: persistent blocks pull tiles from an atomic counter (a.flags[1]; a.flags[2] is the
+//       ticket with which the last block resets both) -- removes the tail of the FP64-bound kernels.
+template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
+          bool DYN = false>
 __global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -439,7 +442,15 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         __syncthreads();
         if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) tma_issue(blockIdx.x);
     }
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __shared__ long long sh_tile;
+    for (int64_t tile = blockIdx.x;; tile += gridDim.x) {
+        if (DYN) {
+            __syncthreads();                       // previous tile fully consumed sh_tile
+            if (threadIdx.x == 0) sh_tile = (long long)atomicAdd(reinterpret_cast<unsigned int*>(a.flags) + 1, 1u);
+            __syncthreads();
+            tile = sh_tile;
+        }
+        if (tile >= n_tiles) break;
         int64_t idx[PPT];
         bool valid[PPT];
         double th[PPT][DMAX];
@@ -620,6 +631,18 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         }
     }
     if (flag) atomicOr(a.flags, flag);
+    if (DYN) {
+        // the last block to run out of tiles resets the tile counter and the ticket
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int* ctr = reinterpret_cast<unsigned int*>(a.flags);
+            __threadfence();
+            if (atomicAdd(ctr + 2, 1u) == gridDim.x - 1) {
+                ctr[1] = 0u;
+                ctr[2] = 0u;
+            }
+        }
+    }
     if (MODE != 1) return;
     // accept count: warp shuffle reduction, one atomic per warp per launch
 #pragma unroll
@@ -788,14 +811,15 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
     return data + 16;      // + DMAX*DMAX doubles for the Cholesky factor, added per instantiation
 }
 
-template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false>
+template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
+          bool DYN = false>
 static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     const size_t smem = mh_smem_bytes(&a.prob) + (size_t)DMAX * DMAX * sizeof(double) +
                         (TMA ? (size_t)(64 + (DMAX + 2) * TPB) * sizeof(double) : 0);
     if (TMA) {
         static bool attr = false;
         if (!attr) {
-            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP>,
+            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr = true;
         }
@@ -804,7 +828,7 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP>, TPB,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN>, TPB,
                                                           smem) != cudaSuccess || nb < 1)
             nb = 1;
         blocks_per_sm = nb;
@@ -815,10 +839,10 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     // model; one tile per block for the FP64-bound models, where the hardware block scheduler
     // balances the tail better than a static tile loop (SMCB_PERSIST overrides: tuning aid)
     static const int persist_env = getenv("SMCB_PERSIST") ? atoi(getenv("SMCB_PERSIST")) : -1;
-    const bool persist = persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL);
+    const bool persist = DYN || (persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL));
     const int64_t cap = persist ? (int64_t)kNumSMs * blocks_per_sm : n_tiles;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP><<<grid, TPB, smem, s>>>(a);
+    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN><<<grid, TPB, smem, s>>>(a);
     return check_launch("mh_kernel");
 }
 
@@ -857,6 +881,14 @@ static int launch_one(const MhArgs& a, cudaStream_t s) {
         if (cfg == 1) return launch_cfg<KIND, DMAX, MODE, 128, 2>(a, s);
         if (cfg == 2) return launch_cfg<KIND, DMAX, MODE, 128, 4>(a, s);
         if (cfg == 3) return launch_cfg<KIND, DMAX, MODE, 256, 4>(a, s);
+        if constexpr (MODE == 1 && DMAX == 2) {
+            // persistent blocks + dynamic 512-particle tiles (128 threads x 4 particles): measured
+            // 0.2198 ms vs 0.2385 ms for static 1024-particle blocks (C2, same box)
+            const bool dyn_ok = a.prob.n_params == 2 && a.n >= (int64_t)kNumSMs * 16 * 256;
+            if (cfg == 5) return launch_cfg2<KIND, DMAX, MODE, 64, 4, true, false, false, true>(a, s);
+            if (cfg == 6 || (cfg < 0 && dyn_ok))
+                return launch_cfg2<KIND, DMAX, MODE, 128, 4, true, false, false, true>(a, s);
+        }
         if (a.n >= (int64_t)kNumSMs * 4 * 1024) return launch_cfg<KIND, DMAX, MODE, 256, 4>(a, s);
         if (a.n >= (int64_t)kNumSMs * 4 * 512) return launch_cfg<KIND, DMAX, MODE, 128, 4>(a, s);
         if (a.n >= (int64_t)kNumSMs * 4 * 256) return launch_cfg<KIND, DMAX, MODE, 128, 2>(a, s);

@@ -277,7 +277,7 @@ class DeviceState:
         self.idx = torch.empty(self.n, dtype=torch.int64, device=dv)
         self.moved = torch.zeros(self.n, dtype=torch.uint8, device=dv)
         self.accept_counts = torch.zeros(_lib.MAX_MCMC_STEPS, dtype=torch.int64, device=dv)
-        self.flags = torch.zeros(1, dtype=torch.int32, device=dv)
+        self.flags = torch.zeros(4, dtype=torch.int32, device=dv)   # [0] error bits, [1..2] library tile counter/ticket
         self.scalars = torch.zeros(16, dtype=f64, device=dv)
         self.bis = torch.zeros(16, dtype=f64, device=dv)
         self.counts = torch.zeros(4, dtype=torch.int64, device=dv)
@@ -330,10 +330,10 @@ class DeviceState:
         self.uniform_weights = True
 
     def check_flags(self, where, allow_oob=False):
-        f = int(self.flags.item())
+        f = int(self.flags[0].item())
         if f == 0:
             return 0
-        self.flags.zero_()
+        self.flags[0] = 0
         if (f & _lib.FLAG_PRIOR_OOB) and not allow_oob:
             raise ValueError("Initial inputs are out of bounds; prior log prob = -inf (%s)" % where)
         if f & _lib.FLAG_MODEL_NAN:
@@ -549,9 +549,9 @@ def covariance(st):
 def cholesky(st, cov_dev=None):
     call("smcb_cholesky", ptr(st.cov if cov_dev is None else cov_dev), st.d, ptr(st.chol), ptr(st.flags),
          stream_ptr())
-    f = int(st.flags.item())
+    f = int(st.flags[0].item())
     if f & _lib.FLAG_CHOL_FAIL:
-        st.flags.zero_()
+        st.flags[0] = 0
         cov = (st.cov if cov_dev is None else cov_dev).cpu().numpy()
         st.chol.copy_(dev(_host_chol_psd(cov)))
     return st.chol
@@ -640,10 +640,10 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
         # (or none does): [moved, flag bit 0..3 set on this rank]
         pack = torch.zeros(5, dtype=torch.int64, device=st.cols.device)
         pack[0] = st.counts[1]
-        pack[1:] = (st.flags.to(torch.int64) >> torch.arange(4, device=st.cols.device)) & 1
+        pack[1:] = (st.flags[0].to(torch.int64) >> torch.arange(4, device=st.cols.device)) & 1
         _all_reduce_sum(pack)
         host = pack.cpu().numpy()
-        st.flags.fill_(int(sum((1 << b) for b in range(4) if host[1 + b] > 0)))
+        st.flags[0] = int(sum((1 << b) for b in range(4) if host[1 + b] > 0))
         st.check_flags("smc_metropolis")
         return float(host[0]) / st.n_global
     moved = st.counts[1:2].clone()

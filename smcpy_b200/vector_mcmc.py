@@ -148,7 +148,7 @@ class B200VectorMCMC:
         """(N,1)  (vector_mcmc.py:116-118); every row is evaluated, whatever its prior."""
         st = self._load(inputs)
         engine.eval_incoming(st, self.spec)
-        f = int(st.flags.item())
+        f = int(st.flags[0].item())
         if f & _lib.FLAG_MODEL_NAN:
             raise ValueError("nan in model output.")
         return st.ll.cpu().numpy().reshape(-1, 1)
