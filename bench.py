@@ -327,7 +327,9 @@ def run_gpu(args):
                 "note": "C2's Metropolis kernel is FP64-pipe bound (SURVEY.md 8d: ~78 flop/B), see fp64",
                 "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
                          "peak_source": "smcb_fp64_probe FMA microbenchmark, this run",
-                         "flops_per_particle_step": flops_per_unit}}
+                         "flops_per_particle_step": flops_per_unit,
+                         # FP64 instructions issued (fma, sub, fma per data point) / FMA issue peak
+                         "issue_frac": (3.0 * M_DATA * N_PER_GPU / (mh_ms * 1e-3)) / (fp64_peak * 1e12 / 2.0)}}
     other = {"share_of_step": share, "avg_ms": {k: float(np.mean(v)) for k, v in prof.items()},
              "calls_per_step": {k: len(v) for k, v in prof.items()}}
     if "reweight" in prof:                      # single-GPU entry points (fused calls) only
