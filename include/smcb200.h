@@ -43,7 +43,8 @@ enum {
     SMCB_MODEL_IDENTITY = 3      /* y_j = theta_j               (config C5) */
 };
 /* log-likelihoods (smcpy/log_likelihoods.py) */
-enum { SMCB_LL_NORMAL = 1 /* :22-49 */, SMCB_LL_MVNORMAL = 2 /* :121-192 */ };
+enum { SMCB_LL_NORMAL = 1 /* :22-49 */, SMCB_LL_MVNORMAL = 2 /* :121-192 */, SMCB_LL_MULTISOURCE = 3 /* :52-118 */ };
+#define SMCB_MAX_SEGMENTS 8
 /* priors (smcpy/mcmc/vector_mcmc.py:98-114) */
 enum {
     SMCB_PRIOR_UNIFORM = 1,           /* scipy.stats.uniform(loc=a, scale=b) */
@@ -103,6 +104,12 @@ typedef struct smcb_problem {
     int32_t has_proposal;    /* 1: the path has a proposal; one entry per parameter column below */
     int32_t pad;
     smcb_proposal_col_t proposal[SMCB_MAX_PARAMS];
+    /* MultiSourceNormal: consecutive data segments with their own std-dev */
+    int32_t n_segments;
+    int32_t seg_len[SMCB_MAX_SEGMENTS];
+    int32_t seg_sigma_col[SMCB_MAX_SEGMENTS]; /* -1 = fixed (seg_sigma), else parameter column */
+    int32_t pad2;
+    double seg_sigma[SMCB_MAX_SEGMENTS];
 } smcb_problem_t;
 
 /* GeometricPath state (smcpy/paths.py:64-112): exponents are derived inside the

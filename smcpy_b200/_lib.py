@@ -19,7 +19,8 @@ MAX_COV_ARGS = 6
 MAX_MCMC_STEPS = 4096
 
 MODEL_LINEAR, MODEL_SPRING_MASS, MODEL_IDENTITY = 1, 2, 3
-LL_NORMAL, LL_MVNORMAL = 1, 2
+LL_NORMAL, LL_MVNORMAL, LL_MULTISOURCE = 1, 2, 3
+MAX_SEGMENTS = 8
 PRIOR_UNIFORM, PRIOR_IMPROPER_UNIFORM, PRIOR_IMPROPER_COV = 1, 2, 3
 FLAG_PRIOR_OOB, FLAG_MODEL_NAN, FLAG_COV_NOT_PD, FLAG_CHOL_FAIL = 1, 2, 4, 8
 RESAMPLE_STANDARD, RESAMPLE_STRATIFIED, RESAMPLE_SYSTEMATIC = 0, 1, 2
@@ -45,7 +46,9 @@ class Problem(C.Structure):
                 ("model_args", C.c_double * 8), ("data", C.c_void_p), ("xgrid", C.c_void_p),
                 ("cov_fixed", C.c_double * MAX_COV_ARGS), ("cov_param_col", C.c_int32 * MAX_COV_ARGS),
                 ("priors", Prior * MAX_PRIORS), ("has_proposal", C.c_int32), ("pad", C.c_int32),
-                ("proposal", ProposalCol * MAX_PARAMS)]
+                ("proposal", ProposalCol * MAX_PARAMS), ("n_segments", C.c_int32),
+                ("seg_len", C.c_int32 * MAX_SEGMENTS), ("seg_sigma_col", C.c_int32 * MAX_SEGMENTS),
+                ("pad2", C.c_int32), ("seg_sigma", C.c_double * MAX_SEGMENTS)]
 
 
 class Path(C.Structure):

@@ -386,6 +386,61 @@ __host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt) {
     return 65536 / (tpb * regs) > 0 ? 65536 / (tpb * regs) : 1;
 }
 
+// MultiSourceNormal (log_likelihoods.py:52-118) for the three built-in models: consecutive data
+// segments, each with its own (fixed or sampled) std-dev; data resident in shared memory.
+// Generic one-point-at-a-time loop: this likelihood is a coverage feature, not a tuned path.
+template <int KIND, int DMAX>
+__device__ __forceinline__ double ll_multisource(const MhArgs& a, const double (&th)[DMAX], bool run,
+                                                 const double* sdata) {
+    if (!run) return 0.0;
+    const double2* sxy = reinterpret_cast<const double2*>(sdata);
+    double x = a.prob.model_args[0], v = a.prob.model_args[1];          // spring-mass state
+    const int nsub = (int)a.prob.model_args[3];
+    const double h = (KIND == K_SPRING_NORMAL) ? a.prob.model_args[2] / (double)nsub : 0.0;
+    double ll = 0.0;
+    int j = 0;
+    for (int sgm = 0; sgm < a.prob.n_segments; ++sgm) {
+        const int len = a.prob.seg_len[sgm];
+        if (len == 0) continue;
+        double sigma = a.prob.seg_sigma[sgm];
+        const int col = a.prob.seg_sigma_col[sgm];
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k) sigma = (k == col) ? th[k] : sigma;
+        double ssq = 0.0;
+        for (int e = j + len; j < e; ++j) {
+            double out;
+            if (KIND == K_LINEAR_NORMAL) {
+                out = fma(th[0], sxy[j].x, th[1]);
+            } else if (KIND == K_SPRING_NORMAL) {
+                if (j > 0) {
+                    for (int s = 0; s < nsub; ++s) {
+                        const double K = th[0], g = th[1], hh = 0.5 * h, h6 = h / 6.0;
+                        const double k1x = v, k1v = g - K * x;
+                        const double x2 = x + hh * k1x, v2 = v + hh * k1v;
+                        const double k2x = v2, k2v = g - K * x2;
+                        const double x3 = x + hh * k2x, v3 = v + hh * k2v;
+                        const double k3x = v3, k3v = g - K * x3;
+                        const double x4 = x + h * k3x, v4 = v + h * k3v;
+                        const double k4x = v4, k4v = g - K * x4;
+                        x = x + h6 * (k1x + 2.0 * k2x + 2.0 * k3x + k4x);
+                        v = v + h6 * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
+                    }
+                }
+                out = x;
+            } else {
+                out = 0.0;
+#pragma unroll
+                for (int k = 0; k < DMAX; ++k) out = (k == j) ? th[k] : out;
+            }
+            const double y = (KIND == K_LINEAR_NORMAL) ? sxy[j].y : sdata[j];
+            const double dd = out - y;
+            ssq = fma(dd, dd, ssq);
+        }
+        ll += normal_ll(ssq, sigma, len);
+    }
+    return ll;
+}
+
 // mode: 0 = init (evaluate incoming particles), 1 = fused Metropolis step, 2 = propose only,
 //       3 = log-priors only.  EXACT: n_params == DMAX (drops every per-column bounds check).
 //       TMA: the next tile's d+2 column segments are bulk-copied (cp.async.bulk + mbarrier) into
@@ -393,8 +448,9 @@ __host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt) {
 //       PROP: the path has a proposal q: its log-pdf is a third resident column next to ll, lp.
 //       DYN: persistent blocks pull tiles from an atomic counter (a.flags[1]; a.flags[2] is the
 //       ticket with which the last block resets both) -- removes the tail of the FP64-bound kernels.
+//       MULTI: MultiSourceNormal likelihood (segment table in the problem).
 template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
-          bool DYN = false>
+          bool DYN = false, bool MULTI = false>
 __global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -574,7 +630,10 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             not_pd[p] = false;
             run_any = run_any || run[p];
         }
-        if (KIND == K_LINEAR_NORMAL) {
+        if (MULTI) {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) ll_new[p] = ll_multisource<KIND, DMAX>(a, th[p], run[p], sdata);
+        } else if (KIND == K_LINEAR_NORMAL) {
             ll_linear_normal<DMAX, PPT>(a, th, run_any, resident, sdata, ll_new);
         } else {
 #pragma unroll
@@ -812,14 +871,14 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
 }
 
 template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
-          bool DYN = false>
+          bool DYN = false, bool MULTI = false>
 static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     const size_t smem = mh_smem_bytes(&a.prob) + (size_t)DMAX * DMAX * sizeof(double) +
                         (TMA ? (size_t)(64 + (DMAX + 2) * TPB) * sizeof(double) : 0);
     if (TMA) {
         static bool attr = false;
         if (!attr) {
-            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN>,
+            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr = true;
         }
@@ -828,7 +887,7 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN>, TPB,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI>, TPB,
                                                           smem) != cudaSuccess || nb < 1)
             nb = 1;
         blocks_per_sm = nb;
@@ -842,7 +901,7 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     const bool persist = DYN || (persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL));
     const int64_t cap = persist ? (int64_t)kNumSMs * blocks_per_sm : n_tiles;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN><<<grid, TPB, smem, s>>>(a);
+    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI><<<grid, TPB, smem, s>>>(a);
     return check_launch("mh_kernel");
 }
 
@@ -870,6 +929,15 @@ static int launch_cfg(const MhArgs& a, cudaStream_t s) {
 template <int KIND, int DMAX, int MODE>
 static int launch_one(const MhArgs& a, cudaStream_t s) {
     if constexpr (MODE == 0 || MODE == 1) {
+        if constexpr (KIND != K_LINEAR_MVN) {
+            if (a.prob.loglike_id == SMCB_LL_MULTISOURCE) {
+                if (a.prob.has_proposal) {
+                    set_error("MultiSourceNormal with a path proposal has no device kernel");
+                    return SMCB_ERR_UNSUPPORTED;
+                }
+                return launch_cfg2<KIND, DMAX, MODE, kMhThreads, 1, false, false, false, false, true>(a, s);
+            }
+        }
         // paths with a proposal: generic 1-particle-per-thread variant with the log q column
         if (a.prob.has_proposal) return launch_cfg2<KIND, DMAX, MODE, kMhThreads, 1, false, false, true>(a, s);
     }
@@ -918,13 +986,20 @@ static int dispatch(const MhArgs& a, cudaStream_t s) {
         if (d <= 8) SMCB_CASE(K_IDENTITY_NORMAL, 8);
         if (d <= 16) SMCB_CASE(K_IDENTITY_NORMAL, 16);
         if (d <= 32) SMCB_CASE(K_IDENTITY_NORMAL, 32);
+    } else if (p.loglike_id == SMCB_LL_MULTISOURCE && p.model_id == SMCB_MODEL_LINEAR) {
+        if (d <= 4) SMCB_CASE(K_LINEAR_NORMAL, 4);
+        if (d <= 8) SMCB_CASE(K_LINEAR_NORMAL, 8);
+    } else if (p.loglike_id == SMCB_LL_MULTISOURCE && p.model_id == SMCB_MODEL_SPRING_MASS) {
+        if (d <= 4) SMCB_CASE(K_SPRING_NORMAL, 4);
+        if (d <= 8) SMCB_CASE(K_SPRING_NORMAL, 8);
     } else if (p.loglike_id == SMCB_LL_NORMAL && p.model_id == SMCB_MODEL_LINEAR) {
         if (d == 2) SMCB_CASE(K_LINEAR_NORMAL, 2);
         if (d == 3) SMCB_CASE(K_LINEAR_NORMAL, 4);
     } else if (p.loglike_id == SMCB_LL_NORMAL && p.model_id == SMCB_MODEL_SPRING_MASS) {
         if (d == 2) SMCB_CASE(K_SPRING_NORMAL, 2);
         if (d == 3) SMCB_CASE(K_SPRING_NORMAL, 4);
-    } else if (p.loglike_id == SMCB_LL_NORMAL && p.model_id == SMCB_MODEL_IDENTITY) {
+    } else if ((p.loglike_id == SMCB_LL_NORMAL || p.loglike_id == SMCB_LL_MULTISOURCE) &&
+               p.model_id == SMCB_MODEL_IDENTITY) {
         if (d <= 2) SMCB_CASE(K_IDENTITY_NORMAL, 2);
         if (d <= 4) SMCB_CASE(K_IDENTITY_NORMAL, 4);
         if (d <= 8) SMCB_CASE(K_IDENTITY_NORMAL, 8);
@@ -965,6 +1040,24 @@ static int validate_problem(const smcb_problem_t* p, ColPriors* cp) {
         if (p->model_id == SMCB_MODEL_SPRING_MASS && (p->n_model_params != 2 || p->model_args[3] < 1)) { set_error("spring-mass model needs 2 params and nsub >= 1"); return SMCB_ERR_ARG; }
         if (p->model_id == SMCB_MODEL_IDENTITY && p->n_model_params != p->n_data) { set_error("identity model needs n_data == n_model_params"); return SMCB_ERR_ARG; }
         if (p->model_id == SMCB_MODEL_IDENTITY && p->sigma_is_param) { set_error("identity model: fused kernels need a fixed sigma"); return SMCB_ERR_UNSUPPORTED; }
+        if (cp->n_cov > 0) { set_error("ImproperCov priors are fused for the MVNormal likelihood only"); return SMCB_ERR_UNSUPPORTED; }
+    } else if (p->loglike_id == SMCB_LL_MULTISOURCE) {
+        if (p->n_segments < 1 || p->n_segments > SMCB_MAX_SEGMENTS) { set_error("MultiSourceNormal: 1..8 segments"); return SMCB_ERR_ARG; }
+        int total = 0, n_sampled = 0;
+        for (int k = 0; k < p->n_segments; ++k) {
+            if (p->seg_len[k] < 0) { set_error("negative segment length"); return SMCB_ERR_ARG; }
+            total += p->seg_len[k];
+            if (p->seg_sigma_col[k] >= 0) {
+                ++n_sampled;
+                if (p->seg_sigma_col[k] >= p->n_params) { set_error("segment sigma column out of range"); return SMCB_ERR_ARG; }
+            }
+        }
+        if (total != p->n_data) { set_error("data segments in args[0] must sum to dim of data"); return SMCB_ERR_ARG; }
+        if (p->n_model_params + n_sampled != p->n_params) { set_error("MultiSourceNormal: n_model_params + sampled sigmas != n_params"); return SMCB_ERR_ARG; }
+        if (p->n_data > kChunk) { set_error("MultiSourceNormal: at most %d data points", kChunk); return SMCB_ERR_UNSUPPORTED; }
+        if (p->model_id == SMCB_MODEL_LINEAR && (!p->xgrid || p->n_model_params != 2)) { set_error("linear model needs xgrid and 2 params"); return SMCB_ERR_ARG; }
+        if (p->model_id == SMCB_MODEL_SPRING_MASS && (p->n_model_params != 2 || p->model_args[3] < 1)) { set_error("spring-mass model needs 2 params and nsub >= 1"); return SMCB_ERR_ARG; }
+        if (p->model_id == SMCB_MODEL_IDENTITY && p->n_model_params != p->n_data) { set_error("identity model needs n_data == n_model_params"); return SMCB_ERR_ARG; }
         if (cp->n_cov > 0) { set_error("ImproperCov priors are fused for the MVNormal likelihood only"); return SMCB_ERR_UNSUPPORTED; }
     } else if (p->loglike_id == SMCB_LL_MVNORMAL) {
         if (p->model_id != SMCB_MODEL_LINEAR || !p->xgrid || p->n_model_params != 2) { set_error("MVNormal is built in for the linear model only"); return SMCB_ERR_ARG; }

@@ -179,6 +179,27 @@ class ProblemSpec:
             c.sigma_is_param = 1 if log_like_args is None else 0
             c.sigma = 0.0 if log_like_args is None else float(np.asarray(log_like_args).reshape(-1)[0])
             c.n_model_params = d - c.sigma_is_param
+        elif kind == "multisource":
+            lens, stds = list(log_like_args[0]), list(log_like_args[1])
+            if len(lens) != len(stds) or len(lens) > _lib.MAX_SEGMENTS:
+                raise NotImplementedError("MultiSourceNormal on the device supports up to %d segments" % _lib.MAX_SEGMENTS)
+            if sum(lens) != data.reshape(-1).shape[0]:
+                raise ValueError("data segments in args[0] must sum to dim of data")
+            c.loglike_id = _lib.LL_MULTISOURCE
+            c.n_data = int(data.reshape(-1).shape[0])
+            c.n_snapshots = 1
+            n_none = stds.count(None)
+            c.n_segments = len(lens)
+            j = 0
+            for i, (ln, sd) in enumerate(zip(lens, stds)):
+                c.seg_len[i] = int(ln)
+                if sd is None:
+                    c.seg_sigma_col[i] = d - n_none + j
+                    j += 1
+                else:
+                    c.seg_sigma_col[i] = -1
+                    c.seg_sigma[i] = float(sd)
+            c.n_model_params = d - n_none
         elif kind == "mvnormal":
             if data.ndim != 2:
                 raise ValueError("MVNormal data must be (snapshots, features)")
@@ -223,7 +244,7 @@ class ProblemSpec:
             if not callable(model):
                 raise TypeError("model must be a smcpy_b200.models.DeviceModel or a torch callable")
             if kind != "normal":
-                raise NotImplementedError("torch-callable models support the Normal likelihood")
+                raise NotImplementedError("torch-callable models support the Normal likelihood only")
             c.model_id = _lib.MODEL_IDENTITY      # unused by the un-fused kernels
         self.c = c
         self.device = rt.device

@@ -33,6 +33,18 @@ class Normal(BaseLogLike):
     kind = "normal"
 
 
+class MultiSourceNormal(Normal):
+    """Several data sources with their own std-dev: args = [segment lengths, std-devs], None
+    std-devs are sampled as the trailing parameter columns (smcpy/log_likelihoods.py:52-118)."""
+    kind = "multisource"
+
+    def __init__(self, model, data, args):
+        super().__init__(model, data, args)
+        self._num_nones = list(self._args[1]).count(None)
+        if sum(args[0]) != np.asarray(data).shape[0]:
+            raise ValueError("data segments in args[0] must sum to dim of data")
+
+
 class MVNormal(BaseLogLike):
     """Multivariate normal errors; args = packed row-major upper-triangular covariance terms,
     None entries are sampled as the trailing parameter columns
@@ -51,4 +63,6 @@ def loglike_kind(obj_or_cls):
         return "normal"
     if name == "MVNormal":
         return "mvnormal"
+    if name == "MultiSourceNormal":
+        return "multisource"
     raise NotImplementedError("log-likelihood %s has no device kernel (Normal, MVNormal)" % name)

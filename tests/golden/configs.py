@@ -80,6 +80,22 @@ def proposal_problem(required_phi=1):
     return p
 
 
+def multisource_problem(data_seed=12):
+    """Linear model, three data sources with different noise levels; the middle one's std-dev is
+    sampled (examples/likelihood_functions/multisource_example)."""
+    x = np.linspace(0.5, 2.5, 90)
+    rng = np.random.default_rng(data_seed)
+    lens, true_std = (40, 20, 30), (0.3, 1.0, 0.6)
+    noise = np.concatenate([rng.normal(0, s, n) for n, s in zip(lens, true_std)])
+    return {
+        "model": ("linear", x),
+        "data": 2.0 * x + 3.5 + noise,
+        "loglike": ("multisource", [lens, (0.3, None, 0.6)]),
+        "priors": [("uniform", -6.0, 12.0), ("uniform", -6.0, 12.0), ("uniform", 0.0, 5.0)],
+        "names": ["a", "b", "std1"],
+    }
+
+
 # name -> (problem builder, sampler kind, sampler kwargs, rng seed)
 CASES = {
     "c1_adaptive": (lambda: linear_problem(100), "adaptive",
@@ -98,6 +114,9 @@ CASES = {
                   dict(n=400, K=4, target_ess=0.8, resampler="stratified"), 6),
     "c5_gauss32": (lambda: gauss_problem(32), "adaptive",
                    dict(n=200, K=3, target_ess=0.85, resampler="standard"), 7),
+    "c2_multisource": (lambda: multisource_problem(), "fixed",
+                       dict(n=400, K=5, phi=np.linspace(0, 1, 10) ** 2, ess_threshold=0.7,
+                            resampler="standard"), 10),
     "c1_proposal": (lambda: proposal_problem(), "adaptive",
                     dict(n=400, K=5, target_ess=0.8, resampler="standard"), 8),
     "c1_proposal_reqphi": (lambda: proposal_problem([0.2, 0.6]), "adaptive",

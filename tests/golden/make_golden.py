@@ -26,7 +26,7 @@ sys.path.insert(0, os.environ.get("SMCPY_REFERENCE", "/root/reference"))
 import smcpy                                                  # noqa: E402
 from smcpy import (AdaptiveSampler, FixedPhiSampler, VectorMCMC, VectorMCMCKernel,  # noqa: E402
                    ImproperUniform, ImproperCov, MVNormal)
-from smcpy.log_likelihoods import Normal                      # noqa: E402
+from smcpy.log_likelihoods import MultiSourceNormal, Normal   # noqa: E402
 from smcpy.paths import GeometricPath                         # noqa: E402
 from smcpy.proposals import MultivarIndependent               # noqa: E402
 from smcpy.resampler_rngs import standard, stratified         # noqa: E402
@@ -59,7 +59,9 @@ def ref_objects(problem):
         elif p[0] == "improper_cov":
             priors.append(ImproperCov(int(p[1]), dof=5, S=np.eye(int(p[1]))))
     lk, largs = problem["loglike"]
-    ll_cls = Normal if lk == "normal" else MVNormal
+    ll_cls = {"normal": Normal, "mvnormal": MVNormal, "multisource": MultiSourceNormal}[lk]
+    if lk == "multisource":
+        largs = [tuple(largs[0]), tuple(largs[1])]
     return model, priors, largs, ll_cls
 
 
@@ -256,6 +258,14 @@ def unit_vectors():
     mth2 = np.column_stack([th[:, :2], rng.uniform(-0.1, 0.1, 40), rng.uniform(0.3, 0.6, 40)])
     out.update(mv_theta_mixed=mth2,
                mv_mixed=MVNormal(lambda t: orc.model_linear(t, X), mdata, args_mixed)(mth2).flatten())
+
+    # MultiSourceNormal incl. an empty segment and two sampled std-devs  (log_likelihoods.py:52-118)
+    msx = np.linspace(0, 1, 12)
+    msd = 1.5 * msx + 0.5 + rng.normal(0, 0.3, 12)
+    msth = np.column_stack([rng.uniform(1, 2, 30), rng.uniform(0, 1, 30), rng.uniform(0.2, 1, 30), rng.uniform(0.2, 1, 30)])
+    msargs = [(5, 0, 3, 4), (None, 0.4, 0.25, None)]
+    out.update(ms_x=msx, ms_data=msd, ms_theta=msth,
+               ms_ll=MultiSourceNormal(lambda t: orc.model_linear(t, msx), msd, msargs)(msth))
 
     # priors                                                   (priors.py, scipy.stats.uniform)
     xs = np.concatenate([rng.uniform(-8, 8, 50), [-6.0, 6.0, np.nextafter(6.0, 7.0), np.nextafter(-6.0, -7)]])

@@ -58,7 +58,7 @@ def make_b200(problem, rng=None, path=None):
         elif p[0] == "improper_cov":
             priors.append(sb.ImproperCov(int(p[1]), dof=5, S=np.eye(int(p[1]))))
     lk, largs = problem["loglike"]
-    cls = sb.Normal if lk == "normal" else sb.MVNormal
+    cls = {"normal": sb.Normal, "mvnormal": sb.MVNormal, "multisource": sb.MultiSourceNormal}[lk]
     mcmc = sb.B200VectorMCMC(model, problem["data"], priors, largs, cls)
     if path is None and problem.get("proposal"):
         dists = [stats.norm(loc, sc) if k == "normal" else stats.uniform(loc, sc)

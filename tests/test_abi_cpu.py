@@ -38,7 +38,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(L.Xchg) == 8 + 8 + 8 * 8 + 8 + 8
     # 8 ints + sigma + 8 args + 2 ptrs + 6 doubles + 6 ints + priors
     assert ctypes.sizeof(L.ProposalCol) == 24
-    assert ctypes.sizeof(L.Problem) == 32 + 8 + 64 + 16 + 48 + 24 + 32 * 32 + 8 + 32 * 24
+    assert ctypes.sizeof(L.Problem) == 32 + 8 + 64 + 16 + 48 + 24 + 32 * 32 + 8 + 32 * 24 + 4 + 32 + 32 + 4 + 64
 
 
 def test_argument_errors_are_reported_without_a_gpu():

@@ -301,6 +301,12 @@ def test_loglikes_vs_reference_fixture(sb):
     args = [0.5, None, 0.005, None, 0.04, 1.0]
     mc = sb.B200VectorMCMC(sb.LinearModel(X), U["mv_data"], wide + [stats.uniform(-1, 2)] * 2, args, sb.MVNormal)
     np.testing.assert_allclose(mc.evaluate_log_likelihood(U["mv_theta_mixed"])[:, 0], U["mv_mixed"], rtol=RTOL)
+    # MultiSourceNormal incl. an empty segment and two sampled std-devs (log_likelihoods.py:52-118)
+    mc = sb.B200VectorMCMC(sb.LinearModel(U["ms_x"]), U["ms_data"], wide + [stats.uniform(0, 10)] * 2,
+                           [(5, 0, 3, 4), (None, 0.4, 0.25, None)], sb.MultiSourceNormal)
+    np.testing.assert_allclose(mc.evaluate_log_likelihood(U["ms_theta"])[:, 0], U["ms_ll"], rtol=RTOL)
+    with pytest.raises(ValueError, match="must sum to dim of data"):
+        sb.MultiSourceNormal(None, np.zeros(5), [(2, 2), (1.0, 1.0)])
     # reference KAT tests/unit/test_likelihoods.py:107-119: -4 pi per snapshot
     mc = sb.B200VectorMCMC(sb.LinearModel(np.array([0.0])), np.full((5, 1), 3.0), wide, [1 / (2 * np.pi)], sb.MVNormal)
     np.testing.assert_allclose(mc.evaluate_log_likelihood(np.array([[0.0, 1.0]] * 4)), -4 * np.pi * 5, rtol=1e-14)

@@ -112,6 +112,21 @@ def test_kat_mvnormal_1d():
     np.testing.assert_allclose(orc.log_likelihood(prob, np.ones((4, 2))), np.full((4, 1), -4 * np.pi * 5))
 
 
+def test_kat_multisource():
+    # tests/unit/test_likelihoods.py:30-104: segment-wise Normal, sampled std-devs are trailing columns
+    x = np.array([1.0, 2, 3])
+    model = lambda q: np.tile(q[:, :1] * 0 + 1, (1, 6)) * np.array([1, 2, 3, 4, 5, 6.0])
+    prob = {"model": ("callable", model), "data": np.array([1.0, 2, 3, 4, 5, 7]),
+            "loglike": ("multisource", [(2, 3, 1), (1.0, 2.0, None)])}
+    th = np.array([[0.3, 0.5], [0.1, 2.0]])
+    got = orc.loglike_multisource(prob, th)
+    want = [-1.0 * np.log(2 * np.pi) - 1.5 * np.log(2 * np.pi * 4.0) - 0.5 * np.log(2 * np.pi * s * s) - 0.5 / (s * s)
+            for s in (0.5, 2.0)]
+    np.testing.assert_allclose(got, want, rtol=1e-14)
+    with pytest.raises(ValueError):
+        orc.loglike_multisource({**prob, "loglike": ("multisource", [(2, 3), (1.0, 2.0)])}, th)
+
+
 def test_kat_path_logpdf():
     # tests/unit/test_kernel_overrides.py:26-58,97-140
     ll = np.full((3, 1), 2.0)
@@ -194,6 +209,9 @@ def test_fixture_resample_likelihoods_priors():
     np.testing.assert_allclose(orc.loglike_mvnormal(prob, U["mv_theta"]), U["mv_all"], rtol=1e-12)
     prob["loglike"] = ("mvnormal", [0.5, None, 0.005, None, 0.04, 1.0])
     np.testing.assert_allclose(orc.loglike_mvnormal(prob, U["mv_theta_mixed"]), U["mv_mixed"], rtol=1e-12)
+    prob = {"model": ("linear", U["ms_x"]), "data": U["ms_data"],
+            "loglike": ("multisource", [(5, 0, 3, 4), (None, 0.4, 0.25, None)])}
+    np.testing.assert_allclose(orc.loglike_multisource(prob, U["ms_theta"]), U["ms_ll"], rtol=1e-13)
     np.testing.assert_array_equal(orc.logpdf_uniform(U["pr_x"], -6.0, 12.0), U["pr_uniform"])
     np.testing.assert_array_equal(orc.logpdf_improper_uniform(U["pr_x"], -6, 6), U["pr_improper"])
     np.testing.assert_array_equal(orc.logpdf_improper_cov(U["pr_cov_x"], 3), U["pr_cov"])
