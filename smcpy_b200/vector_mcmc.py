@@ -179,6 +179,43 @@ class B200VectorMCMC:
         engine.mutate(st, self.spec, num_samples, path, self._rng)
         return st.params_host(), st.ll.cpu().numpy().reshape(-1, 1)
 
-    def metropolis(self, *args, **kwargs):
-        raise NotImplementedError("stand-alone long-chain metropolis() is outside the SMC hot path "
-                                  "(SURVEY.md section 8f-4)")
+    def metropolis(self, inputs, num_samples, cov, adapt_interval=None, adapt_delay=0, progress_bar=False,
+                   **kwargs):
+        """Stand-alone long chain (vector_mcmc.py:64-86): every step is the fused device kernel,
+        the chain (N, d, num_samples + 1) is recorded on the device and copied back once; the
+        windowed covariance adaptation (:153-160,185-197) is host logic on the recorded window."""
+        st = self._load(inputs)
+        path = self._path_from_posterior()
+        engine.eval_incoming(st, self.spec)
+        st.check_flags("metropolis")
+        n, d = st.n, st.d
+        cov = np.asarray(cov, dtype=np.float64).reshape(d, d)
+        st.cov.copy_(engine.dev(cov))
+        engine.cholesky(st)
+        chain = torch.empty((num_samples + 1, d, n), dtype=torch.float64, device=st.cols.device)
+        chain[0].copy_(st.params)
+        it = range(1, num_samples + 1)
+        if progress_bar:
+            from tqdm import tqdm
+            it = tqdm(it)
+        for i in it:
+            engine.mutate(st, self.spec, 1, path, self._rng)        # one step, no covariance rescaling
+            chain[i].copy_(st.params)
+            if self._is_adapt_iteration(adapt_interval, i, adapt_delay):
+                start = self._get_window_start(i, adapt_delay, adapt_interval)
+                win = chain[start:i + 1].permute(1, 2, 0).reshape(d, -1).cpu().numpy()   # (d, N * window)
+                st.cov.copy_(engine.dev(np.cov(win).reshape(d, d)))
+                engine.cholesky(st)
+        return chain.permute(2, 1, 0).contiguous().cpu().numpy()
+
+    @staticmethod
+    def _is_adapt_iteration(adapt_interval, idx, adapt_delay):
+        if adapt_interval is None:
+            return False
+        return idx >= adapt_delay and (idx - adapt_delay) % adapt_interval == 0
+
+    @staticmethod
+    def _get_window_start(idx, adapt_delay, adapt_interval):
+        if idx >= adapt_delay + adapt_interval:
+            return adapt_delay + 1
+        return max(adapt_delay - adapt_interval + 1, 1)

@@ -313,11 +313,27 @@ def unit_vectors():
     print("unit_vectors", len(out), "arrays")
 
 
+def metropolis_fixture():
+    """Stand-alone VectorMCMC.metropolis chain with covariance adaptation (vector_mcmc.py:64-86)."""
+    problem = configs.linear_problem(40, unknown_sigma=True)
+    rng0 = np.random.default_rng(2)
+    theta = np.column_stack([rng0.uniform(1.5, 2.5, 64), rng0.uniform(3, 4, 64), rng0.uniform(0.3, 0.8, 64)])
+    cov = np.diag([0.01, 0.02, 0.005])
+    x = problem["model"][1]
+    m = VectorMCMC(lambda t: orc.model_linear(t, x), problem["data"],
+                   [stats.uniform(-6, 12)] * 2 + [stats.uniform(0, 10)], None)
+    m.rng = np.random.default_rng(8)
+    chain = m.metropolis(theta, 12, cov, adapt_interval=4, adapt_delay=2)
+    np.savez_compressed(os.path.join(HERE, "metropolis_chain.npz"), theta=theta, cov=cov, chain=chain)
+    print("metropolis_chain", chain.shape)
+
+
 if __name__ == "__main__":
     print("reference smcpy", smcpy.__version__, "numpy", np.__version__)
     only = sys.argv[1:]
     if not only:
         unit_vectors()
+        metropolis_fixture()
     for name in configs.CASES:
         if not only or name in only:
             run_case(name)

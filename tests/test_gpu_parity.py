@@ -622,3 +622,20 @@ def test_step_operators_api_parity(sb):
     r = upd2.update(host)
     assert not upd2.resampled
     np.testing.assert_allclose(np.exp(r.log_weights).sum(), 1.0, rtol=1e-12)
+
+
+def test_standalone_metropolis_chain_vs_oracle(sb):
+    """VectorMCMC.metropolis (vector_mcmc.py:64-86) incl. windowed covariance adaptation."""
+    problem = configs.linear_problem(40, unknown_sigma=True)
+    rng0 = np.random.default_rng(2)
+    theta = np.column_stack([rng0.uniform(1.5, 2.5, 64), rng0.uniform(3, 4, 64), rng0.uniform(0.3, 0.8, 64)])
+    cov = np.diag([0.01, 0.02, 0.005])
+    o_chain = orc.metropolis(problem, theta, 12, cov, np.random.default_rng(8), adapt_interval=4, adapt_delay=2)
+    mc, kernel = make_b200(problem, rng=np.random.default_rng(8))
+    mc.evaluate_log_posterior = sb.B200VectorMCMC.evaluate_log_posterior      # plain posterior target
+    g_chain = mc.metropolis(theta, 12, cov, adapt_interval=4, adapt_delay=2)
+    assert g_chain.shape == (64, 3, 13)
+    np.testing.assert_array_equal(g_chain[:, :, 0], theta)
+    np.testing.assert_allclose(g_chain, o_chain, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(g_chain, golden("metropolis_chain")["chain"], rtol=1e-9, atol=1e-11)   # reference run
+    assert np.any(g_chain[:, :, -1] != theta)

@@ -246,3 +246,11 @@ def test_fixture_full_runs(name):
     np.testing.assert_allclose(steps[-1].log_likes, g["log_likes_last"], rtol=1e-10)
     np.testing.assert_allclose([s.mutation_ratio for s in steps], g["mutation_ratio"])
     np.testing.assert_array_equal(rng.uniform(0, 1, 4), g["rng_check"])     # tape exactly exhausted
+
+
+def test_fixture_standalone_metropolis():
+    g = golden("metropolis_chain")
+    problem = configs.linear_problem(40, unknown_sigma=True)
+    chain = orc.metropolis(problem, g["theta"], 12, g["cov"], np.random.default_rng(8), adapt_interval=4,
+                           adapt_delay=2)
+    np.testing.assert_allclose(chain, g["chain"], rtol=1e-13, atol=1e-14)
