@@ -207,6 +207,14 @@ int smcb_ess_bisect_max_iters(void);
 /* u for `count` global slots starting at `first` out of n_global (resampler_rngs.py:4-9) */
 int smcb_resample_uniforms(int32_t kind, int64_t n_global, int64_t first, int64_t count,
                            uint64_t seed, uint64_t stream_id, double* u_out, void* stream);
+/* multinomial uniforms for sharded particles, locality preserving: the N iid uniforms are
+ * generated as order-statistic blocks -- interval q = [q/world, (q+1)/world) holds
+ * prefix[q+1]-prefix[q] of them (the caller draws those counts ~ Multinomial(N; 1/world), the
+ * same on every rank); global sorted position g in interval q, j = g - prefix[q], gets
+ * u = (q + U(q, j)) / world.  A rank's own positions [first, first+count) therefore fall mostly
+ * into its own CDF segment and few rows cross NVLink.  prefix: device int64[world+1]. */
+int smcb_resample_uniforms_sharded(int32_t world, const int64_t* prefix, int64_t first, int64_t count,
+                                   uint64_t seed, uint64_t stream_id, double* u_out, void* stream);
 /* inclusive prefix sum of normalised weights -> CDF (np.cumsum, updater.py:152) */
 int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mode, void* ws, void* stream);
 /* idx_k = #{j : cdf_j <= u_k}  (np.digitize / searchsorted side='right', updater.py:152),
@@ -220,6 +228,15 @@ int smcb_searchsorted_offset(const double* cdf, int64_t n_cdf, const double* off
 /* dst[c][k] = src[c][idx[k]] for n_cols SoA columns (updater.py:140-143) */
 int smcb_gather(const double* src, int64_t src_stride, double* dst, int64_t dst_stride,
                 const int64_t* idx, int64_t n_out, int32_t n_cols, void* stream);
+/* fused gather + all-to-all over NVLink peer memory (multi-GPU resampling): request j of this
+ * rank's n_req incoming requests came from rank q = the block with block_off[q] <= j <
+ * block_off[q+1]; the selected row idx[j] is written column by column straight into THAT rank's
+ * SoA buffer dst[q] (a peer-mapped pointer) at row slot_off[q] + (j - block_off[q]).
+ * block_off (world+1) and slot_off (world) are device int64 arrays, dst is a HOST array of
+ * `world` device pointers.  The caller synchronises the ranks afterwards. */
+int smcb_gather_p2p(const double* src, int64_t src_stride, const int64_t* idx, int64_t n_req, int32_t n_cols,
+                    int32_t world, const int64_t* block_off, const int64_t* slot_off, double* const* dst,
+                    int64_t dst_stride, void* stream);
 /* number of distinct ancestors (updater.py:154-165); flags = n_src bytes of scratch */
 int smcb_count_unique(const int64_t* idx, int64_t n_idx, int64_t n_src, int64_t* count_out,
                       void* ws, void* stream);

@@ -92,10 +92,12 @@ SIGNATURES = {
     "smcb_ess_bisect_update": [_P, _I32, _D, _D, _I64, _P, _P],
     "smcb_ess_bisect_max_iters": [],
     "smcb_resample_uniforms": [_I32, _I64, _I64, _I64, _U64, _U64, _P, _P],
+    "smcb_resample_uniforms_sharded": [_I32, _P, _I64, _I64, _U64, _U64, _P, _P],
     "smcb_cdf_scan": [_P, _P, _I64, _I32, _P, _P],
     "smcb_searchsorted": [_P, _I64, _P, _I64, _P, _P],
     "smcb_searchsorted_offset": [_P, _I64, _P, _P, _I64, _P, _P],
     "smcb_gather": [_P, _I64, _P, _I64, _P, _I64, _I32, _P],
+    "smcb_gather_p2p": [_P, _I64, _P, _I64, _I32, _I32, _P, _P, C.POINTER(C.c_void_p), _I64, _P],
     "smcb_count_unique": [_P, _I64, _I64, _P, _P, _P],
     "smcb_weighted_cov": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P, _P],
     "smcb_weighted_sums1": [_P, _I64, _P, _I64, _I32, _P, _P, _P],

@@ -40,6 +40,24 @@ __global__ void resample_uniforms_kernel(int kind, int64_t n_global, int64_t fir
     }
 }
 
+__global__ void resample_uniforms_sharded_kernel(int world, const int64_t* __restrict__ prefix, int64_t first,
+                                                 int64_t count, uint64_t seed, uint32_t stream_id, double* u) {
+    __shared__ int64_t s_pre[SMCB_MAX_RANKS + 1];
+    if (threadIdx.x <= world) s_pre[threadIdx.x] = prefix[threadIdx.x];
+    __syncthreads();
+    const Philox rng(seed);
+    const double inv_g = 1.0 / (double)world;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const int64_t g = first + i;
+        int q = 0;
+        while (q + 1 < world && g >= s_pre[q + 1]) ++q;
+        const uint64_t j = (uint64_t)(g - s_pre[q]);
+        const uint4 r = rng(j, 0x5AD0u + (uint32_t)q, stream_id);
+        u[i] = ((double)q + u01_53(r.x, r.y)) * inv_g;
+    }
+}
+
 // ---- sequential scan: bit-equal to np.cumsum ----------------------------------------------------
 constexpr int kSeqChunk = 2048;
 __global__ void __launch_bounds__(256) scan_sequential_kernel(const double* __restrict__ w,
@@ -248,6 +266,41 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
     }
 }
 
+// ---- fused gather + all-to-all over peer memory ---------------------------------------------------------
+struct PeerDst {
+    double* p[SMCB_MAX_RANKS];
+};
+__global__ void __launch_bounds__(256) gather_p2p_kernel(const double* __restrict__ src, int64_t src_stride,
+                                                         const int64_t* __restrict__ idx, int64_t n_req, int n_cols,
+                                                         int world, const int64_t* __restrict__ block_off,
+                                                         const int64_t* __restrict__ slot_off, PeerDst dst,
+                                                         int64_t dst_stride) {
+    __shared__ int64_t s_boff[SMCB_MAX_RANKS + 1], s_soff[SMCB_MAX_RANKS];
+    if (threadIdx.x <= world) s_boff[threadIdx.x] = block_off[threadIdx.x];
+    if (threadIdx.x < world) s_soff[threadIdx.x] = slot_off[threadIdx.x];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_req; j += stride) {
+        int q = 0;
+        while (q + 1 < world && j >= s_boff[q + 1]) ++q;            // requester rank of request j
+        const int64_t row = s_soff[q] + (j - s_boff[q]);
+        const int64_t a = idx[j];
+        double* out = dst.p[q] + row;
+        int c = 0;
+        for (; c + 4 <= n_cols; c += 4) {
+            const double v0 = __ldg(src + (int64_t)(c + 0) * src_stride + a);
+            const double v1 = __ldg(src + (int64_t)(c + 1) * src_stride + a);
+            const double v2 = __ldg(src + (int64_t)(c + 2) * src_stride + a);
+            const double v3 = __ldg(src + (int64_t)(c + 3) * src_stride + a);
+            out[(int64_t)(c + 0) * dst_stride] = v0;
+            out[(int64_t)(c + 1) * dst_stride] = v1;
+            out[(int64_t)(c + 2) * dst_stride] = v2;
+            out[(int64_t)(c + 3) * dst_stride] = v3;
+        }
+        for (; c < n_cols; ++c) out[(int64_t)c * dst_stride] = __ldg(src + (int64_t)c * src_stride + a);
+    }
+}
+
 // ---- distinct ancestors -------------------------------------------------------------------------------
 __global__ void mark_kernel(const int64_t* __restrict__ idx, int64_t n_idx, uint8_t* flags) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -292,6 +345,14 @@ extern "C" int smcb_resample_uniforms(int32_t kind, int64_t n_global, int64_t fi
     return check_launch("resample_uniforms_kernel");
 }
 
+extern "C" int smcb_resample_uniforms_sharded(int32_t world, const int64_t* prefix, int64_t first, int64_t count,
+                                              uint64_t seed, uint64_t stream_id, double* u_out, void* stream) {
+    SMCB_REQUIRE(world >= 1 && world <= SMCB_MAX_RANKS && prefix && count > 0 && u_out, "bad argument");
+    resample_uniforms_sharded_kernel<<<grid_for(count, 256, 4, 8), 256, 0, as_stream(stream)>>>(
+        world, prefix, first, count, seed, (uint32_t)stream_id, u_out);
+    return check_launch("resample_uniforms_sharded_kernel");
+}
+
 extern "C" int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mode, void* ws, void* stream) {
     SMCB_REQUIRE(w && cdf && n > 0 && ws, "bad argument");
     if (mode == SMCB_SCAN_SEQUENTIAL) {
@@ -329,6 +390,20 @@ extern "C" int smcb_gather(const double* src, int64_t src_stride, double* dst, i
     gather_kernel<<<grid_for(n_out, 256, 1, 8), 256, 0, as_stream(stream)>>>(src, src_stride, dst, dst_stride,
                                                                               idx, n_out, n_cols);
     return check_launch("gather_kernel");
+}
+
+extern "C" int smcb_gather_p2p(const double* src, int64_t src_stride, const int64_t* idx, int64_t n_req,
+                               int32_t n_cols, int32_t world, const int64_t* block_off, const int64_t* slot_off,
+                               double* const* dst, int64_t dst_stride, void* stream) {
+    SMCB_REQUIRE(src && idx && block_off && slot_off && dst && n_req > 0 && n_cols > 0, "bad argument");
+    SMCB_REQUIRE(world >= 1 && world <= SMCB_MAX_RANKS, "world out of range");
+    PeerDst d;
+    for (int r = 0; r < SMCB_MAX_RANKS; ++r) d.p[r] = (r < world) ? dst[r] : nullptr;
+    for (int r = 0; r < world; ++r) SMCB_REQUIRE(d.p[r] != nullptr, "peer destination pointer is NULL");
+    gather_p2p_kernel<<<grid_for(n_req, 256, 1, 8), 256, 0, as_stream(stream)>>>(src, src_stride, idx, n_req, n_cols,
+                                                                                  world, block_off, slot_off, d,
+                                                                                  dst_stride);
+    return check_launch("gather_p2p_kernel");
 }
 
 extern "C" int smcb_count_unique(const int64_t* idx, int64_t n_idx, int64_t n_src, int64_t* count_out,

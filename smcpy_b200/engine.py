@@ -66,8 +66,8 @@ class AcceptExchange:
         self.gen = 0
         x = _lib.Xchg()
         x.world, x.rank = world, rank
-        for r in range(world):
-            x.peer_slots[r] = int(self.handle.buffer_ptrs[r])
+        for r, p in enumerate(peer_pointers(self.slots, self.handle)):
+            x.peer_slots[r] = p
         x.global_counts = self.global_counts.data_ptr()
         x.ticket = self.ticket.data_ptr()
         self.x = x
@@ -97,6 +97,49 @@ class AcceptExchange:
             raise RuntimeError("accept-count exchange generation overflow")
         self.x.gen = self.gen
         return self.x
+
+
+def peer_pointers(t, handle):
+    """Device pointers of tensor `t` in every rank's address space: buffer_ptrs are the bases of
+    the symmetric allocation, the tensor may sit at an offset inside it."""
+    rank, _ = dist_info()
+    base = [int(p) for p in handle.buffer_ptrs]
+    off = int(t.data_ptr()) - base[rank]
+    if off < 0:
+        raise RuntimeError("symmetric tensor lies outside its allocation")
+    return [b + off for b in base]
+
+
+class SymmetricPool:
+    """Peer-mapped (symmetric-memory) particle buffers for the multi-GPU resampler, cached per
+    shape so that repeated sample() calls do not rendezvous again.  get() returns
+    [(tensor, [peer pointers])] x 2 (the ping-pong pair) or None when symmetric memory is
+    unavailable (then the NCCL all-to-all path is used)."""
+    _cache = {}
+    _failed = False
+
+    @classmethod
+    def get(cls, rows, n_max):
+        import os
+        if cls._failed or os.environ.get("SMCB_NO_P2P"):
+            return None
+        key = (int(rows), int(n_max))
+        if key not in cls._cache:
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm_mem
+                dv = Runtime.get().device
+                pair = []
+                for _ in range(2):
+                    t = symm_mem.empty((rows, n_max), dtype=torch.float64, device=dv)
+                    h = symm_mem.rendezvous(t, dist.group.WORLD)
+                    pair.append((t, peer_pointers(t, h), h))
+                cls._cache[key] = pair
+            except Exception as e:            # pragma: no cover - depends on the box
+                warnings.warn("symmetric particle buffers unavailable (%s); using NCCL all-to-all" % e)
+                cls._failed = True
+                return None
+        return cls._cache[key]
 
 
 def dist_info():
@@ -279,15 +322,28 @@ class ProblemSpec:
 class DeviceState:
     """Working set of one particle shard."""
 
-    def __init__(self, n_local, n_global, d, id_offset=0, with_lq=False):
+    def __init__(self, n_local, n_global, d, id_offset=0, with_lq=False, symmetric=False):
         rt = Runtime.get()
         dv = rt.device
         self.n, self.n_global, self.d, self.id_offset = int(n_local), int(n_global), int(d), int(id_offset)
         f64 = torch.float64
         self.with_lq = bool(with_lq)            # third resident column: proposal log-pdf
         rows = d + 3 if with_lq else d + 2
-        self.cols = torch.empty((rows, self.n), dtype=f64, device=dv)
-        self.cols_alt = torch.empty((rows, self.n), dtype=f64, device=dv)
+        self.peer_cols = self.peer_cols_alt = None      # peer pointers of cols / cols_alt (multi-GPU)
+        self.col_stride = self.n
+        pool = None
+        if symmetric:
+            _, world = dist_info()
+            n_max = -(-self.n_global // world)
+            pool = SymmetricPool.get(rows, n_max)
+        if pool is not None:
+            (self.cols, self.peer_cols, _), (self.cols_alt, self.peer_cols_alt, _) = pool
+            self.col_stride = int(self.cols.shape[1])
+            if self.col_stride != self.n:
+                raise NotImplementedError("multi-GPU runs need the particle count to be a multiple of the GPU count")
+        else:
+            self.cols = torch.empty((rows, self.n), dtype=f64, device=dv)
+            self.cols_alt = torch.empty((rows, self.n), dtype=f64, device=dv)
         self.log_w = torch.empty(self.n, dtype=f64, device=dv)
         self.w = torch.empty(self.n, dtype=f64, device=dv)
         self.log_w_alt = torch.empty(self.n, dtype=f64, device=dv)
@@ -329,6 +385,10 @@ class DeviceState:
     @lq.setter
     def lq(self, value):
         self._lq_host = value
+
+    def swap_cols(self):
+        self.cols, self.cols_alt = self.cols_alt, self.cols
+        self.peer_cols, self.peer_cols_alt = self.peer_cols_alt, self.peer_cols
 
     def set_params_host(self, params):
         """(n, d) host array -> SoA columns."""
@@ -488,7 +548,7 @@ def count_unique(st, idx):
 def gather_particles(st, idx):
     call("smcb_gather", ptr(st.cols), st.n, ptr(st.cols_alt), st.n, ptr(idx), st.n, int(st.cols.shape[0]),
          stream_ptr())
-    st.cols, st.cols_alt = st.cols_alt, st.cols
+    st.swap_cols()
     st.set_uniform_weights()
 
 
@@ -515,7 +575,8 @@ def _resample_local(st, kernel, resample_rng, warn_threshold, n, host_rng, kind)
         idx = resample_indices(st, dev(u1), _lib.SCAN_SEQUENTIAL)
         idx_sel = idx.clone()
         u2 = np.asarray(resample_rng(kernel, n), dtype=np.float64)
-        call("smcb_searchsorted", ptr(st.cdf), n, ptr(dev(u2)), n, ptr(st.idx), stream_ptr())
+        u2_dev = dev(u2)
+        call("smcb_searchsorted", ptr(st.cdf), n, ptr(u2_dev), n, ptr(st.idx), stream_ptr())
         n_unique = count_unique(st, st.idx)
         idx = idx_sel
     else:

@@ -31,7 +31,8 @@ class Initializer:
         spec = kernel.spec
         rank, world = engine.dist_info()
         lo, hi = engine.shard_bounds(num_particles, rank, world)
-        st = engine.DeviceState(hi - lo, num_particles, spec.d, id_offset=lo, with_lq=spec.has_device_proposal)
+        st = engine.DeviceState(hi - lo, num_particles, spec.d, id_offset=lo, with_lq=spec.has_device_proposal,
+                                symmetric=(world > 1))
         host_rng = isinstance(kernel.rng, np.random.Generator)
         if kernel.has_proposal() or host_rng:
             if kernel.has_proposal():

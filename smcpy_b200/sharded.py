@@ -16,6 +16,7 @@ multinomial uniforms are sorted first (particles are exchangeable, so slot order
 Collectives are NCCL over NVLink; every count that decides a split is exchanged explicitly.
 """
 
+import os
 import warnings
 
 import numpy as np
@@ -61,36 +62,75 @@ def resample_sharded(st, kernel, resample_rng, warn_threshold):
     totals = engine._all_gather_rows(st.cdf[n - 1:n]).reshape(-1)
     off = segment_offsets(totals)
     # 3: uniforms of my output slots, routed to the owning rank
-    call("smcb_resample_uniforms", int(kind), st.n_global, st.id_offset, n, rng.seed, rng.next_stream(),
-         ptr(st.u), s)
-    u = st.u
+    stream_id = rng.next_stream()
     if kind == _lib.RESAMPLE_STANDARD:
-        u = torch.sort(u).values
+        # multinomial: shared interval counts ~ Multinomial(N; 1/G) (same generator on every rank),
+        # then this rank's block of the order statistics; sorted so that routing is a contiguous split
+        host = np.random.default_rng([rng.seed & 0xFFFFFFFF, rng.seed >> 32, stream_id])
+        prefix = np.concatenate([[0], np.cumsum(host.multinomial(st.n_global, [1.0 / world] * world))])
+        pre_dev = engine.dev(prefix, torch.int64)
+        call("smcb_resample_uniforms_sharded", world, ptr(pre_dev), st.id_offset, n, rng.seed, stream_id,
+             ptr(st.u), s)
+        u = torch.sort(st.u).values
+    else:
+        call("smcb_resample_uniforms", int(kind), st.n_global, st.id_offset, n, rng.seed, stream_id, ptr(st.u), s)
+        u = st.u
     bounds = torch.cat([off[1:world], torch.full((1,), float("inf"), dtype=torch.float64, device=dv)])
     dest = torch.empty(n, dtype=torch.int64, device=dv)
     call("smcb_searchsorted", ptr(bounds), world, ptr(u), n, ptr(dest), s)
     send_counts = route_counts(dest, world)
-    recv_counts = exchange_counts(send_counts)
-    sc, rc = send_counts.tolist(), recv_counts.tolist()          # host sync: split sizes
+    counts = torch.empty((world, world), dtype=torch.int64, device=dv)      # counts[q][r]: requests q -> r
+    dist.all_gather_into_tensor(counts, send_counts.contiguous())
+    cm = counts.cpu().numpy()                                               # host sync: split sizes
+    sc, rc = cm[rank, :].tolist(), cm[:, rank].tolist()
     n_req = int(sum(rc))
     u_in = torch.empty(max(n_req, 1), dtype=torch.float64, device=dv)
     dist.all_to_all_single(u_in[:n_req], u.contiguous(), output_split_sizes=rc, input_split_sizes=sc)
-    # 4: owner-side search + gather (rows in AoS for the exchange)
-    rows_out = torch.empty((max(n_req, 1), ncol), dtype=torch.float64, device=dv)
     n_unique = torch.zeros(1, dtype=torch.int64, device=dv)
+    idx = None
     if n_req > 0:
         idx = torch.empty(n_req, dtype=torch.int64, device=dv)
         call("smcb_searchsorted_offset", ptr(st.cdf), n, ptr(off[rank:rank + 1]), ptr(u_in), n_req, ptr(idx), s)
-        soa = torch.empty((ncol, n_req), dtype=torch.float64, device=dv)
-        call("smcb_gather", ptr(st.cols), n, ptr(soa), n_req, ptr(idx), n_req, ncol, s)
-        call("smcb_soa_to_aos", ptr(soa), ptr(rows_out), n_req, ncol, n_req, s)
         call("smcb_count_unique", ptr(idx), n_req, n, ptr(st.counts), ptr(st.ws), s)
         n_unique = st.counts[0:1].clone()
-    # 5: rows back to the requesters
-    rows_in = torch.empty((n, ncol), dtype=torch.float64, device=dv)
-    dist.all_to_all_single(rows_in, rows_out[:n_req], output_split_sizes=sc, input_split_sizes=rc)
-    call("smcb_aos_to_soa", ptr(rows_in), ptr(st.cols_alt), n, ncol, n, s)
-    st.cols, st.cols_alt = st.cols_alt, st.cols
+    if st.peer_cols_alt is not None:
+        # 4-5 fused: the owner writes every requested row straight into the requester's SoA
+        # buffer over NVLink peer memory (no staging transposes, no NCCL payload exchange)
+        block_off = np.concatenate([[0], np.cumsum(cm[:, rank])])               # my incoming blocks by requester
+        slot_off = np.array([cm[q, :rank].sum() for q in range(world)])         # where my block sits at requester q
+        if n_req > 0:
+            import ctypes as C
+            dst = (C.c_void_p * world)(*st.peer_cols_alt)
+            # keep both offset tensors alive across the launch: temporaries would be returned to
+            # the caching allocator at once and alias each other
+            bo_dev = engine.dev(block_off, torch.int64)
+            so_dev = engine.dev(slot_off, torch.int64)
+            call("smcb_gather_p2p", ptr(st.cols), st.col_stride, ptr(idx), n_req, ncol, world,
+                 ptr(bo_dev), ptr(so_dev), dst, st.col_stride, s)
+        if os.environ.get("SMCB_P2P_VERIFY"):
+            torch.cuda.synchronize(); dist.barrier()
+            rows_out = torch.empty((max(n_req, 1), ncol), dtype=torch.float64, device=dv)
+            soa = torch.empty((ncol, max(n_req, 1)), dtype=torch.float64, device=dv)
+            call("smcb_gather", ptr(st.cols), n, ptr(soa), n_req, ptr(idx), n_req, ncol, s)
+            call("smcb_soa_to_aos", ptr(soa), ptr(rows_out), n_req, ncol, n_req, s)
+            rows_in = torch.empty((n, ncol), dtype=torch.float64, device=dv)
+            dist.all_to_all_single(rows_in, rows_out[:n_req], output_split_sizes=sc, input_split_sizes=rc)
+            ref = rows_in.t().contiguous()
+            bad = (ref != st.cols_alt).sum().item()
+            print("[verify] rank", rank, "n_req", n_req, "sc", sc, "rc", rc, "block_off", block_off.tolist(),
+                  "slot_off", slot_off.tolist(), "mismatching entries", bad, "of", ref.numel(), flush=True)
+        st.swap_cols()      # the all-reduce of n_unique below orders every rank's peer writes before any use
+    else:
+        # 4: owner-side gather (rows in AoS for the exchange); 5: rows back to the requesters
+        rows_out = torch.empty((max(n_req, 1), ncol), dtype=torch.float64, device=dv)
+        if n_req > 0:
+            soa = torch.empty((ncol, n_req), dtype=torch.float64, device=dv)
+            call("smcb_gather", ptr(st.cols), n, ptr(soa), n_req, ptr(idx), n_req, ncol, s)
+            call("smcb_soa_to_aos", ptr(soa), ptr(rows_out), n_req, ncol, n_req, s)
+        rows_in = torch.empty((n, ncol), dtype=torch.float64, device=dv)
+        dist.all_to_all_single(rows_in, rows_out[:n_req], output_split_sizes=sc, input_split_sizes=rc)
+        call("smcb_aos_to_soa", ptr(rows_in), ptr(st.cols_alt), n, ncol, n, s)
+        st.swap_cols()
     st.set_uniform_weights()
     engine._all_reduce_sum(n_unique)
     if int(n_unique.item()) <= max(1, warn_threshold * st.n_global):

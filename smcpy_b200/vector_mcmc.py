@@ -46,7 +46,8 @@ def device_log_priors(priors, x, problem_c=None):
     n = x.shape[0]
     rt = engine.Runtime.get()
     soa = torch.empty((d, n), dtype=torch.float64, device=rt.device)
-    call("smcb_aos_to_soa", ptr(engine.dev(x)), ptr(soa), n, d, n, stream_ptr())
+    x_dev = engine.dev(x)
+    call("smcb_aos_to_soa", ptr(x_dev), ptr(soa), n, d, n, stream_ptr())
     lp = torch.empty(n, dtype=torch.float64, device=rt.device)
     cols = torch.empty((int(problem_c.n_priors), n), dtype=torch.float64, device=rt.device)
     call("smcb_log_priors", C.byref(problem_c), ptr(soa), n, n, ptr(lp), ptr(cols), stream_ptr())
