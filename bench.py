@@ -145,6 +145,38 @@ def oracle_run(n, cores, seed=1):
     return dt, n * K_MCMC * (len(PHI) - 1), float(mll[-1])
 
 
+def smcpy_run(n, seed=1):
+    """The unmodified reference (pip-installed under baseline/_ref, when present) on the same
+    bounded C2 sample: smcpy.VectorMCMC + VectorMCMCKernel + FixedPhiSampler, one process."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "smcpy")):
+        return None
+    import types
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        import smcpy
+        from scipy import stats
+        from smcpy.resampler_rngs import standard
+        problem = c2_problem()
+        x = problem["model"][1]
+        model = lambda th: th[:, 0:1] * x[None, :] + th[:, 1:2]
+        mcmc = smcpy.VectorMCMC(model, problem["data"], [stats.uniform(-6.0, 12.0)] * 2, 0.5)
+        kernel = smcpy.VectorMCMCKernel(mcmc, param_order=("a", "b"), rng=np.random.default_rng(seed))
+        smc = smcpy.FixedPhiSampler(kernel, show_progress_bar=False)
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            steps, mll = smc.sample(n, K_MCMC, PHI, ESS_THRESHOLD, resample_rng=standard)
+        dt = time.perf_counter() - t0
+        return {"value": n * K_MCMC * (len(PHI) - 1) / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": "unmodified smcpy %s from baseline/_ref, C2 at N=%d, one process, %.1f s"
+                          % (getattr(smcpy, "__version__", "?"), n, dt), "mll_last": float(mll[-1])}
+    except Exception as e:                                   # pragma: no cover
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -171,6 +203,9 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": use, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    pkg = smcpy_run(2048)
+    if pkg is not None:
+        out["smcpy_package"] = pkg          # the real reference on one core, for context
     print(json.dumps(out))
 
 

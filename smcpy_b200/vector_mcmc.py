@@ -170,8 +170,8 @@ class B200VectorMCMC:
 
     def smc_metropolis(self, inputs, num_samples, cov):
         """vector_mcmc.py:46-62 on the device; returns (inputs (N,d), log_like (N,1))."""
+        path = self._path_from_posterior()             # binds a path proposal before the state is laid out
         st = self._load(inputs)
-        path = self._path_from_posterior()
         engine.eval_incoming(st, self.spec)
         st.check_flags("smc_metropolis")
         cov = np.asarray(cov, dtype=np.float64).reshape(self.spec.d, self.spec.d)
@@ -185,8 +185,8 @@ class B200VectorMCMC:
         """Stand-alone long chain (vector_mcmc.py:64-86): every step is the fused device kernel,
         the chain (N, d, num_samples + 1) is recorded on the device and copied back once; the
         windowed covariance adaptation (:153-160,185-197) is host logic on the recorded window."""
-        st = self._load(inputs)
         path = self._path_from_posterior()
+        st = self._load(inputs)
         engine.eval_incoming(st, self.spec)
         st.check_flags("metropolis")
         n, d = st.n, st.d
