@@ -211,6 +211,36 @@ struct Philox {
         return make_uint4(c0, c1, c2, c3);
     }
 };
+// Same generator with the 10 round keys precomputed on the host (they are the same for every
+// thread): the key schedule becomes constant-bank operands instead of ~20 adds per call.
+struct PhiloxKeys {
+    uint32_t k[20];
+};
+inline PhiloxKeys make_philox_keys(uint64_t seed) {
+    PhiloxKeys r;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; ++i) {
+        r.k[2 * i] = a;
+        r.k[2 * i + 1] = b;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    return r;
+}
+__device__ __forceinline__ uint4 philox_k(const PhiloxKeys& rk, uint64_t id, uint32_t call, uint32_t stream) {
+    uint32_t c0 = (uint32_t)id, c1 = (uint32_t)(id >> 32), c2 = call, c3 = stream;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ rk.k[2 * r], n2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
 // 53-bit uniform in [0,1) from two 32-bit words (same construction as numpy's next_double)
 __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
     const uint64_t x = ((uint64_t)hi << 32) | lo;
@@ -219,6 +249,16 @@ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
 // two standard normals from two 32-bit words: Box-Muller in fp32 with the hardware
 // approximations (lg2 / sin / cos MUFU).  Proposals only need a symmetric, well-distributed z
 // (the Metropolis ratio does not involve the proposal density) -- see DESIGN.md "RNG".
+__device__ __forceinline__ void normal_pair_f(uint32_t w0, uint32_t w1, float& z0, float& z1) {
+    const float u1 = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
+    const float th = ((float)(int32_t)w1) * (3.14159265358979f / 2147483648.0f);   // [-pi, pi)
+    const float x = -1.38629436111989f * __log2f(u1);       // -2 ln(u1) > 0
+    const float r = x * __frsqrt_rn(x);
+    float s, c;
+    __sincosf(th, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
 __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, double& z0, double& z1) {
     const float u1 = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
     const float th = ((float)(int32_t)w1) * (3.14159265358979f / 2147483648.0f);   // [-pi, pi)

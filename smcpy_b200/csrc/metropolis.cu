@@ -59,6 +59,7 @@ struct MhArgs {
     double* new_params;   // propose only
     double* new_lp;       // propose only
     smcb_xchg_t x;        // world <= 1: no cross-GPU exchange
+    PhiloxKeys rk;        // Philox round keys of rng.seed
 };
 
 // covariance scale after the first `step` Metropolis steps (vector_mcmc.py:55-60):
@@ -110,6 +111,22 @@ __device__ __forceinline__ double cov_scale_sqrt_xchg(const smcb_xchg_t& x, int 
 }
 
 // ---- priors -----------------------------------------------------------------------------------
+__device__ __noinline__ double gen_uniform53(const PhiloxKeys* rk, uint64_t pid, uint32_t call, uint32_t stream) {
+    const uint4 r = philox_k(*rk, pid, call, stream);
+    return u01_53(r.x, r.y);
+}
+
+// Four standard normals (fp32) from one Philox call.  Deliberately NOT inlined: the wide
+// kernels call it DMAX/4 times per particle and eight inlined copies push the tile body past the
+// 32 KB instruction cache (ncu: 21 % of stall samples were `no_inst`, profiles/r01_mh_kernels.md).
+__device__ __noinline__ float4 gen_normals4(const PhiloxKeys* rk, uint64_t pid, uint32_t call, uint32_t stream) {
+    const uint4 r = philox_k(*rk, pid, call, stream);
+    float4 z;
+    normal_pair_f(r.x, r.y, z.x, z.y);
+    normal_pair_f(r.z, r.w, z.z, z.w);
+    return z;
+}
+
 template <int KIND, int DMAX, bool EXACT>
 __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th)[DMAX], double* lp_cols_row,
                                               int64_t col_stride) {
@@ -219,6 +236,11 @@ __device__ __forceinline__ void stage_data(const MhArgs& a, double* sdata, int b
         for (int j = threadIdx.x; j < F; j += blockDim.x) sdata[S * F + j] = a.prob.xgrid[j];
     } else {
         for (int j = threadIdx.x; j < cnt; j += blockDim.x) sdata[j] = a.prob.data[base + j];
+        if (KIND == K_IDENTITY_NORMAL && threadIdx.x == 0) {       // constants of normal_ll, slots past DMAX <= 32
+            const double var = a.prob.sigma * a.prob.sigma;
+            sdata[SMCB_MAX_PARAMS] = -log(2 * 3.141592653589793 * var) * ((double)a.prob.n_data / 2.0);
+            sdata[SMCB_MAX_PARAMS + 1] = var;
+        }
     }
 }
 
@@ -311,6 +333,8 @@ __device__ __forceinline__ double ll_spring_normal(const MhArgs& a, const double
     return normal_ll(ssq, sigma, m);
 }
 
+// sy[m] = term1 = -log(2 pi var) * (M/2), sy[m+1] = -1/(2 var): computed once per block by
+// stage_data (the identity model always has a fixed sigma), same arithmetic as normal_ll
 template <int DMAX, bool EXACT>
 __device__ __forceinline__ double ll_identity_normal(const MhArgs& a, const double (&th)[DMAX], bool run,
                                                      const double* sy) {
@@ -323,7 +347,7 @@ __device__ __forceinline__ double ll_identity_normal(const MhArgs& a, const doub
             if (j + 1 < DMAX && (EXACT || j + 1 < m)) { const double dd = th[j + 1] - sy[j + 1]; s1 = fma(dd, dd, s1); }
         }
     }
-    return normal_ll(s0 + s1, a.prob.sigma, m);
+    return sy[SMCB_MAX_PARAMS] + (-1 / 2.0 * (s0 + s1)) / sy[SMCB_MAX_PARAMS + 1];
 }
 
 // MVNormal (log_likelihoods.py:150-192) with one Cholesky per particle:
@@ -381,8 +405,13 @@ __device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&
 
 // register budget per thread -> minimum resident blocks per SM (keeps ptxas from trading
 // occupancy for unrolling: profiles/r01_mh_kernels.md)
-__host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt) {
-    const int regs = dmax >= 32 ? 128 : (dmax >= 16 ? 96 : (ppt >= 4 ? 84 : 64));
+__host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt, bool tma = false) {
+#ifdef SMCB_TMA_REGS
+    const int tma_regs = SMCB_TMA_REGS;
+#else
+    const int tma_regs = 128;
+#endif
+    const int regs = dmax >= 32 ? (tma ? tma_regs : 128) : (dmax >= 16 ? 96 : (ppt >= 4 ? 84 : 64));
     return 65536 / (tpb * regs) > 0 ? 65536 / (tpb * regs) : 1;
 }
 
@@ -451,7 +480,7 @@ __device__ __forceinline__ double ll_multisource(const MhArgs& a, const double (
 //       MULTI: MultiSourceNormal likelihood (segment table in the problem).
 template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
           bool DYN = false, bool MULTI = false>
-__global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT))
+__global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT, TMA))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double sh_scale;
@@ -466,7 +495,9 @@ mh_kernel(const __grid_constant__ MhArgs a) {
     if (MODE == 1 || MODE == 2) {
         for (int e = threadIdx.x; e < DMAX * DMAX; e += TPB) {
             const int j = e / DMAX, r = e - j * DMAX;
-            sLt[e] = (r < d && j <= r) ? a.chol[r * d + j] : 0.0;
+            const double v = (r < d && j <= r) ? a.chol[r * d + j] : 0.0;
+            if (TMA) reinterpret_cast<float*>(sLt)[e] = (float)v;      // TMA variant: fp32 increment path
+            else sLt[e] = v;
         }
         if (threadIdx.x == 0)
             sh_scale = (a.x.world > 1) ? cov_scale_sqrt_xchg(a.x, a.step, a.n_global)
@@ -489,6 +520,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         const uint32_t bytes = cnt * 8u;
         fence_proxy_async();                       // generic-proxy reads of the stage are done
         mbar_expect_tx(&mbar, bytes * (uint32_t)(d + 2));
+#pragma unroll 1
         for (int c = 0; c < d; ++c) tma_load_1d(stage + c * TPB, a.params + (int64_t)c * a.stride + base, bytes, &mbar);
         tma_load_1d(stage + d * TPB, a.ll + base, bytes, &mbar);
         tma_load_1d(stage + (d + 1) * TPB, a.lp + base, bytes, &mbar);
@@ -514,13 +546,40 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         double lq_old[PPT], lq_new[PPT];
         bool prior_ok[PPT];
         if (TMA) {
+            // native RNG only.  The proposal increment sqrt(s) L z is accumulated in fp32 (z has
+            // fp32 resolution; symmetry z -> -z is exact, which is all the Metropolis ratio needs)
+            // BEFORE the tile is read from the TMA stage, so the stage wait hides behind it.
             const int64_t i = tile * per_tile + threadIdx.x;
             valid[0] = i < a.n;
             idx[0] = valid[0] ? i : 0;
+            const float* sLf = reinterpret_cast<const float*>(sLt);     // fp32 copy of L^T, padded
+            const float scf = (float)sc;
+            float delta[DMAX];
+#pragma unroll
+            for (int c = 0; c < DMAX; ++c) delta[c] = 0.0f;
+            const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[0]);
+#pragma unroll
+            for (int c = 0; c < DMAX; c += 4) {
+                const float4 zz = gen_normals4(&a.rk, pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
+                const float z4[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = c + q;
+                    const float zs = scf * z4[q];
+#pragma unroll
+                    for (int r4 = c; r4 < DMAX; r4 += 4) {                 // rows above the diagonal hold 0
+                        const float4 l4 = *reinterpret_cast<const float4*>(&sLf[j * DMAX + r4]);
+                        delta[r4 + 0] = fmaf(l4.x, zs, delta[r4 + 0]);
+                        delta[r4 + 1] = fmaf(l4.y, zs, delta[r4 + 1]);
+                        delta[r4 + 2] = fmaf(l4.z, zs, delta[r4 + 2]);
+                        delta[r4 + 3] = fmaf(l4.w, zs, delta[r4 + 3]);
+                    }
+                }
+            }
             mbar_wait(&mbar, tma_phase);
             tma_phase ^= 1u;
 #pragma unroll
-            for (int c = 0; c < DMAX; ++c) th[0][c] = (EXACT || c < d) ? stage[c * TPB + threadIdx.x] : 0.0;
+            for (int c = 0; c < DMAX; ++c) th[0][c] = stage[c * TPB + threadIdx.x] + (double)delta[c];
             ll_old[0] = stage[d * TPB + threadIdx.x];
             lp_old[0] = stage[(d + 1) * TPB + threadIdx.x];
             __syncthreads();                       // the whole block has drained the stage
@@ -547,12 +606,11 @@ mh_kernel(const __grid_constant__ MhArgs a) {
 #pragma unroll
         for (int p = 0; p < PPT; ++p) lq_old[p] = (PROP && MODE == 1) ? a.lq[idx[p]] : 0.0;
 
-        if (MODE == 1 || MODE == 2) {
+        if ((MODE == 1 || MODE == 2) && !TMA) {
             // proposal x' = x + sqrt(s) L z, column-outer: z_j updates rows j..d-1, which are
             // independent accumulators (the parameter registers themselves)
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
-                const Philox rng(a.rng.seed);
                 const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[p]);
                 const double* zt = (a.rng.mode == 1) ? a.rng.z + idx[p] * d : nullptr;
 #pragma unroll
@@ -563,7 +621,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) z4[q] = (c + q < d) ? zt[c + q] : 0.0;
                         } else {
-                            const uint4 r = rng(pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
+                            const uint4 r = philox_k(a.rk, pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
                             normal_pair(r.x, r.y, z4[0], z4[1]);
                             normal_pair(r.z, r.w, z4[2], z4[3]);
                         }
@@ -668,9 +726,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                 if (a.rng.mode == 1) {
                     u = a.rng.u[i];
                 } else {
-                    const Philox rng(a.rng.seed);
-                    const uint4 r = rng((uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
-                    u = u01_53(r.x, r.y);
+                    u = gen_uniform53(&a.rk, (uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
                 }
                 const bool rejected = ratio < u;     // NaN compares false -> accept, as numpy does
                 if (!rejected && !(run[p] && not_pd[p])) {
@@ -865,7 +921,7 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
     if (p->loglike_id == SMCB_LL_MVNORMAL) data = (size_t)(p->n_snapshots * p->n_data + p->n_data) * 8;
     else if (p->model_id == SMCB_MODEL_LINEAR) data = (size_t)kChunk * 16;
     else if (p->model_id == SMCB_MODEL_SPRING_MASS) data = (size_t)kChunk * 8;
-    else data = (size_t)SMCB_MAX_PARAMS * 8;
+    else data = (size_t)(SMCB_MAX_PARAMS + 2) * 8;
     (void)d;
     return data + 16;      // + DMAX*DMAX doubles for the Cholesky factor, added per instantiation
 }
@@ -917,7 +973,7 @@ static int launch_cfg(const MhArgs& a, cudaStream_t s) {
                 static const bool no_tma = getenv("SMCB_NO_TMA") != nullptr;     // tuning aid
                 const bool aligned = ((((uintptr_t)a.params | (uintptr_t)a.ll | (uintptr_t)a.lp) & 15) == 0) &&
                                      (a.stride % 2 == 0) && (a.n % 2 == 0);
-                if (!no_tma && aligned && a.n >= (int64_t)kNumSMs * 8 * TPB)
+                if (!no_tma && aligned && a.rng.mode == 0 && a.n >= (int64_t)kNumSMs * 8 * TPB)
                     return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true, true>(a, s);
             }
             return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true>(a, s);
@@ -1105,6 +1161,7 @@ static void fill_step_args(MhArgs& a, const smcb_problem_t* prob, const smcb_pat
     a.accept_counts = reinterpret_cast<unsigned long long*>(accept_counts);
     a.step = step;
     a.rng = *rng;
+    a.rk = make_philox_keys(rng->seed);
     if (path) {
         const PathCoef c = make_path_coef(path->phi, path->phi_prev, path->lambda);
         a.phi = c.phi;
