@@ -306,6 +306,22 @@ int smcb_mh_accept(const smcb_path_t* path, double* params, const double* new_pa
                    const double* new_lp, uint8_t* moved, int64_t* accept_counts, int32_t step,
                    const smcb_rng_t* rng, void* stream);
 
+/* user model registered as CUDA source (north_star: "a registered __device__ model through the C-ABI").
+ * `source` defines
+ *     __device__ double smcb_user_model(const double* theta, int j, double x, double* state)
+ * = model output at data point j for the model parameters theta[0..n_model_params) (x = xgrid[j] or 0;
+ * state = 8 doubles per particle, zero at j = 0, persisting over j).  It replaces the user's
+ * `model(inputs)` callable of VectorMCMC.evaluate_model (smcpy/mcmc/vector_mcmc.py:88-89); NVRTC
+ * compiles it for sm_100a with a kernel that also evaluates the Normal log-likelihood
+ * (smcpy/log_likelihoods.py:22-49), so model outputs never reach HBM.  Host pointers; handle >= 1. */
+int smcb_model_register_nvrtc(const char* source, int32_t n_model_params, int32_t* handle_out);
+/* ll_out[i] = Normal log-likelihood of the registered model at SoA particle i (replaces
+ * "user model + smcb_normal_loglike_rows" in the un-fused route above) */
+int smcb_user_loglike(int32_t handle, const double* params, int64_t stride, int64_t n, int32_t m,
+                      const double* data, const double* xgrid /*or NULL*/, const double* sigma_col /*or NULL*/,
+                      double sigma, const double* lp /*or NULL: rows with -inf keep 0*/, double* ll_out,
+                      int32_t* flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

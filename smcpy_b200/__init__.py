@@ -11,7 +11,7 @@ __version__ = "0.1.0"
 from .engine import PhiloxRNG                                               # noqa: F401
 from .kernel import KernelBase, VectorMCMCKernel                            # noqa: F401
 from .log_likelihoods import MultiSourceNormal, MVNormal, Normal                               # noqa: F401
-from .models import IdentityModel, LinearModel, SpringMassModel             # noqa: F401
+from .models import IdentityModel, LinearModel, NvrtcModel, SpringMassModel             # noqa: F401
 from .particles import Particles                                            # noqa: F401
 from .paths import GeometricPath                                            # noqa: F401
 from .priors import ImproperCov, ImproperUniform                            # noqa: F401

@@ -116,6 +116,8 @@ SIGNATURES = {
     "smcb_mh_propose": [_PP(Problem), _P, _I64, _I64, _I64, _P, _P, _I32, _PP(Rng), _P, _P, _P],
     "smcb_normal_loglike_rows": [_P, _I64, _I32, _P, _P, _D, _P, _P, _P, _P],
     "smcb_mh_accept": [_PP(Path), _P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _P, _I32, _PP(Rng), _P],
+    "smcb_model_register_nvrtc": [C.c_char_p, _I32, C.POINTER(C.c_int32)],
+    "smcb_user_loglike": [_I32, _P, _I64, _I64, _I32, _P, _P, _P, _D, _P, _P, _P, _P],
 }
 OTHER_SYMBOLS = ["smcb_version", "smcb_last_error", "smcb_workspace_bytes"]
 

@@ -1,9 +1,10 @@
 """
-Un-fused Metropolis route for user models given as torch callables on device tensors
-(BASELINE.json north_star: "User models plug in either as a torch callable on device tensors
-or as a registered __device__ model").  Per step: smcb_mh_propose -> user model ->
-smcb_normal_loglike_rows -> smcb_mh_accept.  Pays 8*M bytes per particle for the model
-outputs, which the fused built-ins avoid.
+Un-fused Metropolis route for user models (BASELINE.json north_star: "User models plug in
+either as a torch callable on device tensors or as a registered __device__ model").
+Torch callable, per step: smcb_mh_propose -> user model -> smcb_normal_loglike_rows ->
+smcb_mh_accept; pays 8*M bytes per particle for the model outputs, which the fused built-ins
+avoid.  Registered CUDA source (models.NvrtcModel): smcb_mh_propose -> smcb_user_loglike ->
+smcb_mh_accept; outputs stay in registers.
 """
 
 import ctypes as C
@@ -12,6 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
+from .models import NvrtcModel
 
 
 def _model_ll(st, spec, soa_params, lp, ll_out):
@@ -19,6 +21,13 @@ def _model_ll(st, spec, soa_params, lp, ll_out):
     c = spec.c
     n, d = st.n, st.d
     dm = int(c.n_model_params)
+    sigma_col = soa_params[d - 1] if c.sigma_is_param else None
+    if isinstance(spec.model, NvrtcModel):                     # registered __device__ model: one kernel
+        m = spec.model
+        call("smcb_user_loglike", m.handle, ptr(soa_params), soa_params.stride(0), n, int(c.n_data),
+             C.c_void_p(int(c.data)), ptr(m.x_dev()), ptr(sigma_col), float(c.sigma), ptr(lp), ptr(ll_out),
+             ptr(st.flags), stream_ptr())
+        return
     aos = soa_params[:dm].t().contiguous()                     # (n, d_model) for the user callable
     out = spec.model(aos)
     if not (torch.is_tensor(out) and out.is_cuda and out.dtype == torch.float64):
@@ -26,7 +35,6 @@ def _model_ll(st, spec, soa_params, lp, ll_out):
     out = out.contiguous()
     if out.shape != (n, int(c.n_data)):
         raise ValueError("model output shape %s != (%d, %d)" % (tuple(out.shape), n, int(c.n_data)))
-    sigma_col = soa_params[d - 1] if c.sigma_is_param else None
     call("smcb_normal_loglike_rows", ptr(out), n, int(c.n_data), C.c_void_p(int(c.data)), ptr(sigma_col),
          float(c.sigma), ptr(lp), ptr(ll_out), ptr(st.flags), stream_ptr())
 

@@ -284,8 +284,15 @@ class ProblemSpec:
                 if model.n_out != c.n_data:
                     raise ValueError("identity model size and data length differ")
         else:
-            if not callable(model):
-                raise TypeError("model must be a smcpy_b200.models.DeviceModel or a torch callable")
+            from .models import NvrtcModel
+            if not (callable(model) or isinstance(model, NvrtcModel)):
+                raise TypeError("model must be a smcpy_b200.models.DeviceModel, NvrtcModel or a torch callable")
+            if isinstance(model, NvrtcModel):
+                if model.n_model_params != d - (1 if log_like_args is None else 0):
+                    raise ValueError("model takes %d parameters but the priors/likelihood leave %d"
+                                     % (model.n_model_params, d - (1 if log_like_args is None else 0)))
+                if kind == "normal" and model.n_out != int(data.reshape(-1).shape[0]):
+                    raise ValueError("model output count and data length differ")
             if kind != "normal":
                 raise NotImplementedError("torch-callable models support the Normal likelihood only")
             c.model_id = _lib.MODEL_IDENTITY      # unused by the un-fused kernels

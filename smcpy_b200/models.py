@@ -80,3 +80,44 @@ class IdentityModel(DeviceModel):
 
     def torch_eval(self, t):
         return t.clone()
+
+
+class NvrtcModel:
+    """User model given as CUDA source, registered through the C ABI (smcb_model_register_nvrtc)
+    -- the device-side counterpart of the reference's user callable `model(inputs)`
+    (smcpy/mcmc/vector_mcmc.py:88-89).  `source` defines
+
+        __device__ double smcb_user_model(const double* theta, int j, double x, double* state)
+
+    = output j of the model for parameters theta[0..n_params) (x = x[j] if a grid is given;
+    state = 8 doubles per particle, zero at j = 0, persisting over j).  Used by the un-fused
+    Metropolis route with the Normal likelihood; model outputs stay in registers."""
+
+    def __init__(self, source, n_params, n_out, x=None):
+        self.source = str(source)
+        self.n_model_params = int(n_params)
+        self.n_out = int(n_out)
+        self.x = None if x is None else np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+        if self.x is not None and self.x.shape[0] != self.n_out:
+            raise ValueError("grid length and n_out differ")
+        self._handle = None
+        self._x_dev = None
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            import ctypes as C
+            _lib.require_cuda()
+            h = C.c_int32(0)
+            _lib.call("smcb_model_register_nvrtc", self.source.encode(), self.n_model_params, C.byref(h), launches=0)
+            self._handle = int(h.value)
+        return self._handle
+
+    def x_dev(self):
+        if self.x is not None and self._x_dev is None:
+            import torch
+            self._x_dev = torch.as_tensor(self.x, device="cuda")
+        return self._x_dev
+
+    def __call__(self, inputs):
+        raise TypeError("NvrtcModel is evaluated inside the log-likelihood kernel; it has no host form")
