@@ -116,6 +116,7 @@ SIGNATURES = {
     "smcb_mh_propose": [_PP(Problem), _P, _I64, _I64, _I64, _P, _P, _I32, _PP(Rng), _P, _P, _P],
     "smcb_normal_loglike_rows": [_P, _I64, _I32, _P, _P, _D, _P, _P, _P, _P],
     "smcb_mh_accept": [_PP(Path), _P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _P, _I32, _PP(Rng), _P],
+    "smcb_exp_probe": [_P, _P, _I64, _P],
     "smcb_model_register_nvrtc": [C.c_char_p, _I32, C.POINTER(C.c_int32)],
     "smcb_user_loglike": [_I32, _P, _I64, _I64, _I32, _P, _P, _P, _D, _P, _P, _P, _P],
 }
@@ -160,7 +161,7 @@ class _LazyLib:
 
 lib = _LazyLib()
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
-LAUNCHES = {"smcb_reweight": 3, "smcb_cdf_scan": 2, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
+LAUNCHES = {"smcb_reweight": 2, "smcb_cdf_scan": 2, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
             "smcb_weighted_sums1": 2, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0}
 launch_count = 0
 

@@ -45,6 +45,20 @@ extern "C" int smcb_fp64_probe(double* out, int32_t blocks, int32_t iters, void*
     return smcb::check_launch("fp64_probe_kernel");
 }
 
+__global__ void exp_probe_kernel(const double* x, double* out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = smcb::exp_nonpos(x[i]);
+}
+
+extern "C" int smcb_exp_probe(const double* x, double* out, int64_t n, void* stream) {
+    if (!x || !out || n < 1) {
+        smcb::set_error("smcb_exp_probe: bad argument");
+        return SMCB_ERR_ARG;
+    }
+    exp_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, smcb::as_stream(stream)>>>(x, out, n);
+    return smcb::check_launch("exp_probe_kernel");
+}
+
 extern "C" int smcb_version(void) { return SMCB_VERSION; }
 
 extern "C" const char* smcb_last_error(void) { return smcb::g_err; }

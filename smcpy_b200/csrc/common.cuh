@@ -117,41 +117,74 @@ __device__ __forceinline__ Lse block_lse(Lse v, double* sh) {
     r.s2 = block_sum(v.s2 * (e * e), sh);
     return r;
 }
-// Merge of n partial triples stored as (m, s1, s2) rows by ONE warp (all 32 lanes call):
-// lane l handles rows l, l+32, ... in order.  Deterministic; result in every lane.
-__device__ __forceinline__ Lse warp_merge_partials(const volatile double* parts, int n) {
-    const int lane = threadIdx.x & 31;
+// Merge of n partial triples stored as (m, s1, s2) rows by a whole block (all threads call; result
+// valid in thread 0): every thread
+// takes rows t, t + blockDim, ... so the L2 round trips overlap instead of chaining ten deep in
+// one lane (the one-warp version cost ~9 us for 296 rows).  Rows are read with ld.global.cg:
+// they were written by other SMs.  Fixed reduction order: deterministic, identical in every block.
+__device__ __forceinline__ Lse block_merge_partials(const double* parts, int n, double* sh) {
     double m = kNegInf;
-    for (int b = lane; b < n; b += 32) m = fmax(m, parts[3 * b]);
-    m = warp_max(m);
+    for (int b = threadIdx.x; b < n; b += blockDim.x) m = fmax(m, __ldcg(parts + 3 * b));
+    const double bm = block_max_all(m, sh);
     double s1 = 0.0, s2 = 0.0;
-    if (m != kNegInf) {
-        for (int b = lane; b < n; b += 32) {
-            const double mb = parts[3 * b];
-            const double e = (mb == kNegInf) ? 0.0 : exp(mb - m);
-            s1 += parts[3 * b + 1] * e;
-            s2 += parts[3 * b + 2] * (e * e);
+    if (bm != kNegInf) {
+        for (int b = threadIdx.x; b < n; b += blockDim.x) {
+            const double mb = __ldcg(parts + 3 * b);
+            const double e = (mb == kNegInf) ? 0.0 : exp(mb - bm);
+            s1 += __ldcg(parts + 3 * b + 1) * e;
+            s2 += __ldcg(parts + 3 * b + 2) * (e * e);
         }
     }
     Lse r;
-    r.m = m;
-    r.s1 = warp_sum(s1);
-    r.s2 = warp_sum(s2);
+    r.m = bm;
+    r.s1 = block_sum(s1, sh);
+    r.s2 = block_sum(s2, sh);
     return r;
+}
+// exp(x) for x <= 0 (or -inf) as the streaming log-sum-exp loops need it: 2^(k/32) table + degree-6
+// polynomial on |r| <= ln2/64 (truncation 3.5e-18), no special-case paths; arguments below -708
+// (results under 1e-307 next to a maximum term of 1) return 0.  ~1 ulp; 11 FP64 instructions
+// against ~17 + select chains in the CUDA library exp.
+static __device__ const double kExpTab[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double kMagic = 6755399441055744.0;                      // 1.5 * 2^52: round-to-nearest-integer trick
+    double kd = fma(x, 0x1.71547652b82fep+5, kMagic);              // x * 32/ln2
+    const int ki = __double2loint(kd);
+    kd -= kMagic;
+    double r = fma(kd, -0x1.62e42fefa39efp-6, x);                  // ln2/32, hi + lo
+    r = fma(kd, -0x1.abc9e3b39803fp-61, r);
+    double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+    q = fma(q, r, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    const double t = __ldg(&kExpTab[ki & 31]);
+    const double sres = fma(r * r, q, r);                          // exp(r) - 1
+    const double v = fma(t, sres, t);
+    const double scaled = __hiloint2double(__double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
+    return (x >= -708.0) ? scaled : 0.0;
 }
 // add one value with a running max (rescale only when the max moves)
 __device__ __forceinline__ void lse_push4(Lse& acc, double v0, double v1, double v2, double v3) {
     const double tm = fmax(fmax(v0, v1), fmax(v2, v3));
     if (tm > acc.m) {
         if (acc.m != kNegInf) {
-            const double e = exp(acc.m - tm);
+            const double e = exp_nonpos(acc.m - tm);
             acc.s1 *= e;
             acc.s2 *= e * e;
         }
         acc.m = tm;
     }
     if (acc.m == kNegInf) return;
-    const double e0 = exp(v0 - acc.m), e1 = exp(v1 - acc.m), e2 = exp(v2 - acc.m), e3 = exp(v3 - acc.m);
+    const double e0 = exp_nonpos(v0 - acc.m), e1 = exp_nonpos(v1 - acc.m), e2 = exp_nonpos(v2 - acc.m),
+                 e3 = exp_nonpos(v3 - acc.m);
     acc.s1 += (e0 + e1) + (e2 + e3);
     acc.s2 += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
 }

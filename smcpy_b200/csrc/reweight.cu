@@ -15,7 +15,8 @@ namespace smcb {
 
 constexpr int kRwThreads = 256;
 constexpr int kRwItems = 4;
-constexpr int kRwBlocksPerSM = 4;   // LSE passes: few fat blocks keep the finalizer's merge short
+constexpr int kLseThreads = 512;    // streaming log-sum-exp passes: 32 warps/SM at 2 blocks hide the load latency
+constexpr int kLseBlocksPerSM = 2;
 
 struct RwIn {
     const double* ll;
@@ -44,6 +45,33 @@ __device__ __forceinline__ double inc_value(const RwIn& in, int64_t i) {
     return path_inc(ll, lp, lq, in.c);
 }
 
+// One thread's share of a streaming log-sum-exp pass: grid-stride, eight independent loads in
+// flight, then the (max, S1, S2) update four values at a time; the ragged end is predicated.
+template <bool kIncOnly>
+__device__ __forceinline__ double lse_val(const RwIn& in, int64_t i, int64_t n) {
+    if (i >= n) return kNegInf;
+    return kIncOnly ? inc_value(in, i) : rw_value(in, i);
+}
+template <bool kIncOnly>
+__device__ __forceinline__ void lse_stream(const RwIn& in, int64_t n, Lse& acc) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (kIncOnly) {          // (the reweight form reads up to four arrays: four wide is its register budget)
+        for (; i + 7 * stride < n; i += 8 * stride) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = inc_value(in, i + k * stride);
+            lse_push4(acc, v[0], v[1], v[2], v[3]);
+            lse_push4(acc, v[4], v[5], v[6], v[7]);
+        }
+    }
+    for (; i < n; i += 4 * stride) {
+        const double v0 = lse_val<kIncOnly>(in, i, n), v1 = lse_val<kIncOnly>(in, i + stride, n),
+                     v2 = lse_val<kIncOnly>(in, i + 2 * stride, n), v3 = lse_val<kIncOnly>(in, i + 3 * stride, n);
+        lse_push4(acc, v0, v1, v2, v3);
+    }
+}
+
 // Per-block (max, S1, S2) partials; the last block to finish merges them in block order
 // (deterministic) and writes the merged triple to `out3`.
 template <bool kIncOnly>
@@ -52,19 +80,7 @@ __device__ __forceinline__ bool lse_partials_body(const RwIn& in, int64_t n, dou
     __shared__ double sh[96];
     __shared__ bool is_last;
     Lse acc = lse_empty();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n; i += 4 * stride) {
-        const double v0 = kIncOnly ? inc_value(in, i) : rw_value(in, i);
-        const double v1 = kIncOnly ? inc_value(in, i + stride) : rw_value(in, i + stride);
-        const double v2 = kIncOnly ? inc_value(in, i + 2 * stride) : rw_value(in, i + 2 * stride);
-        const double v3 = kIncOnly ? inc_value(in, i + 3 * stride) : rw_value(in, i + 3 * stride);
-        lse_push4(acc, v0, v1, v2, v3);
-    }
-    for (; i < n; i += stride) {
-        const double v = kIncOnly ? inc_value(in, i) : rw_value(in, i);
-        lse_push4(acc, v, kNegInf, kNegInf, kNegInf);
-    }
+    lse_stream<kIncOnly>(in, n, acc);
     acc = block_lse(acc, sh);
     if (threadIdx.x == 0) {
         partials[3 * blockIdx.x + 0] = acc.m;
@@ -77,25 +93,17 @@ __device__ __forceinline__ bool lse_partials_body(const RwIn& in, int64_t n, dou
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    // warp 0 merges the block partials (max first, then independent rescales, fixed order)
-    if (threadIdx.x < 32) {
-        const Lse a = warp_merge_partials(partials, (int)gridDim.x);
-        if (threadIdx.x == 0) {
-            out3[0] = a.m;
-            out3[1] = a.s1;
-            out3[2] = a.s2;
-            *ticket = 0u;
-            merged = a;
-            return true;      // the one finalizer thread of the grid
-        }
+    // the last block merges the block partials (max first, then independent rescales, fixed order)
+    const Lse a = block_merge_partials(partials, (int)gridDim.x, sh);
+    if (threadIdx.x == 0) {
+        out3[0] = a.m;
+        out3[1] = a.s1;
+        out3[2] = a.s2;
+        *ticket = 0u;
+        merged = a;
+        return true;          // the one finalizer thread of the grid
     }
     return false;
-}
-
-__global__ void __launch_bounds__(kRwThreads) rw_partials_kernel(RwIn in, int64_t n, double* partials,
-                                                                 unsigned int* ticket, double* out3) {
-    Lse merged;
-    lse_partials_body<false>(in, n, partials, ticket, out3, merged);
 }
 
 // scalars: [0] max, [1] S1, [2] S2, [3] total_unnorm_log_weight, [4] ESS, [5] log S1
@@ -107,6 +115,15 @@ __device__ __forceinline__ void write_scalars(const Lse& a, double* sc) {
     sc[3] = a.m + ls;                       // = Z0 + log(1 + sum exp(Z - Z0)), particles.py:200-205
     sc[4] = (a.s1 * a.s1) / a.s2;           // = 1 / sum w^2, particles.py:158-162
     sc[5] = ls;
+}
+
+// `scalars` != nullptr (single GPU): the finalizer thread also writes the normalisation scalars,
+// which saves the separate merge launch.
+__global__ void __launch_bounds__(kLseThreads, kLseBlocksPerSM) rw_partials_kernel(RwIn in, int64_t n, double* partials,
+                                                                                  unsigned int* ticket, double* out3,
+                                                                                  double* scalars) {
+    Lse merged;
+    if (lse_partials_body<false>(in, n, partials, ticket, out3, merged) && scalars) write_scalars(merged, scalars);
 }
 
 __global__ void lse_merge_kernel(const double* parts, int n_parts, double* sc) {
@@ -122,11 +139,13 @@ __global__ void __launch_bounds__(kRwThreads) rw_finalize_kernel(RwIn in, int64_
                                                                  double* log_w, double* w) {
     const double m = sc[0], ls = sc[5];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n; i += 4 * stride) {          // four independent load/exp/store chains
+    // back to front: the partials pass streamed the inputs front to back, so its tail is what
+    // the L2 still holds
+    int64_t i = n - 1 - ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    for (; i - 3 * stride >= 0; i -= 4 * stride) {          // four independent load/exp/store chains
         double v[4], lw[4], wi[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = rw_value(in, i + k * stride);
+        for (int k = 0; k < 4; ++k) v[k] = rw_value(in, i - k * stride);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             lw[k] = (v[k] - m) - ls;
@@ -135,11 +154,11 @@ __global__ void __launch_bounds__(kRwThreads) rw_finalize_kernel(RwIn in, int64_
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            log_w[i + k * stride] = lw[k];
-            w[i + k * stride] = wi[k];
+            log_w[i - k * stride] = lw[k];
+            w[i - k * stride] = wi[k];
         }
     }
-    for (; i < n; i += stride) {
+    for (; i >= 0; i -= stride) {
         const double v = rw_value(in, i);
         double lw = (v - m) - ls;
         double wi = exp(lw);
@@ -231,7 +250,7 @@ __device__ void bisect_advance(double* st, const Lse& a, double phi_old, double 
 }
 
 // one ESS evaluation at x = state[6]; the last block advances the bisection (single GPU)
-__global__ void __launch_bounds__(kRwThreads) ess_eval_kernel(RwIn in, int64_t n, double phi_old,
+__global__ void __launch_bounds__(kLseThreads, kLseBlocksPerSM) ess_eval_kernel(RwIn in, int64_t n, double phi_old,
                                                              double lambda, double target, double n_global,
                                                              double* st, double* partials,
                                                              unsigned int* ticket, double* out3,
@@ -260,8 +279,8 @@ __global__ void bisect_update_kernel(const double* parts, int n_parts, double ph
 // barrier after each evaluation; every block merges the same block partials in the same order
 // and advances an identical copy of the scipy state machine, so no block ever disagrees about
 // the next evaluation point.  Partials are double-buffered by iteration parity and read with
-// volatile (L2) loads.
-__global__ void __launch_bounds__(kRwThreads) ess_bisect_coop_kernel(RwIn in, int64_t n, double phi_old,
+// ld.global.cg (L2) loads.
+__global__ void __launch_bounds__(1024, 1) ess_bisect_coop_kernel(RwIn in, int64_t n, double phi_old,
                                                                     double lambda, double target, double n_global,
                                                                     double* st_out, double* partials, int max_iters) {
     namespace cg = cooperative_groups;
@@ -273,7 +292,6 @@ __global__ void __launch_bounds__(kRwThreads) ess_bisect_coop_kernel(RwIn in, in
         st[5] = 0.0; st[6] = 1.0; st[7] = 0.0; st[8] = 0.0; st[9] = 0.0;
     }
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int it = 0; it < max_iters; ++it) {
         if (st[2] != 0.0) break;                       // identical in every block
         const double x = st[6];
@@ -281,11 +299,7 @@ __global__ void __launch_bounds__(kRwThreads) ess_bisect_coop_kernel(RwIn in, in
         in.c.pe = fmin(1.0, x / lambda);
         in.c.qe = fmax(0.0, (lambda - x) / lambda);
         Lse acc = lse_empty();
-        int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        for (; i + 3 * stride < n; i += 4 * stride)
-            lse_push4(acc, inc_value(in, i), inc_value(in, i + stride), inc_value(in, i + 2 * stride),
-                      inc_value(in, i + 3 * stride));
-        for (; i < n; i += stride) lse_push4(acc, inc_value(in, i), kNegInf, kNegInf, kNegInf);
+        lse_stream<true>(in, n, acc);
         acc = block_lse(acc, sh);
         double* buf = partials + (size_t)(it & 1) * 3 * gridDim.x;
         if (threadIdx.x == 0) {
@@ -294,10 +308,8 @@ __global__ void __launch_bounds__(kRwThreads) ess_bisect_coop_kernel(RwIn in, in
             buf[3 * blockIdx.x + 2] = acc.s2;
         }
         grid.sync();
-        if (threadIdx.x < 32) {
-            const Lse m = warp_merge_partials(buf, (int)gridDim.x);
-            if (threadIdx.x == 0) bisect_advance(st, m, phi_old, target, n_global);
-        }
+        const Lse m = block_merge_partials(buf, (int)gridDim.x, sh);
+        if (threadIdx.x == 0) bisect_advance(st, m, phi_old, target, n_global);
         __syncthreads();
     }
     if (blockIdx.x == 0 && threadIdx.x < 10) st_out[threadIdx.x] = st[threadIdx.x];
@@ -333,10 +345,10 @@ extern "C" int smcb_reweight_partials(int64_t n, const double* ll, const double*
                                       double* partial_out, void* ws, void* stream) {
     SMCB_REQUIRE(n > 0 && ll && lp && path && partial_out && ws, "bad argument");
     RwIn in = make_in(ll, lp, lq, log_w_in, n_global, path);
-    const int grid = grid_for(n, kRwThreads, kRwItems, kRwBlocksPerSM);
+    const int grid = grid_for(n, kLseThreads, kRwItems, kLseBlocksPerSM);
     char* w = (char*)ws;
-    rw_partials_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(
-        in, n, (double*)(w + kWsPartials), (unsigned int*)(w + kWsTickets), partial_out);
+    rw_partials_kernel<<<grid, kLseThreads, 0, as_stream(stream)>>>(
+        in, n, (double*)(w + kWsPartials), (unsigned int*)(w + kWsTickets), partial_out, nullptr);
     return check_launch("rw_partials_kernel");
 }
 
@@ -361,11 +373,13 @@ extern "C" int smcb_reweight(int64_t n, const double* ll, const double* lp, cons
                              const double* log_w_in, int64_t n_global, const smcb_path_t* path,
                              double* log_w_out, double* w_out, double* scalars_out, void* ws,
                              void* stream) {
-    SMCB_REQUIRE(ws != nullptr, "workspace required");
-    double* part = (double*)((char*)ws + kWsSmall);
-    int rc = smcb_reweight_partials(n, ll, lp, lq, log_w_in, n_global, path, part, ws, stream);
-    if (rc) return rc;
-    rc = smcb_lse_merge(part, 1, scalars_out, stream);
+    SMCB_REQUIRE(n > 0 && ll && lp && path && scalars_out && ws, "bad argument");
+    char* w = (char*)ws;
+    RwIn in = make_in(ll, lp, lq, log_w_in, n_global, path);
+    const int grid = grid_for(n, kLseThreads, kRwItems, kLseBlocksPerSM);
+    rw_partials_kernel<<<grid, kLseThreads, 0, as_stream(stream)>>>(
+        in, n, (double*)(w + kWsPartials), (unsigned int*)(w + kWsTickets), (double*)(w + kWsSmall), scalars_out);
+    int rc = check_launch("rw_partials_kernel");
     if (rc) return rc;
     return smcb_reweight_finalize(n, ll, lp, lq, log_w_in, n_global, path, scalars_out, log_w_out, w_out,
                                   stream);
@@ -387,9 +401,9 @@ extern "C" int smcb_ess_partial(int64_t n, const double* ll, const double* lp, c
     smcb_path_t p{phi_old, phi_old, lambda};
     RwIn in = make_in(ll, lp, lq, nullptr, 1, &p);
     in.lp_const = lp_const;
-    const int grid = grid_for(n, kRwThreads, kRwItems, kRwBlocksPerSM);
+    const int grid = grid_for(n, kLseThreads, kRwItems, kLseBlocksPerSM);
     char* w = (char*)ws;
-    ess_eval_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(
+    ess_eval_kernel<<<grid, kLseThreads, 0, as_stream(stream)>>>(
         in, n, phi_old, lambda, 0.0, 0.0, const_cast<double*>(state), (double*)(w + kWsPartials),
         (unsigned int*)(w + kWsTickets), partial_out, 0);
     return check_launch("ess_eval_kernel");
@@ -421,24 +435,28 @@ extern "C" int smcb_ess_bisect(int64_t n, const double* ll, const double* lp, co
     in.lp_const = lp_const;
     char* w = (char*)ws;
     int iters = bisect_iters(phi_old);
+    static int coop_tpb = kLseThreads;
     static int coop_blocks = -1;       // co-resident blocks of the cooperative kernel (0: unsupported)
     if (coop_blocks < 0) {
         int dev = 0, coop = 0, per_sm = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ess_bisect_coop_kernel, kRwThreads, 0);
-        coop_blocks = (coop && per_sm > 0) ? sms * (per_sm < 2 ? per_sm : 2) : 0;
+        if (const char* e = getenv("SMCB_COOP_TPB")) coop_tpb = atoi(e);   // tuning aids: threads per block, blocks per SM
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ess_bisect_coop_kernel, coop_tpb, 0);
+        int want = 1;                  // one fat block per SM: the grid barrier + partial merge per evaluation scale with the block count
+        if (const char* e = getenv("SMCB_COOP_BPS")) want = atoi(e);
+        coop_blocks = (coop && per_sm > 0) ? sms * (per_sm < want ? per_sm : want) : 0;
         if (getenv("SMCB_NO_COOP")) coop_blocks = 0;        // tuning aid: launch-chain version
     }
     if (coop_blocks > 0) {
-        int grid = grid_for(n, kRwThreads, kRwItems, 2);
+        int grid = grid_for(n, coop_tpb, kRwItems, 8);
         if (grid > coop_blocks) grid = coop_blocks;
         double* partials = (double*)(w + kWsPartials);
         double ng = (double)n_global;
         void* args[] = {&in, &n, &phi_old, &lambda, &target_ess, &ng, &state, &partials, &iters};
         const cudaError_t e = cudaLaunchCooperativeKernel((const void*)ess_bisect_coop_kernel, dim3(grid),
-                                                          dim3(kRwThreads), args, 0, as_stream(stream));
+                                                          dim3(coop_tpb), args, 0, as_stream(stream));
         if (e != cudaSuccess) {
             set_error("ess_bisect_coop_kernel: %s", cudaGetErrorString(e));
             return SMCB_ERR_CUDA;
@@ -447,9 +465,9 @@ extern "C" int smcb_ess_bisect(int64_t n, const double* ll, const double* lp, co
     }
     int rc = smcb_ess_bisect_begin(phi_old, state, stream);
     if (rc) return rc;
-    const int grid = grid_for(n, kRwThreads, kRwItems, kRwBlocksPerSM);
+    const int grid = grid_for(n, kLseThreads, kRwItems, kLseBlocksPerSM);
     for (int it = 0; it < iters; ++it) {
-        ess_eval_kernel<<<grid, kRwThreads, 0, as_stream(stream)>>>(
+        ess_eval_kernel<<<grid, kLseThreads, 0, as_stream(stream)>>>(
             in, n, phi_old, lambda, target_ess, (double)n_global, state, (double*)(w + kWsPartials),
             (unsigned int*)(w + kWsTickets), (double*)(w + kWsSmall), 1);
     }

@@ -623,6 +623,27 @@ def test_nvrtc_model_in_adaptive_sampler_and_compile_error(sb):
         bad.handle
 
 
+def test_streaming_exp_accuracy(sb):
+    """The table-driven exp of the log-sum-exp loops (common.cuh exp_nonpos) against numpy's exp
+    on its whole domain: <= 2 ulp, exact 1 at 0, 0 for -inf and below -708."""
+    import torch
+    from smcpy_b200 import _lib
+    rng = np.random.default_rng(0)
+    x = np.concatenate([-rng.uniform(0, 1, 200000), -rng.uniform(0, 708, 400000), -10.0 ** rng.uniform(-300, 0, 100000),
+                        np.array([0.0, -0.0, -708.0, -708.5, -745.0, -1e300, -np.inf]),
+                        -np.arange(0, 1400) * (np.log(2) / 64)])
+    xd = torch.as_tensor(x, device="cuda")
+    out = torch.empty_like(xd)
+    _lib.call("smcb_exp_probe", _lib.ptr(xd), _lib.ptr(out), x.shape[0], _lib.stream_ptr())
+    got = out.cpu().numpy()
+    want = np.exp(x)
+    keep = x >= -708.0
+    ulp = np.abs(got[keep] - want[keep]) / np.spacing(want[keep])
+    assert ulp.max() <= 2.0, ulp.max()
+    assert np.all(got[~keep] == 0.0)
+    assert np.all(got[x == 0.0] == 1.0)
+
+
 def test_wide_identity_kernel_tma_path_vs_oracle(sb):
     """2^18 particles x d=32 takes the persistent, TMA-staged (cp.async.bulk + mbarrier) variant
     of the fused Metropolis kernel; replayed draws against the oracle, 1e-10."""
