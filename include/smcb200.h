@@ -205,6 +205,16 @@ int smcb_ess_partial(int64_t n, const double* ll, const double* lp, const double
 int smcb_ess_bisect_update(const double* partials, int32_t n_parts, double phi_old,
                            double target_ess, int64_t n_global, double* state, void* stream);
 int smcb_ess_bisect_max_iters(void);
+/* multi-GPU form of smcb_ess_bisect (replaces the MPI-free but collective-per-evaluation loop
+ * smcb_ess_partial -> all-gather -> smcb_ess_bisect_update): ONE cooperative launch per rank; after
+ * every evaluation the ranks exchange their (max, S1, S2) over NVLink peer memory inside the kernel.
+ * x->peer_slots[r]: rank r's symmetric slot buffer of smcb_ess_bisect_xchg_slot_words() uint64
+ * (zero-initialised once, mapped by every peer); x->gen must increase with every call;
+ * x->global_counts / x->ticket are unused.  state[2] = -1 if a peer never answered. */
+int smcb_ess_bisect_xchg_slot_words(void);
+int smcb_ess_bisect_xchg(int64_t n, const double* ll, const double* lp, const double* lq,
+                         double lp_const, double phi_old, double lambda, double target_ess,
+                         int64_t n_global, double* state, void* ws, const smcb_xchg_t* x, void* stream);
 
 /* ---- (c) resampling ---------------------------------------------------------------- */
 /* u for `count` global slots starting at `first` out of n_global (resampler_rngs.py:4-9) */

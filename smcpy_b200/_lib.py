@@ -91,6 +91,7 @@ SIGNATURES = {
     "smcb_ess_partial": [_I64, _P, _P, _P, _D, _D, _D, _P, _P, _P, _P],
     "smcb_ess_bisect_update": [_P, _I32, _D, _D, _I64, _P, _P],
     "smcb_ess_bisect_max_iters": [],
+    "smcb_ess_bisect_xchg_slot_words": [],
     "smcb_resample_uniforms": [_I32, _I64, _I64, _I64, _U64, _U64, _P, _P],
     "smcb_resample_uniforms_sharded": [_I32, _P, _I64, _I64, _U64, _U64, _P, _P],
     "smcb_cdf_scan": [_P, _P, _I64, _I32, _P, _P],
@@ -116,6 +117,7 @@ SIGNATURES = {
     "smcb_mh_propose": [_PP(Problem), _P, _I64, _I64, _I64, _P, _P, _I32, _PP(Rng), _P, _P, _P],
     "smcb_normal_loglike_rows": [_P, _I64, _I32, _P, _P, _D, _P, _P, _P, _P],
     "smcb_mh_accept": [_PP(Path), _P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _P, _I32, _PP(Rng), _P],
+    "smcb_ess_bisect_xchg": [_I64, _P, _P, _P, _D, _D, _D, _D, _I64, _P, _P, _PP(Xchg), _P],
     "smcb_exp_probe": [_P, _P, _I64, _P],
     "smcb_model_register_nvrtc": [C.c_char_p, _I32, C.POINTER(C.c_int32)],
     "smcb_user_loglike": [_I32, _P, _I64, _I64, _I32, _P, _P, _P, _D, _P, _P, _P, _P],
@@ -162,7 +164,8 @@ class _LazyLib:
 lib = _LazyLib()
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
 LAUNCHES = {"smcb_reweight": 2, "smcb_cdf_scan": 2, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
-            "smcb_weighted_sums1": 2, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0}
+            "smcb_weighted_sums1": 2, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0,
+            "smcb_ess_bisect_xchg_slot_words": 0}
 launch_count = 0
 
 

@@ -315,6 +315,100 @@ __global__ void __launch_bounds__(1024, 1) ess_bisect_coop_kernel(RwIn in, int64
     if (blockIdx.x == 0 && threadIdx.x < 10) st_out[threadIdx.x] = st[threadIdx.x];
 }
 
+// ---- multi-GPU: the same single launch, partial exchange over NVLink peer memory ----------------
+// Each rank owns a symmetric slot buffer of kBisSlotWords uint64 mapped by every peer:
+// [call parity][iteration parity][rank][4] = (max, S1, S2 bit patterns, flag).  After the local
+// grid barrier block 0 stores the rank's merged triple into slot [..][rank] of EVERY rank, fences
+// (system scope) and then stores the flag gen * 64 + iteration + 1; thread 0 of every block waits
+// for all `world` flags in its OWN memory, merges the triples in rank order (the order of the
+// all-gather fallback, bisect_update_kernel) and advances its copy of the search.  A peer can be
+// at most one evaluation ahead (it needs this rank's next triple to go further), so two
+// iteration parities suffice; the call parity keeps a slow peer's last slot of the previous
+// search intact.
+constexpr int kBisSlotWords = 2 * 2 * SMCB_MAX_RANKS * 4;
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(1024, 1) ess_bisect_coop_xchg_kernel(RwIn in, int64_t n, double phi_old,
+                                                                      double lambda, double target, double n_global,
+                                                                      double* st_out, double* partials, int max_iters,
+                                                                      smcb_xchg_t x) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[96];
+    __shared__ double st[16];
+    if (threadIdx.x == 0) {
+        st[0] = 1.0; st[1] = 0.0; st[2] = 0.0; st[3] = phi_old; st[4] = 1.0 - phi_old;
+        st[5] = 0.0; st[6] = 1.0; st[7] = 0.0; st[8] = 0.0; st[9] = 0.0;
+    }
+    __syncthreads();
+    const size_t call_off = (size_t)(x.gen & 1) * 2 * SMCB_MAX_RANKS * 4;
+    for (int it = 0; it < max_iters; ++it) {
+        if (st[2] != 0.0) break;                       // identical in every block of every rank
+        const double xq = st[6];
+        in.c.phi = xq;
+        in.c.pe = fmin(1.0, xq / lambda);
+        in.c.qe = fmax(0.0, (lambda - xq) / lambda);
+        Lse acc = lse_empty();
+        lse_stream<true>(in, n, acc);
+        acc = block_lse(acc, sh);
+        double* buf = partials + (size_t)(it & 1) * 3 * gridDim.x;
+        if (threadIdx.x == 0) {
+            buf[3 * blockIdx.x + 0] = acc.m;
+            buf[3 * blockIdx.x + 1] = acc.s1;
+            buf[3 * blockIdx.x + 2] = acc.s2;
+        }
+        grid.sync();
+        const Lse mine = block_merge_partials(buf, (int)gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            const unsigned long long flag = x.gen * 64ull + (unsigned long long)it + 1ull;
+            const size_t off = call_off + (size_t)(it & 1) * SMCB_MAX_RANKS * 4;
+            if (blockIdx.x == 0) {
+                for (int r = 0; r < x.world; ++r) {
+                    unsigned long long* slot = reinterpret_cast<unsigned long long*>(x.peer_slots[r]) + off + 4 * x.rank;
+                    st_sys_u64(slot + 0, (unsigned long long)__double_as_longlong(mine.m));
+                    st_sys_u64(slot + 1, (unsigned long long)__double_as_longlong(mine.s1));
+                    st_sys_u64(slot + 2, (unsigned long long)__double_as_longlong(mine.s2));
+                }
+                __threadfence_system();
+                for (int r = 0; r < x.world; ++r)
+                    st_sys_u64(reinterpret_cast<unsigned long long*>(x.peer_slots[r]) + off + 4 * x.rank + 3, flag);
+            }
+            const unsigned long long* own = reinterpret_cast<const unsigned long long*>(x.peer_slots[x.rank]) + off;
+            bool ok = true;
+            for (int r = 0; r < x.world && ok; ++r) {
+                long long spins = 0;
+                while (ld_sys_u64(own + 4 * r + 3) != flag) {
+                    __nanosleep(32);
+                    if (++spins > (1ll << 25)) { ok = false; break; }      // a peer is gone: give up (~seconds)
+                }
+            }
+            if (!ok) {
+                st[2] = -1.0;
+            } else {
+                __threadfence_system();
+                Lse a = lse_empty();
+                for (int r = 0; r < x.world; ++r) {
+                    Lse b;
+                    b.m = __longlong_as_double((long long)ld_sys_u64(own + 4 * r + 0));
+                    b.s1 = __longlong_as_double((long long)ld_sys_u64(own + 4 * r + 1));
+                    b.s2 = __longlong_as_double((long long)ld_sys_u64(own + 4 * r + 2));
+                    a = lse_merge(a, b);
+                }
+                bisect_advance(st, a, phi_old, target, n_global);
+            }
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 10) st_out[threadIdx.x] = st[threadIdx.x];
+}
+
 static RwIn make_in(const double* ll, const double* lp, const double* lq, const double* lw,
                     int64_t n_global, const smcb_path_t* path) {
     RwIn in;
@@ -425,6 +519,26 @@ static int bisect_iters(double phi_old) {
     return k < kBisectMaxIters ? k : kBisectMaxIters;
 }
 
+// co-resident grid of the cooperative kernels (0: cooperative launch unsupported / disabled)
+static int coop_config(const void* kernel, int* tpb_out) {
+    static int coop_tpb = kLseThreads;
+    static int want = -1;
+    int dev = 0, coop = 0, per_sm = 0, sms = 0;
+    if (want < 0) {
+        want = 1;      // one fat block per SM: the grid barrier + partial merge per evaluation scale with the block count
+        if (const char* e = getenv("SMCB_COOP_TPB")) coop_tpb = atoi(e);   // tuning aids: threads per block, blocks per SM
+        if (const char* e = getenv("SMCB_COOP_BPS")) want = atoi(e);
+        if (getenv("SMCB_NO_COOP")) want = 0;                              // launch-chain version
+    }
+    *tpb_out = coop_tpb;
+    if (want == 0) return 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, coop_tpb, 0);
+    return (coop && per_sm > 0) ? sms * (per_sm < want ? per_sm : want) : 0;
+}
+
 extern "C" int smcb_ess_bisect(int64_t n, const double* ll, const double* lp, const double* lq,
                                double lp_const, double phi_old, double lambda, double target_ess,
                                int64_t n_global, double* state, void* ws, void* stream) {
@@ -435,20 +549,8 @@ extern "C" int smcb_ess_bisect(int64_t n, const double* ll, const double* lp, co
     in.lp_const = lp_const;
     char* w = (char*)ws;
     int iters = bisect_iters(phi_old);
-    static int coop_tpb = kLseThreads;
-    static int coop_blocks = -1;       // co-resident blocks of the cooperative kernel (0: unsupported)
-    if (coop_blocks < 0) {
-        int dev = 0, coop = 0, per_sm = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (const char* e = getenv("SMCB_COOP_TPB")) coop_tpb = atoi(e);   // tuning aids: threads per block, blocks per SM
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ess_bisect_coop_kernel, coop_tpb, 0);
-        int want = 1;                  // one fat block per SM: the grid barrier + partial merge per evaluation scale with the block count
-        if (const char* e = getenv("SMCB_COOP_BPS")) want = atoi(e);
-        coop_blocks = (coop && per_sm > 0) ? sms * (per_sm < want ? per_sm : want) : 0;
-        if (getenv("SMCB_NO_COOP")) coop_blocks = 0;        // tuning aid: launch-chain version
-    }
+    static int coop_blocks = -1, coop_tpb = 0;
+    if (coop_blocks < 0) coop_blocks = coop_config((const void*)ess_bisect_coop_kernel, &coop_tpb);
     if (coop_blocks > 0) {
         int grid = grid_for(n, coop_tpb, kRwItems, 8);
         if (grid > coop_blocks) grid = coop_blocks;
@@ -472,4 +574,41 @@ extern "C" int smcb_ess_bisect(int64_t n, const double* ll, const double* lp, co
             (unsigned int*)(w + kWsTickets), (double*)(w + kWsSmall), 1);
     }
     return check_launch("ess_eval_kernel");
+}
+
+extern "C" int smcb_ess_bisect_xchg_slot_words(void) { return kBisSlotWords; }
+
+extern "C" int smcb_ess_bisect_xchg(int64_t n, const double* ll, const double* lp, const double* lq,
+                                    double lp_const, double phi_old, double lambda, double target_ess,
+                                    int64_t n_global, double* state, void* ws, const smcb_xchg_t* x,
+                                    void* stream) {
+    SMCB_REQUIRE(n > 0 && ll && state && ws && x, "bad argument");
+    SMCB_REQUIRE(phi_old >= 0.0 && phi_old < 1.0, "phi_old must be in [0, 1)");
+    SMCB_REQUIRE(x->world >= 2 && x->world <= SMCB_MAX_RANKS && x->rank >= 0 && x->rank < x->world && x->gen > 0,
+                 "bad exchange descriptor");
+    smcb_path_t p{phi_old, phi_old, lambda};
+    RwIn in = make_in(ll, lp, lq, nullptr, 1, &p);
+    in.lp_const = lp_const;
+    char* w = (char*)ws;
+    int iters = bisect_iters(phi_old);
+    static int coop_blocks = -1, coop_tpb = 0;
+    if (coop_blocks < 0) coop_blocks = coop_config((const void*)ess_bisect_coop_xchg_kernel, &coop_tpb);
+    if (coop_blocks <= 0) {
+        set_error("smcb_ess_bisect_xchg needs cooperative launch");
+        return SMCB_ERR_UNSUPPORTED;
+    }
+    // every rank must take the same number of local blocks only for its own merge: grids may differ
+    int grid = grid_for(n, coop_tpb, kRwItems, 8);
+    if (grid > coop_blocks) grid = coop_blocks;
+    double* partials = (double*)(w + kWsPartials);
+    double ng = (double)n_global;
+    smcb_xchg_t xv = *x;
+    void* args[] = {&in, &n, &phi_old, &lambda, &target_ess, &ng, &state, &partials, &iters, &xv};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)ess_bisect_coop_xchg_kernel, dim3(grid),
+                                                      dim3(coop_tpb), args, 0, as_stream(stream));
+    if (e != cudaSuccess) {
+        set_error("ess_bisect_coop_xchg_kernel: %s", cudaGetErrorString(e));
+        return SMCB_ERR_CUDA;
+    }
+    return SMCB_OK;
 }

@@ -11,6 +11,7 @@ gather over d+2 columns into the ping-pong twin.
 
 import ctypes as C
 import math
+import os
 import warnings
 
 import numpy as np
@@ -64,6 +65,16 @@ class AcceptExchange:
         self.global_counts = torch.zeros(_lib.MAX_MCMC_STEPS, dtype=torch.int64, device=dv)
         self.ticket = torch.zeros(4, dtype=torch.int32, device=dv)
         self.gen = 0
+        # second symmetric buffer: the (max, S1, S2) exchange of the fused bisection (smcb_ess_bisect_xchg)
+        self.bis_slots = symm_mem.empty(int(_lib.lib.smcb_ess_bisect_xchg_slot_words()), dtype=torch.int64, device=dv)
+        self.bis_slots.zero_()
+        self.bis_handle = symm_mem.rendezvous(self.bis_slots, dist.group.WORLD)
+        self.bis_gen = 0
+        xb = _lib.Xchg()
+        xb.world, xb.rank = world, rank
+        for r, p in enumerate(peer_pointers(self.bis_slots, self.bis_handle)):
+            xb.peer_slots[r] = p
+        self.xb = xb
         x = _lib.Xchg()
         x.world, x.rank = world, rank
         for r, p in enumerate(peer_pointers(self.slots, self.handle)):
@@ -90,6 +101,13 @@ class AcceptExchange:
                 cls._failed = True
                 return None
         return cls._inst
+
+    def next_bisect_gen(self):
+        self.bis_gen += 1
+        if self.bis_gen >= (1 << 56):
+            raise RuntimeError("bisection exchange generation overflow")
+        self.xb.gen = self.bis_gen
+        return self.xb
 
     def next_gen(self):
         self.gen += 1
@@ -500,16 +518,25 @@ def find_phi(st, spec, phi_old, target_ess, lam=1.0):
         with _timed("bisect"):
             call("smcb_ess_bisect", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
                  float(target_ess), st.n_global, ptr(st.bis), ptr(st.ws), s, launches=1)
+    elif AcceptExchange.get() is not None and not os.environ.get("SMCB_NO_BISECT_XCHG"):
+        # one cooperative launch per rank, partials exchanged over NVLink peer memory in the kernel
+        with _timed("bisect"):
+            xb = AcceptExchange.get().next_bisect_gen()
+            call("smcb_ess_bisect_xchg", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
+                 float(target_ess), st.n_global, ptr(st.bis), ptr(st.ws), C.byref(xb), s, launches=1)
     else:
-        call("smcb_ess_bisect_begin", float(phi_old), ptr(st.bis), s)
-        part = st.scalars[8:11]
-        for _ in range(bisect_iters(phi_old)):
-            call("smcb_ess_partial", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
-                 ptr(st.bis), ptr(part), ptr(st.ws), s)
-            parts = _all_gather_rows(part)
-            call("smcb_ess_bisect_update", ptr(parts), world, float(phi_old), float(target_ess), st.n_global,
-                 ptr(st.bis), s)
+        with _timed("bisect"):
+            call("smcb_ess_bisect_begin", float(phi_old), ptr(st.bis), s)
+            part = st.scalars[8:11]
+            for _ in range(bisect_iters(phi_old)):
+                call("smcb_ess_partial", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
+                     ptr(st.bis), ptr(part), ptr(st.ws), s)
+                parts = _all_gather_rows(part)
+                call("smcb_ess_bisect_update", ptr(parts), world, float(phi_old), float(target_ess), st.n_global,
+                     ptr(st.bis), s)
     b = st.bis[:10].cpu().numpy()
+    if b[2] < 0.0:
+        raise RuntimeError("fused multi-GPU bisection: a peer rank never answered")
     if b[2] == 0.0:
         raise RuntimeError("device bisection did not converge")
     return float(b[0])

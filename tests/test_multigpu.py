@@ -112,6 +112,20 @@ def _nccl_worker(rank, world, port, out):
         last = steps[-1]
         res[resampler.__name__] = (float(mll[-1]), last.compute_mean(package=False), last.num_particles,
                                    len(steps), float(last.compute_ess()))
+    # fused bisection (partials exchanged over NVLink inside one cooperative launch) against the
+    # all-gather-per-evaluation fallback: same search, per-rank partials merged in the same order
+    phis = {}
+    for mode in ("fused", "nccl"):
+        if mode == "nccl":
+            os.environ["SMCB_NO_BISECT_XCHG"] = "1"
+        mcmc, kernel = make_b200(configs.linear_problem(100), rng=11)
+        smc = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            steps, mll = smc.sample(30000, 3, target_ess=0.8)
+        phis[mode] = (np.asarray(smc.phi_sequence, dtype=np.float64), float(mll[-1]))
+    os.environ.pop("SMCB_NO_BISECT_XCHG", None)
+    res["bisect"] = phis
     out.put((rank, res))
     dist.destroy_process_group()
 
@@ -131,6 +145,13 @@ def test_sharded_sampler_two_gpus_nccl():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    for r in (0, 1):
+        f, g = res[r]["bisect"]["fused"], res[r]["bisect"]["nccl"]
+        assert len(f[0]) == len(g[0])
+        assert abs(f[0][1] - g[0][1]) < 1e-11                 # first step: identical particles, same root
+        np.testing.assert_allclose(f[0], g[0], rtol=1e-3)
+        assert abs(f[1] - g[1]) < 0.05
+    np.testing.assert_array_equal(res[0]["bisect"]["fused"][0], res[1]["bisect"]["fused"][0])
     for name in ("stratified", "standard", "systematic"):
         a, b = res[0][name], res[1][name]
         assert a[0] == b[0] and a[3] == b[3]                  # identical scalars on every rank
