@@ -228,6 +228,19 @@ int smcb_resample_uniforms(int32_t kind, int64_t n_global, int64_t first, int64_
  * into its own CDF segment and few rows cross NVLink.  prefix: device int64[world+1]. */
 int smcb_resample_uniforms_sharded(int32_t world, const int64_t* prefix, int64_t first, int64_t count,
                                    uint64_t seed, uint64_t stream_id, double* u_out, void* stream);
+/* `standard` uniforms (resampler_rngs.py:4-5) in SORTED order by exponential spacings, for sharded
+ * particles: U_(k) = S_k / S_(N+1), S = running sum of i.i.d. unit exponentials.
+ *   1. smcb_resample_exponentials: e_out[i] = E / (2 N) of global slot first + i (Philox keyed by the
+ *      slot; the scale keeps every running sum below 1 for the fixed-point scan carries);
+ *   2. smcb_cdf_scan over e (local running sums t); the caller sums the rank totals in rank order;
+ *   3. smcb_resample_spacings_finish: u_out[i] = (offset + t[i]) / (total + E_(N+1)), offset = sum of
+ *      the lower ranks' totals, total = sum of all ranks' totals (device scalars).
+ * Same distribution as sorting N i.i.d. uniforms; no sort, and routing becomes a contiguous split. */
+int smcb_resample_exponentials(int64_t first, int64_t count, int64_t n_global, uint64_t seed,
+                               uint64_t stream_id, double* e_out, void* stream);
+int smcb_resample_spacings_finish(const double* t, int64_t n, const double* offset, const double* total,
+                                  int64_t n_global, uint64_t seed, uint64_t stream_id, double* u_out,
+                                  void* stream);
 /* inclusive prefix sum of normalised weights -> CDF (np.cumsum, updater.py:152) */
 int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mode, void* ws, void* stream);
 /* idx_k = #{j : cdf_j <= u_k}  (np.digitize / searchsorted side='right', updater.py:152),

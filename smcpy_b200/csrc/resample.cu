@@ -58,6 +58,36 @@ __global__ void resample_uniforms_sharded_kernel(int world, const int64_t* __res
     }
 }
 
+// ---- sorted multinomial uniforms by exponential spacings ------------------------------------------
+// N i.i.d. uniforms in sorted order are U_(k) = S_k / S_(N+1), S_k = E_1 + ... + E_k with i.i.d.
+// unit exponentials: draw E per global slot (Philox keyed by the slot id: independent of the GPU
+// count), prefix-scan them like the weights (local look-back scan + rank offsets), divide.  The
+// slots come out sorted, so a sharded resampler needs no sort and its routing is a contiguous split.
+// The exponentials are scaled by 1 / (2 N) so that every running sum stays below 1 (the look-back
+// scan carries tile sums in 2^-61 fixed point); the ratio in the last step does not see the scale.
+__global__ void resample_exponentials_kernel(int64_t first, int64_t count, int64_t n_global, uint64_t seed,
+                                             uint32_t stream_id, double* e) {
+    const Philox rng(seed);
+    const double scale = 0.5 / (double)n_global;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const uint4 r = rng((uint64_t)(first + i), 0xE590u, stream_id);
+        e[i] = -log1p(-u01_53(r.x, r.y)) * scale;         // u in [0, 1): E in [0, 36.8]
+    }
+}
+__global__ void resample_spacings_finish_kernel(const double* __restrict__ t, int64_t n, const double* offset,
+                                                const double* total, int64_t n_global, uint64_t seed,
+                                                uint32_t stream_id, double* __restrict__ u) {
+    const Philox rng(seed);
+    const uint4 r = rng((uint64_t)n_global, 0xE590u, stream_id);      // E_(N+1): same value in every thread / rank
+    const double s_all = *total + -log1p(-u01_53(r.x, r.y)) * (0.5 / (double)n_global);
+    const double off = *offset;
+    const double below_one = 1.0 - 0x1p-53;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        u[i] = fmin((off + t[i]) / s_all, below_one);
+}
+
 // ---- sequential scan: bit-equal to np.cumsum ----------------------------------------------------
 constexpr int kSeqChunk = 2048;
 __global__ void __launch_bounds__(256) scan_sequential_kernel(const double* __restrict__ w,
@@ -351,6 +381,23 @@ extern "C" int smcb_resample_uniforms_sharded(int32_t world, const int64_t* pref
     resample_uniforms_sharded_kernel<<<grid_for(count, 256, 4, 8), 256, 0, as_stream(stream)>>>(
         world, prefix, first, count, seed, (uint32_t)stream_id, u_out);
     return check_launch("resample_uniforms_sharded_kernel");
+}
+
+extern "C" int smcb_resample_exponentials(int64_t first, int64_t count, int64_t n_global, uint64_t seed,
+                                          uint64_t stream_id, double* e_out, void* stream) {
+    SMCB_REQUIRE(first >= 0 && count > 0 && n_global >= first + count && e_out, "bad argument");
+    resample_exponentials_kernel<<<grid_for(count, 256, 4, 8), 256, 0, as_stream(stream)>>>(
+        first, count, n_global, seed, (uint32_t)stream_id, e_out);
+    return check_launch("resample_exponentials_kernel");
+}
+
+extern "C" int smcb_resample_spacings_finish(const double* t, int64_t n, const double* offset, const double* total,
+                                             int64_t n_global, uint64_t seed, uint64_t stream_id, double* u_out,
+                                             void* stream) {
+    SMCB_REQUIRE(t && n > 0 && offset && total && n_global >= n && u_out, "bad argument");
+    resample_spacings_finish_kernel<<<grid_for(n, 256, 4, 8), 256, 0, as_stream(stream)>>>(
+        t, n, offset, total, n_global, seed, (uint32_t)stream_id, u_out);
+    return check_launch("resample_spacings_finish_kernel");
 }
 
 extern "C" int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mode, void* ws, void* stream) {

@@ -615,8 +615,15 @@ def _resample_local(st, kernel, resample_rng, warn_threshold, n, host_rng, kind)
         idx = idx_sel
     else:
         rng = kernel.rng
-        call("smcb_resample_uniforms", int(kind), st.n_global, 0, n, rng.seed, rng.next_stream(), ptr(st.u),
-             stream_ptr())
+        if kind == _lib.RESAMPLE_STANDARD and os.environ.get("SMCB_SORTED_STANDARD", "1") != "0":
+            # multinomial uniforms generated in sorted order (exponential spacings): the ancestor
+            # indices come out non-decreasing, so the CDF search and the row gather walk memory
+            # front to back instead of at random
+            from .sharded import sorted_uniforms
+            sorted_uniforms(st, rng.seed, rng.next_stream())
+        else:
+            call("smcb_resample_uniforms", int(kind), st.n_global, 0, n, rng.seed, rng.next_stream(), ptr(st.u),
+                 stream_ptr())
         idx = resample_indices(st, st.u, _lib.SCAN_LOOKBACK)
         n_unique = count_unique(st, idx)
     gather_particles(st, idx)

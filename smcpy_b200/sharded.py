@@ -27,6 +27,22 @@ from . import _lib, engine
 from ._lib import call, ptr, stream_ptr
 
 
+class _Phases:
+    """Sub-phase CUDA-event timers (engine.PROFILE set: tools/c5_run.py); free otherwise."""
+
+    def __init__(self):
+        self.cur = None
+
+    def __call__(self, name):
+        if engine.PROFILE is None:
+            return
+        if self.cur is not None:
+            self.cur.__exit__()
+        self.cur = engine._timed(name) if name else None
+        if self.cur is not None:
+            self.cur.__enter__()
+
+
 def segment_offsets(totals):
     """O_0 = 0, O_r = W_0 + ... + W_{r-1} summed in rank order (identical on every rank)."""
     off = torch.zeros(totals.shape[0] + 1, dtype=torch.float64, device=totals.device)
@@ -39,11 +55,35 @@ def route_counts(dest, world):
     return torch.bincount(dest, minlength=world)[:world]
 
 
+def route_counts_sorted(u, bounds):
+    """The same counts for SORTED uniforms without touching every slot: destinations are
+    non-decreasing, so the counts are the differences of the positions of the segment boundaries
+    inside u (slot goes to rank r iff bounds[r-1] <= u < bounds[r])."""
+    cum = torch.searchsorted(u, bounds, right=False)
+    return torch.diff(cum, prepend=torch.zeros(1, dtype=cum.dtype, device=u.device))
+
+
 def exchange_counts(send_counts):
     """all-to-all of the per-destination counts -> per-source counts (works on any backend)."""
     recv = torch.empty_like(send_counts)
     dist.all_to_all_single(recv, send_counts)
     return recv
+
+
+def sorted_uniforms(st, seed, stream_id):
+    """st.u <- this shard's block of the sorted `standard` uniforms (smcb_resample_exponentials ->
+    smcb_cdf_scan -> rank offsets -> smcb_resample_spacings_finish); st.w_alt is scratch."""
+    rank, world = engine.dist_info()
+    s = stream_ptr()
+    n = st.n
+    t = st.w_alt
+    call("smcb_resample_exponentials", st.id_offset, n, st.n_global, seed, stream_id, ptr(st.u), s)
+    call("smcb_cdf_scan", ptr(st.u), ptr(t), n, _lib.SCAN_LOOKBACK, ptr(st.ws), s)
+    totals = engine._all_gather_rows(t[n - 1:n]).reshape(-1) if world > 1 else t[n - 1:n]
+    off = segment_offsets(totals)
+    call("smcb_resample_spacings_finish", ptr(t), n, ptr(off[rank:rank + 1]), ptr(off[world:world + 1]), st.n_global,
+         seed, stream_id, ptr(st.u), s)
+    return st.u
 
 
 def resample_sharded(st, kernel, resample_rng, warn_threshold):
@@ -57,35 +97,35 @@ def resample_sharded(st, kernel, resample_rng, warn_threshold):
     ncol = int(st.cols.shape[0])            # d + 2 (+1 with a proposal log-pdf column)
     s = stream_ptr()
     dv = st.cols.device
+    ph = _Phases()
     # 1-2: local CDF and segment offsets
+    ph("rs_scan")
     call("smcb_cdf_scan", ptr(st.w), ptr(st.cdf), n, _lib.SCAN_LOOKBACK, ptr(st.ws), s)
     totals = engine._all_gather_rows(st.cdf[n - 1:n]).reshape(-1)
     off = segment_offsets(totals)
     # 3: uniforms of my output slots, routed to the owning rank
+    ph("rs_uniforms")
     stream_id = rng.next_stream()
     if kind == _lib.RESAMPLE_STANDARD:
-        # multinomial: shared interval counts ~ Multinomial(N; 1/G) (same generator on every rank),
-        # then this rank's block of the order statistics; sorted so that routing is a contiguous split
-        host = np.random.default_rng([rng.seed & 0xFFFFFFFF, rng.seed >> 32, stream_id])
-        prefix = np.concatenate([[0], np.cumsum(host.multinomial(st.n_global, [1.0 / world] * world))])
-        pre_dev = engine.dev(prefix, torch.int64)
-        call("smcb_resample_uniforms_sharded", world, ptr(pre_dev), st.id_offset, n, rng.seed, stream_id,
-             ptr(st.u), s)
-        u = torch.sort(st.u).values
+        # multinomial: the N i.i.d. uniforms in sorted order by exponential spacings (no sort; slot
+        # order is immaterial, particles are exchangeable) -- running sums of per-slot exponentials,
+        # scanned like the weights, divided by the grand total
+        u = sorted_uniforms(st, rng.seed, stream_id)
     else:
         call("smcb_resample_uniforms", int(kind), st.n_global, st.id_offset, n, rng.seed, stream_id, ptr(st.u), s)
         u = st.u
+    ph("rs_route")
     bounds = torch.cat([off[1:world], torch.full((1,), float("inf"), dtype=torch.float64, device=dv)])
-    dest = torch.empty(n, dtype=torch.int64, device=dv)
-    call("smcb_searchsorted", ptr(bounds), world, ptr(u), n, ptr(dest), s)
-    send_counts = route_counts(dest, world)
+    send_counts = route_counts_sorted(u, bounds)
     counts = torch.empty((world, world), dtype=torch.int64, device=dv)      # counts[q][r]: requests q -> r
     dist.all_gather_into_tensor(counts, send_counts.contiguous())
     cm = counts.cpu().numpy()                                               # host sync: split sizes
     sc, rc = cm[rank, :].tolist(), cm[:, rank].tolist()
     n_req = int(sum(rc))
+    ph("rs_xchg_u")
     u_in = torch.empty(max(n_req, 1), dtype=torch.float64, device=dv)
     dist.all_to_all_single(u_in[:n_req], u.contiguous(), output_split_sizes=rc, input_split_sizes=sc)
+    ph("rs_search")
     n_unique = torch.zeros(1, dtype=torch.int64, device=dv)
     idx = None
     if n_req > 0:
@@ -93,6 +133,7 @@ def resample_sharded(st, kernel, resample_rng, warn_threshold):
         call("smcb_searchsorted_offset", ptr(st.cdf), n, ptr(off[rank:rank + 1]), ptr(u_in), n_req, ptr(idx), s)
         call("smcb_count_unique", ptr(idx), n_req, n, ptr(st.counts), ptr(st.ws), s)
         n_unique = st.counts[0:1].clone()
+    ph("rs_gather")
     if st.peer_cols_alt is not None:
         # 4-5 fused: the owner writes every requested row straight into the requester's SoA
         # buffer over NVLink peer memory (no staging transposes, no NCCL payload exchange)
@@ -131,8 +172,10 @@ def resample_sharded(st, kernel, resample_rng, warn_threshold):
         dist.all_to_all_single(rows_in, rows_out[:n_req], output_split_sizes=sc, input_split_sizes=rc)
         call("smcb_aos_to_soa", ptr(rows_in), ptr(st.cols_alt), n, ncol, n, s)
         st.swap_cols()
+    ph("rs_tail")
     st.set_uniform_weights()
     engine._all_reduce_sum(n_unique)
     if int(n_unique.item()) <= max(1, warn_threshold * st.n_global):
         warnings.warn(f"Resampled to less than {warn_threshold * 100}% of particles; ", UserWarning)
+    ph(None)
     return None

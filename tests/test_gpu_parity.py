@@ -644,6 +644,44 @@ def test_streaming_exp_accuracy(sb):
     assert np.all(got[x == 0.0] == 1.0)
 
 
+def test_sorted_standard_uniforms_by_exponential_spacings(sb):
+    """smcb_resample_exponentials -> smcb_cdf_scan -> smcb_resample_spacings_finish: sorted, uniform
+    on [0, 1), spacings exponential, and a two-shard evaluation equals the one-shard one."""
+    import torch
+    from scipy import stats
+    from smcpy_b200 import _lib, engine
+    n = 1 << 20
+    rt = engine.Runtime.get()
+    ws = rt.workspace(n, 2)
+    s = _lib.stream_ptr()
+
+    def block(first, count):
+        e = torch.empty(count, dtype=torch.float64, device="cuda")
+        t = torch.empty_like(e)
+        _lib.call("smcb_resample_exponentials", first, count, n, 99, 5, _lib.ptr(e), s)
+        _lib.call("smcb_cdf_scan", _lib.ptr(e), _lib.ptr(t), count, _lib.SCAN_LOOKBACK, _lib.ptr(ws), s)
+        return t
+
+    def finish(t, off, tot):
+        u = torch.empty_like(t)
+        o = torch.tensor([off, tot], dtype=torch.float64, device="cuda")
+        _lib.call("smcb_resample_spacings_finish", _lib.ptr(t), t.shape[0], _lib.ptr(o[0:1]), _lib.ptr(o[1:2]), n, 99, 5,
+                  _lib.ptr(u), s)
+        return u.cpu().numpy()
+    t = block(0, n)
+    u = finish(t, 0.0, float(t[-1]))
+    assert np.all(np.diff(u) >= 0) and u[0] >= 0.0 and u[-1] < 1.0
+    assert stats.kstest(u, "uniform").pvalue > 1e-3
+    gaps = np.diff(u) * n
+    assert stats.kstest(gaps[::7], "expon").pvalue > 1e-3
+    assert abs(np.corrcoef(gaps[:-1], gaps[1:])[0, 1]) < 0.01
+    h = n // 2 + 12345
+    t0, t1 = block(0, h), block(h, n - h)
+    a, b = float(t0[-1]), float(t1[-1])
+    u2 = np.concatenate([finish(t0, 0.0, a + b), finish(t1, a, a + b)])
+    np.testing.assert_allclose(u2, u, rtol=1e-12, atol=1e-15)
+
+
 def test_wide_identity_kernel_tma_path_vs_oracle(sb):
     """2^18 particles x d=32 takes the persistent, TMA-staged (cp.async.bulk + mbarrier) variant
     of the fused Metropolis kernel; replayed draws against the oracle, 1e-10."""

@@ -51,6 +51,7 @@ def _gloo_worker(rank, world, port, out):
     bounds = torch.cat([off[1:world], torch.tensor([float("inf")], dtype=torch.float64)])
     dest = torch.searchsorted(bounds, u, right=True)
     send = sharded.route_counts(dest, world)
+    assert torch.equal(send, sharded.route_counts_sorted(u, bounds))
     recv = sharded.exchange_counts(send)
     assert int(send.sum()) == n
     u_in = torch.empty(int(recv.sum()), dtype=torch.float64)
