@@ -18,6 +18,8 @@ elif cfg == "c3":
     problem = configs.spring_problem(500, 4); n = 1 << 20; K = 3
 elif cfg == "c4":
     problem = configs.mvn_problem(50); n = 1 << 22
+if len(sys.argv) > 2:
+    n = 1 << int(sys.argv[2])
 mcmc, kernel = make_b200(problem, rng=3)
 if cfg == "c4":
     init = configs.mvn_init_params(4096, 1)
