@@ -56,7 +56,8 @@ enum {
     SMCB_FLAG_PRIOR_OOB = 1,   /* incoming particle has zero prior (vector_mcmc.py:199-203) */
     SMCB_FLAG_MODEL_NAN = 2,   /* NaN in model output (log_likelihoods.py:14-15) */
     SMCB_FLAG_COV_NOT_PD = 4,  /* MVNormal covariance not PD where the likelihood needed it */
-    SMCB_FLAG_CHOL_FAIL = 8    /* proposal covariance not PD (vector_mcmc.py:224-236) */
+    SMCB_FLAG_CHOL_FAIL = 8,   /* proposal covariance not PD (vector_mcmc.py:224-236) */
+    SMCB_FLAG_COV_RESHIFT = 16 /* one-pass covariance: the shift was too far from the mean, redo in two passes */
 };
 /* resampling uniforms (smcpy/resampler_rngs.py:4-9; systematic is an extension) */
 enum { SMCB_RESAMPLE_STANDARD = 0, SMCB_RESAMPLE_STRATIFIED = 1, SMCB_RESAMPLE_SYSTEMATIC = 2 };
@@ -279,6 +280,17 @@ int smcb_weighted_sums2(const double* params, int64_t stride, const double* w, i
                         const double* mean, double* sums_out /*d*d*/, void* ws, void* stream);
 int smcb_cov_from_sums(const double* wsum /*1*/, const double* sums2 /*d*d*/, int32_t d,
                        double* cov_out, void* stream);
+/* the same covariance (particles.py:189-198) in ONE pass over the particles, for d > 8: moments about
+ * a shift c close to the mean (the previous step's mean).  sums_out = [W, S1 (d), S2 (d x d)] with
+ * S1 = sum w (x - c), S2 = sum w (x - c)(x - c)^T (all-reduce them across ranks), then
+ * smcb_cov_from_shifted_sums: mean = c + S1 / W, cov = S2 / W - (S1 / W)(S1 / W)^T, c <- mean; sets
+ * SMCB_FLAG_COV_RESHIFT when |mean - c|^2 > 1e4 var for some parameter (cancellation: the caller then
+ * recomputes with the two-pass entry points).  Returns SMCB_ERR_UNSUPPORTED for d <= 8, unaligned
+ * columns or fewer than 148 x 128 particles. */
+int smcb_weighted_moments_shifted(const double* params, int64_t stride, const double* w, int64_t n,
+                                  int32_t d, const double* shift, double* sums_out, void* ws, void* stream);
+int smcb_cov_from_shifted_sums(const double* sums, double* shift, int32_t d, double* mean_out,
+                               double* cov_out, int32_t* flags, void* stream);
 /* lower Cholesky factor (np.linalg.cholesky, vector_mcmc.py:225); sets SMCB_FLAG_CHOL_FAIL */
 int smcb_cholesky(const double* cov, int32_t d, double* chol_out, int32_t* flags, void* stream);
 

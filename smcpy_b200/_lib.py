@@ -22,7 +22,7 @@ MODEL_LINEAR, MODEL_SPRING_MASS, MODEL_IDENTITY = 1, 2, 3
 LL_NORMAL, LL_MVNORMAL, LL_MULTISOURCE = 1, 2, 3
 MAX_SEGMENTS = 8
 PRIOR_UNIFORM, PRIOR_IMPROPER_UNIFORM, PRIOR_IMPROPER_COV = 1, 2, 3
-FLAG_PRIOR_OOB, FLAG_MODEL_NAN, FLAG_COV_NOT_PD, FLAG_CHOL_FAIL = 1, 2, 4, 8
+FLAG_PRIOR_OOB, FLAG_MODEL_NAN, FLAG_COV_NOT_PD, FLAG_CHOL_FAIL, FLAG_COV_RESHIFT = 1, 2, 4, 8, 16
 RESAMPLE_STANDARD, RESAMPLE_STRATIFIED, RESAMPLE_SYSTEMATIC = 0, 1, 2
 SCAN_SEQUENTIAL, SCAN_LOOKBACK = 0, 1
 
@@ -107,6 +107,8 @@ SIGNATURES = {
     "smcb_mean_from_sums": [_P, _I32, _P, _P],
     "smcb_weighted_sums2": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P],
     "smcb_cov_from_sums": [_P, _P, _I32, _P, _P],
+    "smcb_weighted_moments_shifted": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P],
+    "smcb_cov_from_shifted_sums": [_P, _P, _I32, _P, _P, _P, _P],
     "smcb_cholesky": [_P, _I32, _P, _P, _P],
     "smcb_mh_init": [_PP(Problem), _P, _I64, _I64, _P, _P, _P, _P, _P, _P],
     "smcb_log_priors": [_PP(Problem), _P, _I64, _I64, _P, _P, _P],
@@ -166,7 +168,7 @@ class _LazyLib:
 lib = _LazyLib()
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
 LAUNCHES = {"smcb_reweight": 2, "smcb_cdf_scan": 2, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
-            "smcb_weighted_sums1": 2, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0,
+            "smcb_weighted_sums1": 2, "smcb_weighted_moments_shifted": 3, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0,
             "smcb_ess_bisect_xchg_slot_words": 0}
 launch_count = 0
 

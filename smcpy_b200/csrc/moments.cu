@@ -243,6 +243,157 @@ wsums2_dmma_kernel(const double* __restrict__ params, int64_t pstride, const dou
     }
 }
 
+// ---- one pass for d > 8: shifted first and second moments together ------------------------------------
+// W = sum w, S1 = sum w (x - c), S2 = sum w (x - c)(x - c)^T about a shift c close to the mean (the
+// previous SMC step's mean): mean = c + S1 / W, cov = S2 / W - (S1 / W)(S1 / W)^T.  The cancellation
+// error is eps * |mean - c|^2 / var, i.e. nil when c is within a few standard deviations of the mean;
+// the finalisation flags SMCB_FLAG_COV_RESHIFT otherwise and the caller falls back to the two passes.
+// Halves the HBM traffic of the covariance (one read of the particles instead of two).
+// Tiles go from TMA straight into rows padded to kWLd (conflict-free fragment loads); centring and
+// weighting happen in registers at fragment-load time, so there is no staging pass and the two
+// stages of raw tiles double-buffer the loads against the DMMAs.
+template <int NB8>
+__global__ void __launch_bounds__(kDmmaWarps * 32, 2)
+wmoments_dmma_kernel(const double* __restrict__ params, int64_t pstride, const double* __restrict__ w, int64_t n,
+                     int d, const double* __restrict__ shift, double* partials /* [grid][NBU8*64 + DP + 1] */) {
+    constexpr int NBU8 = NB8 * (NB8 + 1) / 2;
+    constexpr int DP = NB8 * 8;
+    constexpr int kStage = (DP + 1) * kWLd;
+    constexpr int kOut = NBU8 * 64 + DP + 1;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int frow = lane >> 2, fk = lane & 3;   // fragment row / k index of this lane
+
+    double acc[NBU8][2];
+#pragma unroll
+    for (int q = 0; q < NBU8; ++q) acc[q][0] = acc[q][1] = 0.0;
+    double s1[NB8], sh[NB8], sw = 0.0;
+#pragma unroll
+    for (int I = 0; I < NB8; ++I) {
+        s1[I] = 0.0;
+        sh[I] = (I * 8 + frow < d) ? shift[I * 8 + frow] : 0.0;
+    }
+    const int64_t n_tiles = (n + kWP - 1) / kWP;
+    auto issue = [&](int stage, int64_t tile) {  // one elected thread
+        double* raw = smem + stage * kStage;
+        const int64_t base = tile * kWP;
+        const uint32_t cnt = (uint32_t)((n - base < kWP) ? (n - base) : kWP);
+        const uint32_t bytes = cnt * 8u;
+        fence_proxy_async();
+        mbar_expect_tx(&mbar[stage], bytes * (uint32_t)(d + 1));
+#pragma unroll 1
+        for (int c = 0; c < d; ++c) tma_load_1d(raw + c * kWLd, params + (int64_t)c * pstride + base, bytes, &mbar[stage]);
+        tma_load_1d(raw + DP * kWLd, w + base, bytes, &mbar[stage]);
+    };
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if ((int64_t)blockIdx.x < n_tiles) issue(0, blockIdx.x);
+        if ((int64_t)blockIdx.x + gridDim.x < n_tiles) issue(1, (int64_t)blockIdx.x + gridDim.x);
+    }
+    uint32_t phase0 = 0, phase1 = 0;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const double* raw = smem + stage * kStage;
+        const int64_t base = tile * kWP;
+        const int cnt = (int)((n - base < kWP) ? (n - base) : kWP);
+        if (stage == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1u; }
+        else { mbar_wait(&mbar[1], phase1); phase1 ^= 1u; }
+#pragma unroll
+        for (int ks = 0; ks < kWP / 4 / kDmmaWarps; ++ks) {
+            const int p0 = (wid + ks * kDmmaWarps) * 4 + fk;
+            const bool valid = p0 < cnt;
+            const double wv = valid ? raw[DP * kWLd + p0] : 0.0;
+            double fa[NB8], fb[NB8];
+#pragma unroll
+            for (int I = 0; I < NB8; ++I) {
+                const bool on = valid && (I * 8 + frow < d);
+                fb[I] = on ? raw[(I * 8 + frow) * kWLd + p0] - sh[I] : 0.0;
+                fa[I] = __dmul_rn(fb[I], wv);
+                s1[I] += fa[I];
+            }
+            if (frow == 0) sw += wv;
+            int q = 0;
+#pragma unroll
+            for (int I = 0; I < NB8; ++I)
+#pragma unroll
+                for (int J = I; J < NB8; ++J) {
+                    dmma_m8n8k4(acc[q][0], acc[q][1], fa[I], fb[J]);
+                    ++q;
+                }
+        }
+        __syncthreads();                          // every warp is done with this stage
+        if (tid == 0 && tile + 2 * (int64_t)gridDim.x < n_tiles) issue(stage, tile + 2 * (int64_t)gridDim.x);
+    }
+    // lanes -> warp: the four k-lanes of a fragment row hold different particles
+#pragma unroll
+    for (int I = 0; I < NB8; ++I) {
+        s1[I] += __shfl_xor_sync(0xffffffffu, s1[I], 1);
+        s1[I] += __shfl_xor_sync(0xffffffffu, s1[I], 2);
+    }
+    sw += __shfl_xor_sync(0xffffffffu, sw, 1);
+    sw += __shfl_xor_sync(0xffffffffu, sw, 2);
+    // warps -> CTA partial in warp order (deterministic); the stages are free now
+    double* red = smem;                           // [warp][kOut]
+#pragma unroll
+    for (int q = 0; q < NBU8; ++q) {
+        red[wid * kOut + q * 64 + frow * 8 + fk * 2 + 0] = acc[q][0];
+        red[wid * kOut + q * 64 + frow * 8 + fk * 2 + 1] = acc[q][1];
+    }
+    if (fk == 0) {
+#pragma unroll
+        for (int I = 0; I < NB8; ++I) red[wid * kOut + NBU8 * 64 + I * 8 + frow] = s1[I];
+    }
+    if (lane == 0) red[wid * kOut + NBU8 * 64 + DP] = sw;
+    __syncthreads();
+    for (int e = tid; e < kOut; e += blockDim.x) {
+        double sum = 0.0;
+        for (int wq = 0; wq < kDmmaWarps; ++wq) sum += red[wq * kOut + e];
+        partials[(int64_t)blockIdx.x * kOut + e] = sum;
+    }
+}
+
+// packed (S2 blocks, S1[DP], W) -> sums layout [W, S1[d], S2[d x d]]
+__global__ void moments_unpack8_kernel(const double* packed, int d, int nb8, double* sums) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nbu8 = nb8 * (nb8 + 1) / 2;
+    if (e == 0) sums[0] = packed[nbu8 * 64 + nb8 * 8];
+    if (e < d) sums[1 + e] = packed[nbu8 * 64 + e];
+    if (e >= d * d) return;
+    int i = e / d, j = e - i * d;
+    if (i > j) { const int tmp = i; i = j; j = tmp; }
+    const int bi = i >> 3, bj = j >> 3;
+    const int blk = bi * nb8 - bi * (bi - 1) / 2 + (bj - bi);
+    sums[1 + d + e] = packed[blk * 64 + (i & 7) * 8 + (j & 7)];
+}
+
+// mean = c + S1 / W; cov = S2 / W - (S1 / W)(S1 / W)^T; c <- mean for the next call.
+// One block of >= d*d threads... (d <= 32: 1024 threads)
+__global__ void cov_from_shifted_sums_kernel(const double* sums, double* shift, int d, double* mean, double* cov,
+                                             int* flags) {
+    __shared__ double m1[SMCB_MAX_PARAMS];
+    const int e = threadIdx.x;
+    const double fact = 1.0 / sums[0];
+    if (e < d) m1[e] = __dmul_rn(sums[1 + e], fact);
+    __syncthreads();
+    if (e < d * d) {
+        const int i = e / d, j = e - i * d;
+        const double c = __dmul_rn(sums[1 + d + e], fact) - m1[i] * m1[j];
+        cov[e] = c;
+        if (i == j && !(m1[i] * m1[i] <= 1e4 * c)) atomicOr(flags, SMCB_FLAG_COV_RESHIFT);
+    }
+    if (e < d) {
+        const double mu = shift[e] + m1[e];
+        mean[e] = mu;
+        shift[e] = mu;
+    }
+}
+
 // expand the 8x8-block-packed upper triangle to a full symmetric d x d matrix
 __global__ void sums2_unpack8_kernel(const double* packed, int d, int nb8, double* full) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,6 +575,50 @@ extern "C" int smcb_weighted_sums2(const double* params, int64_t stride, const d
     reduce_partials_kernel<<<(nbu * 16 + 3) / 4, 128, 0, s>>>(partials, grid, nbu * 16, packed);
     sums2_unpack_kernel<<<(d * d + 63) / 64, 64, 0, s>>>(packed, d, sums_out);
     return check_launch("wsums2_kernel");
+}
+
+extern "C" int smcb_weighted_moments_shifted(const double* params, int64_t stride, const double* w, int64_t n,
+                                             int32_t d, const double* shift, double* sums_out, void* ws,
+                                             void* stream) {
+    SMCB_REQUIRE(params && w && shift && sums_out && ws && n > 0 && d > 0 && d <= SMCB_MAX_PARAMS, "bad argument");
+    const bool aligned = ((((uintptr_t)params | (uintptr_t)w) & 15) == 0) && (stride % 2 == 0) && (n % 2 == 0);
+    if (!(d > 8 && aligned && n >= (int64_t)kNumSMs * kWP)) {
+        set_error("smcb_weighted_moments_shifted: needs d > 8, 16-byte aligned even-length columns and n >= %d",
+                  kNumSMs * kWP);
+        return SMCB_ERR_UNSUPPORTED;
+    }
+    const int nb8 = (d + 7) / 8, nbu8 = nb8 * (nb8 + 1) / 2, dp = nb8 * 8;
+    const int k_out = nbu8 * 64 + dp + 1;
+    size_t smem_w = (size_t)2 * (dp + 1) * kWLd * sizeof(double);
+    const size_t red = (size_t)kDmmaWarps * k_out * sizeof(double);
+    if (red > smem_w) smem_w = red;
+    const int grid = kNumSMs * 2;
+    double* partials = (double*)((char*)ws + kWsPartials);
+    cudaStream_t s = as_stream(stream);
+    if (nb8 == 2) {
+        static bool at = false;
+        if (!at) { cudaFuncSetAttribute(wmoments_dmma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); at = true; }
+        wmoments_dmma_kernel<2><<<grid, kDmmaWarps * 32, smem_w, s>>>(params, stride, w, n, d, shift, partials);
+    } else if (nb8 == 3) {
+        static bool at = false;
+        if (!at) { cudaFuncSetAttribute(wmoments_dmma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); at = true; }
+        wmoments_dmma_kernel<3><<<grid, kDmmaWarps * 32, smem_w, s>>>(params, stride, w, n, d, shift, partials);
+    } else {
+        static bool at = false;
+        if (!at) { cudaFuncSetAttribute(wmoments_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); at = true; }
+        wmoments_dmma_kernel<4><<<grid, kDmmaWarps * 32, smem_w, s>>>(params, stride, w, n, d, shift, partials);
+    }
+    double* packed = partials + (int64_t)grid * k_out;
+    reduce_partials_kernel<<<(k_out + 3) / 4, 128, 0, s>>>(partials, grid, k_out, packed);
+    moments_unpack8_kernel<<<(d * d + 63) / 64, 64, 0, s>>>(packed, d, nb8, sums_out);
+    return check_launch("wmoments_dmma_kernel");
+}
+
+extern "C" int smcb_cov_from_shifted_sums(const double* sums, double* shift, int32_t d, double* mean_out,
+                                          double* cov_out, int32_t* flags, void* stream) {
+    SMCB_REQUIRE(sums && shift && mean_out && cov_out && flags && d > 0 && d <= SMCB_MAX_PARAMS, "bad argument");
+    cov_from_shifted_sums_kernel<<<1, 1024, 0, as_stream(stream)>>>(sums, shift, d, mean_out, cov_out, flags);
+    return check_launch("cov_from_shifted_sums_kernel");
 }
 
 extern "C" int smcb_cov_from_sums(const double* wsum, const double* sums2, int32_t d, double* cov_out,

@@ -390,6 +390,7 @@ class DeviceState:
         self.ws = rt.workspace(self.n, d)
         self.uniform_weights = False
         self.total_unnorm_log_weight = None
+        self.shift = None                       # previous mean: shift of the one-pass covariance (d > 8)
 
     @property
     def params(self):
@@ -646,26 +647,47 @@ def _host_chol_psd(cov):
     return np.linalg.cholesky(cov)
 
 
-def covariance(st):
+def covariance(st, two_pass=False):
     """Particles.compute_covariance (particles.py:189-198) + its Cholesky factor; leaves
-    st.cov / st.chol on the device and returns the host copy of cov."""
+    st.cov / st.chol on the device and returns the device covariance.  For d > 8 and a state that
+    already has a mean (every SMC step after the first) the moments are taken in one pass about
+    the previous mean (smcb_weighted_moments_shifted); cholesky() falls back to the two passes
+    if the kernel reports that the shift was too far off."""
     _, world = dist_info()
     s = stream_ptr()
     d = st.d
+    st._cov_one_pass = False
+    if (not two_pass and d > 8 and st.n >= 148 * 128 and getattr(st, "shift", None) is not None
+            and not os.environ.get("SMCB_COV_TWO_PASS")):
+        try:
+            with _timed("cov"):
+                call("smcb_weighted_moments_shifted", ptr(st.params), st.col_stride if hasattr(st, "col_stride") else st.n,
+                     ptr(st.w), st.n, d, ptr(st.shift), ptr(st.sums), ptr(st.ws), s)
+                if world > 1:
+                    _all_reduce_sum(st.sums)
+                call("smcb_cov_from_shifted_sums", ptr(st.sums), ptr(st.shift), d, ptr(st.mean), ptr(st.cov),
+                     ptr(st.flags), s)
+            st._cov_one_pass = True
+            return st.cov
+        except NotImplementedError:
+            pass
+    stride = st.col_stride if hasattr(st, "col_stride") else st.n
     if world == 1:
         with _timed("cov"):
-            call("smcb_weighted_cov", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.mean), ptr(st.cov),
+            call("smcb_weighted_cov", ptr(st.params), stride, ptr(st.w), st.n, d, ptr(st.mean), ptr(st.cov),
                  ptr(st.sums), ptr(st.ws), s)
     else:
         with _timed("cov"):
-            call("smcb_weighted_sums1", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.sums), ptr(st.ws), s)
+            call("smcb_weighted_sums1", ptr(st.params), stride, ptr(st.w), st.n, d, ptr(st.sums), ptr(st.ws), s)
             _all_reduce_sum(st.sums[:1 + d])
             call("smcb_mean_from_sums", ptr(st.sums), d, ptr(st.mean), s)
             s2 = st.sums[1 + d:]
-            call("smcb_weighted_sums2", ptr(st.params), st.n, ptr(st.w), st.n, d, ptr(st.mean), ptr(s2),
+            call("smcb_weighted_sums2", ptr(st.params), stride, ptr(st.w), st.n, d, ptr(st.mean), ptr(s2),
                  ptr(st.ws), s)
             _all_reduce_sum(s2)
             call("smcb_cov_from_sums", ptr(st.sums), ptr(s2), d, ptr(st.cov), s)
+    if hasattr(st, "flags") and d > 8:
+        st.shift = st.mean.clone()           # the next call can take the one-pass route
     return st.cov
 
 
@@ -673,8 +695,15 @@ def cholesky(st, cov_dev=None):
     call("smcb_cholesky", ptr(st.cov if cov_dev is None else cov_dev), st.d, ptr(st.chol), ptr(st.flags),
          stream_ptr())
     f = int(st.flags[0].item())
+    if f & _lib.FLAG_COV_RESHIFT:
+        # one-pass covariance taken about a shift too far from the mean: redo it in two passes
+        st.flags[0] = f & ~(_lib.FLAG_COV_RESHIFT | _lib.FLAG_CHOL_FAIL)
+        if cov_dev is None and getattr(st, "_cov_one_pass", False):
+            covariance(st, two_pass=True)
+            return cholesky(st)
+        f &= ~_lib.FLAG_COV_RESHIFT
     if f & _lib.FLAG_CHOL_FAIL:
-        st.flags[0] = 0
+        st.flags[0] = f & ~_lib.FLAG_CHOL_FAIL
         cov = (st.cov if cov_dev is None else cov_dev).cpu().numpy()
         st.chol.copy_(dev(_host_chol_psd(cov)))
     return st.chol

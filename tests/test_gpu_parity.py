@@ -682,6 +682,41 @@ def test_sorted_standard_uniforms_by_exponential_spacings(sb):
     np.testing.assert_allclose(u2, u, rtol=1e-12, atol=1e-15)
 
 
+def test_one_pass_shifted_covariance_matches_two_pass_and_numpy(sb):
+    """d = 32: moments about the previous mean in one pass (smcb_weighted_moments_shifted) agree
+    with np.cov and the two-pass kernels; a shift far from the mean is flagged and recomputed."""
+    import torch
+    from smcpy_b200 import _lib, engine
+    n, d = 1 << 16, 32
+    rng = np.random.default_rng(4)
+    a = rng.normal(0, 1, (d, d)) * 0.3
+    x = rng.normal(0, 1, (n, d)) @ a + rng.uniform(-3, 3, d)
+    w = rng.exponential(1.0, n)
+    w /= w.sum()
+    st = engine.DeviceState(n, n, d)
+    st.set_params_host(x)
+    st.w.copy_(engine.dev(w))
+    want = np.cov(x.T, ddof=0, aweights=w)
+    c2 = engine.covariance(st).cpu().numpy().reshape(d, d)            # first call: two passes, sets the shift
+    assert not st._cov_one_pass and st.shift is not None
+    np.testing.assert_allclose(c2, want, rtol=1e-10, atol=1e-14)
+    st.set_params_host(x + 0.05)                                      # the mean moves a little, like one SMC step
+    c1 = engine.covariance(st).cpu().numpy().reshape(d, d)
+    assert st._cov_one_pass
+    engine.cholesky(st)
+    assert int(st.flags[0].item()) == 0
+    np.testing.assert_allclose(c1, want, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(st.mean.cpu().numpy(), np.average(x + 0.05, axis=0, weights=w), rtol=1e-12)
+    np.testing.assert_allclose(st.chol.cpu().numpy().reshape(d, d), np.linalg.cholesky(want), rtol=1e-8, atol=1e-12)
+    # shift 1e4 standard deviations away: flagged, cholesky() recomputes in two passes
+    st.shift.add_(1e4)
+    engine.covariance(st)
+    assert st._cov_one_pass
+    engine.cholesky(st)
+    assert not st._cov_one_pass and int(st.flags[0].item()) == 0
+    np.testing.assert_allclose(st.cov.cpu().numpy().reshape(d, d), want, rtol=1e-10, atol=1e-14)
+
+
 def test_wide_identity_kernel_tma_path_vs_oracle(sb):
     """2^18 particles x d=32 takes the persistent, TMA-staged (cp.async.bulk + mbarrier) variant
     of the fused Metropolis kernel; replayed draws against the oracle, 1e-10."""
