@@ -274,6 +274,23 @@ __device__ __forceinline__ uint4 philox_k(const PhiloxKeys& rk, uint64_t id, uin
     }
     return make_uint4(c0, c1, c2, c3);
 }
+// The same generator with the key schedule computed in registers (two adds per round): for the
+// out-of-line RNG blocks of the wide kernels, where a pointer to the precomputed keys would turn
+// every key into a generic load from the parameter space (ncu: 20 LD.E per call).
+__device__ __forceinline__ uint4 philox_s(uint32_t k0, uint32_t k1, uint64_t id, uint32_t call, uint32_t stream) {
+    uint32_t c0 = (uint32_t)id, c1 = (uint32_t)(id >> 32), c2 = call, c3 = stream;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ (k0 + (uint32_t)r * 0x9E3779B9u), n2 = hi0 ^ c3 ^ (k1 + (uint32_t)r * 0xBB67AE85u);
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
 // 53-bit uniform in [0,1) from two 32-bit words (same construction as numpy's next_double)
 __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
     const uint64_t x = ((uint64_t)hi << 32) | lo;
@@ -311,6 +328,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;

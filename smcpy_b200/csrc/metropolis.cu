@@ -111,16 +111,16 @@ __device__ __forceinline__ double cov_scale_sqrt_xchg(const smcb_xchg_t& x, int 
 }
 
 // ---- priors -----------------------------------------------------------------------------------
-__device__ __noinline__ double gen_uniform53(const PhiloxKeys* rk, uint64_t pid, uint32_t call, uint32_t stream) {
-    const uint4 r = philox_k(*rk, pid, call, stream);
+__device__ __noinline__ double gen_uniform53(uint32_t k0, uint32_t k1, uint64_t pid, uint32_t call, uint32_t stream) {
+    const uint4 r = philox_s(k0, k1, pid, call, stream);
     return u01_53(r.x, r.y);
 }
 
 // Four standard normals (fp32) from one Philox call.  Deliberately NOT inlined: the wide
 // kernels call it DMAX/4 times per particle and eight inlined copies push the tile body past the
 // 32 KB instruction cache (ncu: 21 % of stall samples were `no_inst`, profiles/r01_mh_kernels.md).
-__device__ __noinline__ float4 gen_normals4(const PhiloxKeys* rk, uint64_t pid, uint32_t call, uint32_t stream) {
-    const uint4 r = philox_k(*rk, pid, call, stream);
+__device__ __noinline__ float4 gen_normals4(uint32_t k0, uint32_t k1, uint64_t pid, uint32_t call, uint32_t stream) {
+    const uint4 r = philox_s(k0, k1, pid, call, stream);
     float4 z;
     normal_pair_f(r.x, r.y, z.x, z.y);
     normal_pair_f(r.z, r.w, z.z, z.w);
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT, TMA))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double sh_scale;
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar, mbar_empty;
     const int d = EXACT ? DMAX : a.prob.n_params;
     // Cholesky factor transposed and zero-padded to DMAX: sLt[j * DMAX + r] = L[r][j], so column j
     // is contiguous (LDS.128) and the unrolled update needs no bounds checks
@@ -496,8 +496,22 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         for (int e = threadIdx.x; e < DMAX * DMAX; e += TPB) {
             const int j = e / DMAX, r = e - j * DMAX;
             const double v = (r < d && j <= r) ? a.chol[r * d + j] : 0.0;
-            if (TMA) reinterpret_cast<float*>(sLt)[e] = (float)v;      // TMA variant: fp32 increment path
-            else sLt[e] = v;
+            if (!TMA) sLt[e] = v;
+        }
+        if (TMA) {
+            // TMA variant: the increment L z goes through the tensor cores (mma.sync m16n8k8, tf32
+            // inputs, fp32 accumulation).  B fragments of the lower-triangular 8x8 blocks of L, in
+            // fragment order: block q = (nb, kb <= nb), lane (g, t) holds L[nb*8+g][kb*8+t], [..][kb*8+t+4]
+            float* sB = reinterpret_cast<float*>(sLt);
+            constexpr int NB = DMAX >= 8 ? DMAX / 8 : 1;
+            for (int e = threadIdx.x; e < NB * (NB + 1) / 2 * 64; e += TPB) {
+                const int q = e >> 6, ln = (e >> 1) & 31, hi = e & 1;
+                int nb = 0, rem = q;
+                while (rem > nb) { rem -= nb + 1; ++nb; }          // q = nb (nb + 1) / 2 + kb
+                const int kb = rem, g = ln >> 2, t = ln & 3;
+                const int r = nb * 8 + g, j = kb * 8 + t + 4 * hi;
+                sB[e] = (r < d && j <= r) ? (float)a.chol[r * d + j] : 0.0f;
+            }
         }
         if (threadIdx.x == 0)
             sh_scale = (a.x.world > 1) ? cov_scale_sqrt_xchg(a.x, a.step, a.n_global)
@@ -526,7 +540,10 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         tma_load_1d(stage + (d + 1) * TPB, a.lp + base, bytes, &mbar);
     };
     if (TMA) {
-        if (threadIdx.x == 0) mbar_init(&mbar, 1);
+        if (threadIdx.x == 0) {
+            mbar_init(&mbar, 1);
+            mbar_init(&mbar_empty, TPB);
+        }
         __syncthreads();
         if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) tma_issue(blockIdx.x);
     }
@@ -546,35 +563,91 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         double lq_old[PPT], lq_new[PPT];
         bool prior_ok[PPT];
         if (TMA) {
-            // native RNG only.  The proposal increment sqrt(s) L z is accumulated in fp32 (z has
-            // fp32 resolution; symmetry z -> -z is exact, which is all the Metropolis ratio needs)
-            // BEFORE the tile is read from the TMA stage, so the stage wait hides behind it.
+            // native RNG only.  The proposal increment sqrt(s) L z is a (particles x d) x (d x d) product:
+            // tensor cores, tf32 inputs (the mma ignores the low mantissa bits: truncation, exactly
+            // odd in z, so the proposal stays symmetric -- all the Metropolis ratio needs), fp32
+            // accumulation.  Done BEFORE the tile is read from the TMA stage, so the stage wait hides
+            // behind it.
             const int64_t i = tile * per_tile + threadIdx.x;
             valid[0] = i < a.n;
             idx[0] = valid[0] ? i : 0;
-            const float* sLf = reinterpret_cast<const float*>(sLt);     // fp32 copy of L^T, padded
+            const float* sB = reinterpret_cast<const float*>(sLt);      // tf32 B fragments of L (see above)
+            constexpr int NB = DMAX >= 8 ? DMAX / 8 : 1;
+            constexpr int kZLd = DMAX + 4;                               // padded row: conflict-free LDS.128 / fragment loads
+            float* zb = reinterpret_cast<float*>(stage + (DMAX + 2) * TPB) + (threadIdx.x >> 5) * 16 * kZLd;
+            const int lane = threadIdx.x & 31, fg = lane >> 2, ft = lane & 3;
             const float scf = (float)sc;
-            float delta[DMAX];
-#pragma unroll
-            for (int c = 0; c < DMAX; ++c) delta[c] = 0.0f;
+            float delta[DMAX];                                           // first sqrt(s) z, then sqrt(s) L z
             const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[0]);
 #pragma unroll
             for (int c = 0; c < DMAX; c += 4) {
-                const float4 zz = gen_normals4(&a.rk, pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
-                const float z4[4] = {zz.x, zz.y, zz.z, zz.w};
+                const float4 zz = gen_normals4(a.rk.k[0], a.rk.k[1], pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
+                delta[c + 0] = scf * zz.x;
+                delta[c + 1] = scf * zz.y;
+                delta[c + 2] = scf * zz.z;
+                delta[c + 3] = scf * zz.w;
+            }
+            // Each warp multiplies its 32 rows of z by L^T as two 16-row M-tiles.  The rows pass
+            // through a 16-row shared buffer per warp to get from one-particle-per-thread into the
+            // mma fragment layout and back: z -> A fragments, D fragments -> increments.
+            float dfr[2][NB][4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int j = c + q;
-                    const float zs = scf * z4[q];
+            for (int mt = 0; mt < 2; ++mt) {
+                if ((lane >> 4) == mt) {
 #pragma unroll
-                    for (int r4 = c; r4 < DMAX; r4 += 4) {                 // rows above the diagonal hold 0
-                        const float4 l4 = *reinterpret_cast<const float4*>(&sLf[j * DMAX + r4]);
-                        delta[r4 + 0] = fmaf(l4.x, zs, delta[r4 + 0]);
-                        delta[r4 + 1] = fmaf(l4.y, zs, delta[r4 + 1]);
-                        delta[r4 + 2] = fmaf(l4.z, zs, delta[r4 + 2]);
-                        delta[r4 + 3] = fmaf(l4.w, zs, delta[r4 + 3]);
+                    for (int c = 0; c < DMAX; c += 4)
+                        *reinterpret_cast<float4*>(&zb[(lane & 15) * kZLd + c]) =
+                            make_float4(delta[c], delta[c + 1], delta[c + 2], delta[c + 3]);
+                }
+                __syncwarp();
+                uint32_t afr[NB][4];
+#pragma unroll
+                for (int kb = 0; kb < NB; ++kb) {
+                    afr[kb][0] = __float_as_uint(zb[fg * kZLd + kb * 8 + ft]);
+                    afr[kb][1] = __float_as_uint(zb[(fg + 8) * kZLd + kb * 8 + ft]);
+                    afr[kb][2] = __float_as_uint(zb[fg * kZLd + kb * 8 + ft + 4]);
+                    afr[kb][3] = __float_as_uint(zb[(fg + 8) * kZLd + kb * 8 + ft + 4]);
+                }
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+#pragma unroll
+                    for (int kb = 0; kb <= nb; ++kb) {                    // blocks above the diagonal of L are zero
+                        const float2 b = *reinterpret_cast<const float2*>(&sB[(nb * (nb + 1) / 2 + kb) * 64 + lane * 2]);
+                        asm volatile(
+                            "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                            "{%0,%1,%2,%3};"
+                            : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                            : "r"(afr[kb][0]), "r"(afr[kb][1]), "r"(afr[kb][2]), "r"(afr[kb][3]),
+                              "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
+                    }
+                    dfr[mt][nb][0] = c0;
+                    dfr[mt][nb][1] = c1;
+                    dfr[mt][nb][2] = c2;
+                    dfr[mt][nb][3] = c3;
+                }
+                __syncwarp();                                             // fragments read: the buffer is free
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    *reinterpret_cast<float2*>(&zb[fg * kZLd + nb * 8 + 2 * ft]) = make_float2(dfr[mt][nb][0], dfr[mt][nb][1]);
+                    *reinterpret_cast<float2*>(&zb[(fg + 8) * kZLd + nb * 8 + 2 * ft]) =
+                        make_float2(dfr[mt][nb][2], dfr[mt][nb][3]);
+                }
+                __syncwarp();
+                if ((lane >> 4) == mt) {
+#pragma unroll
+                    for (int c = 0; c < DMAX; c += 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(&zb[(lane & 15) * kZLd + c]);
+                        delta[c + 0] = v.x;
+                        delta[c + 1] = v.y;
+                        delta[c + 2] = v.z;
+                        delta[c + 3] = v.w;
                     }
                 }
+                __syncwarp();
             }
             mbar_wait(&mbar, tma_phase);
             tma_phase ^= 1u;
@@ -582,8 +655,13 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             for (int c = 0; c < DMAX; ++c) th[0][c] = stage[c * TPB + threadIdx.x] + (double)delta[c];
             ll_old[0] = stage[d * TPB + threadIdx.x];
             lp_old[0] = stage[(d + 1) * TPB + threadIdx.x];
-            __syncthreads();                       // the whole block has drained the stage
-            if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) tma_issue(tile + gridDim.x);
+            // every thread reports that it has drained the stage; only the issuing thread waits for
+            // the whole block (a block-wide barrier here cost 11 % of the stall samples)
+            mbar_arrive(&mbar_empty);
+            if (threadIdx.x == 0) {
+                mbar_wait(&mbar_empty, tma_phase ^ 1u);
+                if (tile + gridDim.x < n_tiles) tma_issue(tile + gridDim.x);
+            }
         } else {
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
@@ -726,7 +804,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                 if (a.rng.mode == 1) {
                     u = a.rng.u[i];
                 } else {
-                    u = gen_uniform53(&a.rk, (uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
+                    u = gen_uniform53(a.rk.k[0], a.rk.k[1], (uint64_t)(a.rng.id_offset + i), 0xFFFFu, (uint32_t)a.rng.stream);
                 }
                 const bool rejected = ratio < u;     // NaN compares false -> accept, as numpy does
                 if (!rejected && !(run[p] && not_pd[p])) {
@@ -930,7 +1008,8 @@ template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA =
           bool DYN = false, bool MULTI = false>
 static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     const size_t smem = mh_smem_bytes(&a.prob) + (size_t)DMAX * DMAX * sizeof(double) +
-                        (TMA ? (size_t)(64 + (DMAX + 2) * TPB) * sizeof(double) : 0);
+                        (TMA ? (size_t)(64 + (DMAX + 2) * TPB) * sizeof(double) +
+                                   (size_t)(TPB / 32) * 16 * (DMAX + 4) * sizeof(float) : 0);
     if (TMA) {
         static bool attr = false;
         if (!attr) {
