@@ -303,7 +303,7 @@ __device__ __forceinline__ void normal_pair_f(uint32_t w0, uint32_t w1, float& z
     const float u1 = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
     const float th = ((float)(int32_t)w1) * (3.14159265358979f / 2147483648.0f);   // [-pi, pi)
     const float x = -1.38629436111989f * __log2f(u1);       // -2 ln(u1) > 0
-    const float r = x * __frsqrt_rn(x);
+    const float r = x * __frsqrt_rn(fmaxf(x, 1e-30f));      // u1 can round to 1.0f: x = 0 must give r = 0, not 0 * inf
     float s, c;
     __sincosf(th, &s, &c);
     z0 = r * c;
@@ -312,8 +312,8 @@ __device__ __forceinline__ void normal_pair_f(uint32_t w0, uint32_t w1, float& z
 __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, double& z0, double& z1) {
     const float u1 = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
     const float th = ((float)(int32_t)w1) * (3.14159265358979f / 2147483648.0f);   // [-pi, pi)
-    const float x = -2.0f * __logf(u1);       // > 0 since u1 < 1
-    const float r = x * rsqrtf(x);
+    const float x = -2.0f * __logf(u1);       // >= 0 (u1 can round to 1.0f)
+    const float r = x * rsqrtf(fmaxf(x, 1e-30f));   // x = 0 gives r = 0, not 0 * inf
     float s, c;
     __sincosf(th, &s, &c);
     z0 = (double)(r * c);

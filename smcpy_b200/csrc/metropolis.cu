@@ -116,14 +116,23 @@ __device__ __noinline__ double gen_uniform53(uint32_t k0, uint32_t k1, uint64_t 
     return u01_53(r.x, r.y);
 }
 
-// Four standard normals (fp32) from one Philox call.  Deliberately NOT inlined: the wide
-// kernels call it DMAX/4 times per particle and eight inlined copies push the tile body past the
-// 32 KB instruction cache (ncu: 21 % of stall samples were `no_inst`, profiles/r01_mh_kernels.md).
-__device__ __noinline__ float4 gen_normals4(uint32_t k0, uint32_t k1, uint64_t pid, uint32_t call, uint32_t stream) {
-    const uint4 r = philox_s(k0, k1, pid, call, stream);
-    float4 z;
-    normal_pair_f(r.x, r.y, z.x, z.y);
-    normal_pair_f(r.z, r.w, z.z, z.w);
+// Out-of-line on purpose: the wide kernels need DMAX normals per particle and inlined copies push the
+// tile body past the 32 KB instruction cache (ncu: 21 % of stall samples were `no_inst`,
+// profiles/r01_mh_kernels.md).
+// Eight normals from two Philox calls (counters call, call + 1) in one out-of-line block: the two
+// 10-round chains are independent, so the scheduler interleaves them (the single-call version
+// left the four warps of a scheduler waiting on one dependent IMAD chain each: 33 % `wait` stalls).
+struct Float8 {
+    float4 a, b;
+};
+__device__ __noinline__ Float8 gen_normals8(uint32_t k0, uint32_t k1, uint64_t pid, uint32_t call, uint32_t stream) {
+    const uint4 r0 = philox_s(k0, k1, pid, call, stream);
+    const uint4 r1 = philox_s(k0, k1, pid, call + 1u, stream);
+    Float8 z;
+    normal_pair_f(r0.x, r0.y, z.a.x, z.a.y);
+    normal_pair_f(r1.x, r1.y, z.b.x, z.b.y);
+    normal_pair_f(r0.z, r0.w, z.a.z, z.a.w);
+    normal_pair_f(r1.z, r1.w, z.b.z, z.b.w);
     return z;
 }
 
@@ -580,12 +589,16 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             float delta[DMAX];                                           // first sqrt(s) z, then sqrt(s) L z
             const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[0]);
 #pragma unroll
-            for (int c = 0; c < DMAX; c += 4) {
-                const float4 zz = gen_normals4(a.rk.k[0], a.rk.k[1], pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
-                delta[c + 0] = scf * zz.x;
-                delta[c + 1] = scf * zz.y;
-                delta[c + 2] = scf * zz.z;
-                delta[c + 3] = scf * zz.w;
+            for (int c = 0; c + 7 < DMAX; c += 8) {
+                const Float8 zz = gen_normals8(a.rk.k[0], a.rk.k[1], pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
+                delta[c + 0] = scf * zz.a.x;
+                delta[c + 1] = scf * zz.a.y;
+                delta[c + 2] = scf * zz.a.z;
+                delta[c + 3] = scf * zz.a.w;
+                delta[c + 4] = scf * zz.b.x;
+                delta[c + 5] = scf * zz.b.y;
+                delta[c + 6] = scf * zz.b.z;
+                delta[c + 7] = scf * zz.b.w;
             }
             // Each warp multiplies its 32 rows of z by L^T as two 16-row M-tiles.  The rows pass
             // through a 16-row shared buffer per warp to get from one-particle-per-thread into the

@@ -196,6 +196,18 @@ def dev(a, dtype=torch.float64):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(rt.device, non_blocking=False)
 
 
+def host(t):
+    """Device tensor -> numpy array.  Large arrays go through page-locked memory (torch caches the
+    pinned blocks) at PCIe speed; the returned array owns that block.  Small reads take the plain
+    synchronous copy."""
+    if t.numel() * t.element_size() < (1 << 20):
+        return t.cpu().numpy()
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out.numpy()
+
+
 def make_path(phi, phi_prev, lam):
     return _lib.Path(float(phi), float(phi_prev), float(lam))
 
@@ -424,7 +436,7 @@ class DeviceState:
     def params_host(self):
         out = torch.empty((self.n, self.d), dtype=torch.float64, device=self.cols.device)
         call("smcb_soa_to_aos", ptr(self.cols), ptr(out), self.n, self.d, self.n, stream_ptr())
-        return out.cpu().numpy()
+        return host(out)
 
     def set_uniform_weights(self):
         """Weights after initialisation / resampling: log(1/N) normalised the reference's way
@@ -812,7 +824,7 @@ def _path_eval(ll, lp, lq, path, mode):
     a, b = dev(ll.reshape(-1)), dev(lp.reshape(-1))
     c = None if lq is None else dev(lq.reshape(-1))
     call("smcb_path_eval", n, ptr(a), ptr(b), ptr(c), C.byref(path), mode, ptr(out), stream_ptr())
-    return out.cpu().numpy().reshape(-1, 1)
+    return host(out).reshape(-1, 1)
 
 
 def host_path_logpdf(ll, lp, lq, phi, lam):

@@ -85,7 +85,7 @@ class Particles:
             n, d = self._num_particles, self._d
             out = torch.empty((n, d), dtype=torch.float64, device=self._cols.device)
             call("smcb_soa_to_aos", ptr(self._cols), ptr(out), n, d, n, stream_ptr())
-            self._cache["params"] = out.cpu().numpy()
+            self._cache["params"] = engine.host(out)
         return self._cache["params"]
 
     @property
@@ -103,19 +103,19 @@ class Particles:
     @property
     def log_likes(self):
         if "ll" not in self._cache:
-            self._cache["ll"] = self._cols[self._d].cpu().numpy().reshape(-1, 1)
+            self._cache["ll"] = engine.host(self._cols[self._d]).reshape(-1, 1)
         return self._cache["ll"]
 
     @property
     def log_weights(self):
         if "lw" not in self._cache:
-            self._cache["lw"] = self._log_w.cpu().numpy().reshape(-1, 1)
+            self._cache["lw"] = engine.host(self._log_w).reshape(-1, 1)
         return self._cache["lw"]
 
     @property
     def weights(self):
         if "w" not in self._cache:
-            self._cache["w"] = self._w.cpu().numpy().reshape(-1, 1)
+            self._cache["w"] = engine.host(self._w).reshape(-1, 1)
         return self._cache["w"]
 
     @property

@@ -717,6 +717,42 @@ def test_one_pass_shifted_covariance_matches_two_pass_and_numpy(sb):
     np.testing.assert_allclose(st.cov.cpu().numpy().reshape(d, d), want, rtol=1e-10, atol=1e-14)
 
 
+@pytest.mark.parametrize("d", [16, 32])
+def test_wide_native_kernel_proposal_increments(sb, d):
+    """Wide identity kernel, native RNG (TMA-staged variant: the increment sqrt(s) L z goes through
+    mma.sync tf32 fragments).  With phi = 0 and wide-open priors every proposal is accepted, so
+    x' - x are the increments themselves: mean 0, covariance L L^T (tf32 inputs: 1e-3), symmetric,
+    Gaussian marginals."""
+    from scipy import stats
+    from smcpy_b200 import engine
+    n = 1 << 18
+    problem = configs.gauss_problem(d)
+    problem["priors"] = [("uniform", -1e6, 2e6)] * d
+    mcmc, kernel = make_b200(problem, rng=21)
+    rng = np.random.default_rng(d)
+    x0 = rng.normal(0, 1, (n, d))
+    st = _state(sb, n, d)
+    st.set_params_host(x0)
+    engine.eval_incoming(st, mcmc.spec)
+    a = rng.normal(0, 1, (d, d)) * 0.2 + np.eye(d)
+    cov = a @ a.T * 1e-2
+    st.chol.copy_(engine.dev(np.linalg.cholesky(cov)))
+    moved = engine.mutate(st, mcmc.spec, 1, engine.make_path(0.0, 0.0, 1.0), kernel.rng)
+    assert float(moved) == 1.0
+    inc = st.params_host() - x0
+    assert np.all(np.abs(inc.mean(axis=0)) < 5 * np.sqrt(np.diag(cov) / n))
+    emp = inc.T @ inc / n
+    scale = np.sqrt(np.outer(np.diag(cov), np.diag(cov)))
+    assert np.max(np.abs(emp - cov) / scale) < 0.012          # sampling noise 1/sqrt(n) * few + tf32 truncation
+    white = np.linalg.solve(np.linalg.cholesky(cov), inc.T)   # recovers z (up to tf32 rounding)
+    assert abs(stats.skew(white[0])) < 0.02 and abs(stats.kurtosis(white[d - 1])) < 0.05
+    assert stats.kstest(white[d // 2], "norm").pvalue > 1e-4
+    # log-likelihood column consistent with the moved particles (identity model, sigma = 1)
+    x1 = st.params_host()
+    want = -0.5 * d * np.log(2 * np.pi) - 0.5 * ((x1 - problem["data"][None, :]) ** 2).sum(axis=1)
+    np.testing.assert_allclose(st.ll.cpu().numpy(), want, rtol=1e-12)
+
+
 def test_wide_identity_kernel_tma_path_vs_oracle(sb):
     """2^18 particles x d=32 takes the persistent, TMA-staged (cp.async.bulk + mbarrier) variant
     of the fused Metropolis kernel; replayed draws against the oracle, 1e-10."""
