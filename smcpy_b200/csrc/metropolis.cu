@@ -119,20 +119,27 @@ __device__ __noinline__ double gen_uniform53(uint32_t k0, uint32_t k1, uint64_t 
 // Out-of-line on purpose: the wide kernels need DMAX normals per particle and inlined copies push the
 // tile body past the 32 KB instruction cache (ncu: 21 % of stall samples were `no_inst`,
 // profiles/r01_mh_kernels.md).
-// Eight normals from two Philox calls (counters call, call + 1) in one out-of-line block: the two
-// 10-round chains are independent, so the scheduler interleaves them (the single-call version
-// left the four warps of a scheduler waiting on one dependent IMAD chain each: 33 % `wait` stalls).
-struct Float8 {
-    float4 a, b;
+// Sixteen normals from four Philox calls (counters call .. call + 3) in one out-of-line block: the
+// four 10-round chains are independent, so the scheduler interleaves them (one call per block left
+// the four warps of a scheduler waiting on one dependent IMAD chain each: 33 % `wait` stalls;
+// 1.044 -> 0.999 ms with two chains, 0.984 ms with four).
+struct Float16 {
+    float4 a, b, c, d;
 };
-__device__ __noinline__ Float8 gen_normals8(uint32_t k0, uint32_t k1, uint64_t pid, uint32_t call, uint32_t stream) {
+__device__ __noinline__ Float16 gen_normals16(uint32_t k0, uint32_t k1, uint64_t pid, uint32_t call, uint32_t stream) {
     const uint4 r0 = philox_s(k0, k1, pid, call, stream);
     const uint4 r1 = philox_s(k0, k1, pid, call + 1u, stream);
-    Float8 z;
+    const uint4 r2 = philox_s(k0, k1, pid, call + 2u, stream);
+    const uint4 r3 = philox_s(k0, k1, pid, call + 3u, stream);
+    Float16 z;
     normal_pair_f(r0.x, r0.y, z.a.x, z.a.y);
     normal_pair_f(r1.x, r1.y, z.b.x, z.b.y);
+    normal_pair_f(r2.x, r2.y, z.c.x, z.c.y);
+    normal_pair_f(r3.x, r3.y, z.d.x, z.d.y);
     normal_pair_f(r0.z, r0.w, z.a.z, z.a.w);
     normal_pair_f(r1.z, r1.w, z.b.z, z.b.w);
+    normal_pair_f(r2.z, r2.w, z.c.z, z.c.w);
+    normal_pair_f(r3.z, r3.w, z.d.z, z.d.w);
     return z;
 }
 
@@ -589,16 +596,16 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             float delta[DMAX];                                           // first sqrt(s) z, then sqrt(s) L z
             const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[0]);
 #pragma unroll
-            for (int c = 0; c + 7 < DMAX; c += 8) {
-                const Float8 zz = gen_normals8(a.rk.k[0], a.rk.k[1], pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
-                delta[c + 0] = scf * zz.a.x;
-                delta[c + 1] = scf * zz.a.y;
-                delta[c + 2] = scf * zz.a.z;
-                delta[c + 3] = scf * zz.a.w;
-                delta[c + 4] = scf * zz.b.x;
-                delta[c + 5] = scf * zz.b.y;
-                delta[c + 6] = scf * zz.b.z;
-                delta[c + 7] = scf * zz.b.w;
+            for (int c = 0; c + 15 < DMAX; c += 16) {
+                const Float16 zz = gen_normals16(a.rk.k[0], a.rk.k[1], pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
+                const float4 q4[4] = {zz.a, zz.b, zz.c, zz.d};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    delta[c + 4 * q + 0] = scf * q4[q].x;
+                    delta[c + 4 * q + 1] = scf * q4[q].y;
+                    delta[c + 4 * q + 2] = scf * q4[q].z;
+                    delta[c + 4 * q + 3] = scf * q4[q].w;
+                }
             }
             // Each warp multiplies its 32 rows of z by L^T as two 16-row M-tiles.  The rows pass
             // through a 16-row shared buffer per warp to get from one-particle-per-thread into the
