@@ -38,6 +38,8 @@ M_DATA = 1000
 PHI = np.linspace(0, 1, 20)
 ESS_THRESHOLD = 0.8
 METRIC = "particle-MCMC steps/sec"
+WORKLOAD = ("C2: linear model FixedPhiSampler, 2^20 particles per GPU, 20 MCMC steps, 1000 data points, "
+            "phi=linspace(0,1,20), ess_threshold=0.8")
 UNIT = "particle-steps/s"
 
 
@@ -198,8 +200,10 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "C2 linear FixedPhiSampler (bounded sample N=%d)" % n, "num_mcmc_samples": K_MCMC,
-                      "data_points": M_DATA, "smc_steps": len(PHI) - 1},
+           "config": {"workload": WORKLOAD, "particles_per_gpu": N_PER_GPU, "num_mcmc_samples": K_MCMC,
+                      "data_points": M_DATA, "smc_steps": len(PHI) - 1, "rng": "numpy Generator", "resampler": "standard",
+                      "parallelism": "host cores x%d" % use,
+                      "sample": "each step is a bounded sample of the workload: N=%d particles (cpu_baseline.sample)" % n},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": use, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -377,8 +381,7 @@ def run_gpu(args):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "C2: linear model FixedPhiSampler, 2^20 particles per GPU, 20 MCMC steps, "
-                                  "1000 data points, phi=linspace(0,1,20), ess_threshold=0.8",
+           "config": {"workload": WORKLOAD,
                       "particles_per_gpu": N_PER_GPU, "num_mcmc_samples": K_MCMC, "data_points": M_DATA,
                       "smc_steps": len(PHI) - 1, "rng": "philox (native)", "resampler": "standard",
                       "parallelism": "particles sharded x%d" % world,
