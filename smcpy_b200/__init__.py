@@ -18,7 +18,7 @@ from .priors import ImproperCov, ImproperUniform                            # no
 from .proposals import MultivarIndependent                                  # noqa: F401
 from .resampler_rngs import standard, stratified, systematic                # noqa: F401
 from .samplers import AdaptiveSampler, FixedPhiSampler, FixedTimeSampler, MaxStepSampler  # noqa: F401
-from .storage import InMemoryStorage                                        # noqa: F401
+from .storage import HDF5Storage, InMemoryStorage, PickleStorage                                        # noqa: F401
 from .vector_mcmc import B200VectorMCMC                                     # noqa: F401
 
 VectorMCMC = B200VectorMCMC

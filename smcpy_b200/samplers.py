@@ -51,10 +51,31 @@ class SamplerBase:
             self._step = step
 
     def _save_step(self, step):
-        rank, _ = engine.dist_info()
-        self._result.save_step(step)          # every rank keeps its shard (device snapshots)
+        self._result.save_step(step)          # every rank keeps (or writes) its own shard
 
     def _initialize(self, num_particles):
+        """samplers.py:87-92.  With a file-backed result store opened on an existing file the run
+        resumes from the last stored step: its particles go back to the device (log-priors are
+        re-evaluated there), the stored phi sequence is adopted and the path is advanced to the
+        stored phi.  (The reference leaves the path at phi = 0 after a restart, so its first
+        resumed reweight spans 0 -> phi_next; that is not reproduced.)"""
+        if self._result is not None and getattr(self._result, "is_restart", False) and len(self._result) > 0:
+            if engine.dist_info()[1] > 1:
+                raise NotImplementedError("restart from a file-backed store is single-GPU")
+            import ctypes as C
+            from ._lib import call, ptr, stream_ptr
+            last = self._result[-1]
+            st = last.to_state()
+            call("smcb_log_priors", C.byref(self._mcmc_kernel.spec.c), ptr(st.cols), st.n, st.n, ptr(st.lp),
+                 None, stream_ptr())
+            self._st = st
+            self._step = last                      # already stored: not saved again
+            self._restart_phi = list(self._result.phi_sequence)
+            phi = float(self._restart_phi[-1])
+            if phi > self._mcmc_kernel.path.phi:
+                self._mcmc_kernel.path.phi = phi
+            return None
+        self._restart_phi = None
         self._st = self._initializer.initialize_state(num_particles)
         return self._initializer.particles_from_state(self._st)
 
@@ -100,8 +121,11 @@ class FixedPhiSampler(SamplerBase):
                                 particles_warn_threshold=particles_warn_threshold)
         self._phi_sequence = phi_sequence
         self.step = self._initialize(num_particles)
+        done = float(self._restart_phi[-1]) if self._restart_phi else None
         bar = self._pbar_open(float(self._phi_sequence[0]))
         for i, phi in enumerate(self._phi_sequence[1:]):
+            if done is not None and phi <= done:      # resumed run: these steps are already stored
+                continue
             self._do_smc_step(phi, num_mcmc_samples)
             if bar is not None:
                 bar.set_description(f"[ mutation ratio: {self.step.attrs['mutation_ratio']}")
@@ -125,7 +149,9 @@ class AdaptiveSampler(SamplerBase):
                                 particles_warn_threshold=particles_warn_threshold)
         self._phi_sequence = [0]
         self.step = self._initialize(num_particles)
-        bar = self._pbar_open(0.0)
+        if self._restart_phi:
+            self._phi_sequence = list(self._restart_phi)
+        bar = self._pbar_open(float(self._phi_sequence[-1]))
         while self._phi_sequence[-1] < 1:
             proposed_phi = self.optimize_step(self.step, self._phi_sequence[-1], target_ess)
             proposed_phi = self._verify_min_dphi(proposed_phi, min_dphi)

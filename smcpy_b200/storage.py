@@ -1,45 +1,90 @@
 """
-Result storage: the in-memory container and the marginal-log-likelihood estimate of
-smcpy/utils/storage.py:14-76 (estimate_marginal_log_likelihoods :18-21 is on the hot path's
-output side).  File-backed storage (HDF5 / pickle) is out of scope:
-feed the reference's classes with `Particles` host views if checkpoint files are needed.
-Steps hold device snapshots; `retain` bounds how many are kept (all by default, as the
-reference keeps every step).
+Result storage with the interface of smcpy/utils/storage.py: the in-memory container (:43-76), the
+marginal-log-likelihood estimate (:18-21, the output side of the hot path) and the two file-backed
+stores (HDF5Storage :79-170, PickleStorage :173-277).
+
+Steps are device snapshots (`Particles`).  InMemoryStorage keeps them in HBM (`retain` bounds how
+many; the reference keeps every step, 17 GB per step at 64M x 32).  The file-backed stores stream
+every step to the host through page-locked memory (engine.host) as it is produced and keep nothing
+on the device; reading a step back (`storage[i]`, iteration, restart) uploads it again.
+
+On-disk formats:
+  * HDF5Storage writes the reference's layout -- one group per step named by its index, attrs `phi`,
+    `total_unnorm_log_weight`, `mutation_ratio`, datasets `log_likes`, `log_weights`, group `params`
+    with one dataset per parameter in order -- so files are interchangeable with smcpy's
+    (needs h5py, which this image does not ship: the class raises ImportError without it).
+  * PickleStorage appends one pickle per step of a plain dict {params, log_likes, log_weights,
+    attrs} (numpy arrays).  The reference pickles its own Particles class, which only smcpy can
+    load; the plain dict loads anywhere.
+
+Restart (samplers `_initialize`, samplers.py:87-92): a store opened in mode 'a' on an existing file
+sets `is_restart`; the sampler then resumes from the last stored step and phi sequence.
 """
 
+import os
+import pickle
 import threading
 
 import numpy as np
 
+_local = threading.local()
+
+
+def _stack():
+    if not hasattr(_local, "stack"):
+        _local.stack = []
+    return _local.stack
+
 
 class ContextManager:
-    """Thread-local stack of active storage contexts (smcpy/utils/context_manager.py:5-24)."""
-    _contexts = threading.local()
+    """`with storage:` makes `storage` the result container of samplers built inside the block
+    (smcpy/utils/context_manager.py); one stack per thread."""
 
     def __enter__(self):
-        type(self).get_contexts().append(self)
+        _stack().append(self)
         return self
 
-    def __exit__(self, typ, value, traceback):
-        type(self).get_contexts().pop()
+    def __exit__(self, exc_type, exc, tb):
+        _stack().pop()
 
     @classmethod
     def get_contexts(cls):
-        if not hasattr(cls._contexts, "stack"):
-            cls._contexts.stack = []
-        return cls._contexts.stack
+        return _stack()
 
     @classmethod
     def get_context(cls):
-        try:
-            return cls.get_contexts()[-1]
-        except IndexError:
+        s = _stack()
+        if not s:
             raise TypeError("No context on context stack")
+        return s[-1]
 
 
-class InMemoryStorage(ContextManager):
-    def __init__(self, retain=None):
+class BaseStorage(ContextManager):
+    def __init__(self):
         self.is_restart = False
+
+    def estimate_marginal_log_likelihoods(self):
+        """cumsum([0] + per-step total_unnorm_log_weight)  (utils/storage.py:18-21)."""
+        return np.cumsum([0] + [float(t) for t in self._step_totals()])
+
+    def _step_totals(self):
+        return [p.total_unnorm_log_weight for p in self]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def _index(self, idx):
+        n = len(self)
+        if idx < 0:
+            idx += n
+        if idx < 0 or idx >= n:
+            raise IndexError(f"index {idx} out of range.")
+        return idx
+
+
+class InMemoryStorage(BaseStorage):
+    def __init__(self, retain=None):
+        super().__init__()
         self._step_list = []
         self._phi_sequence = []
         self._mut_ratio_sequence = []
@@ -63,6 +108,9 @@ class InMemoryStorage(ContextManager):
     def __len__(self):
         return len(self._step_list)
 
+    def _step_totals(self):
+        return self._totals
+
     def save_step(self, step):
         self._step_list.append(step)
         self._phi_sequence.append(step.attrs["phi"])
@@ -71,6 +119,152 @@ class InMemoryStorage(ContextManager):
         if self._retain is not None and len(self._step_list) > self._retain:
             del self._step_list[0]
 
-    def estimate_marginal_log_likelihoods(self):
-        """cumsum([0] + per-step total_unnorm_log_weight)  (utils/storage.py:18-21)."""
-        return np.cumsum([0] + list(self._totals))
+
+def _check_mode(mode):
+    if mode != "a" and mode != "w":
+        raise ValueError("Available modes are 'a' (default, read/append) and 'w' (overwrite).")
+
+
+def _rank_filename(filename):
+    """One file per rank when particles are sharded over several GPUs (every rank stores its own
+    shard; the reference, where every MPI rank holds all particles, writes on rank 0 only)."""
+    from . import engine
+    rank, world = engine.dist_info()
+    return str(filename) if world == 1 else "%s.rank%d" % (filename, rank)
+
+
+def _host_record(step):
+    """Host copy of one step: what both file formats store."""
+    return {"params": {k: np.array(v) for k, v in step.param_dict.items()},
+            "log_likes": np.array(step.log_likes), "log_weights": np.array(step.log_weights),
+            "attrs": {"phi": step.attrs["phi"], "mutation_ratio": step.attrs["mutation_ratio"],
+                      "total_unnorm_log_weight": step.total_unnorm_log_weight}}
+
+
+def _particles_from_record(rec):
+    from .particles import Particles
+    p = Particles(rec["params"], rec["log_likes"], rec["log_weights"])
+    p.attrs = dict(rec["attrs"])
+    return p
+
+
+class PickleStorage(BaseStorage):
+    """Append-only file of one pickle per step (utils/storage.py:173-277)."""
+
+    def __init__(self, filename, mode="a"):
+        _check_mode(mode)
+        super().__init__()
+        self._filename = _rank_filename(filename)
+        self._offsets = []                   # byte offset of every stored step
+        self._meta = []                      # (phi, mutation_ratio, total_unnorm_log_weight) per step
+        if mode == "w" and os.path.exists(self._filename):
+            os.remove(self._filename)
+        if os.path.exists(self._filename):
+            self._scan()
+            self.is_restart = True
+
+    def _scan(self):
+        self._offsets, self._meta = [], []
+        with open(self._filename, "rb") as f:
+            while True:
+                pos = f.tell()
+                try:
+                    rec = pickle.load(f)
+                except EOFError:
+                    break
+                self._offsets.append(pos)
+                a = rec["attrs"]
+                self._meta.append((a["phi"], a["mutation_ratio"], a["total_unnorm_log_weight"]))
+
+    @property
+    def phi_sequence(self):
+        return [m[0] for m in self._meta]
+
+    @property
+    def mut_ratio_sequence(self):
+        return [m[1] for m in self._meta]
+
+    def _step_totals(self):
+        return [m[2] for m in self._meta]
+
+    def __len__(self):
+        return len(self._offsets)
+
+    def save_step(self, step):
+        rec = _host_record(step)
+        pos = os.path.getsize(self._filename) if os.path.exists(self._filename) else 0
+        with open(self._filename, "ab") as f:
+            pickle.dump(rec, f, pickle.HIGHEST_PROTOCOL)
+        self._offsets.append(pos)
+        a = rec["attrs"]
+        self._meta.append((a["phi"], a["mutation_ratio"], a["total_unnorm_log_weight"]))
+
+    def __getitem__(self, idx):
+        idx = self._index(idx)
+        with open(self._filename, "rb") as f:
+            f.seek(self._offsets[idx])
+            rec = pickle.load(f)
+        return _particles_from_record(rec)
+
+
+class HDF5Storage(BaseStorage):
+    """The reference's HDF5 layout (utils/storage.py:79-170); needs h5py."""
+
+    def __init__(self, filename, mode="a"):
+        _check_mode(mode)
+        super().__init__()
+        try:
+            import h5py
+        except ImportError as e:              # pragma: no cover - h5py is not in this image
+            raise ImportError("HDF5Storage needs h5py; PickleStorage and InMemoryStorage do not") from e
+        self._h5py = h5py
+        self._filename = _rank_filename(filename)
+        self._mode = mode
+        self._len = 0
+        if os.path.exists(self._filename) and mode == "a":
+            with self._open("r") as h5:
+                self._len = len(h5.keys())
+            self.is_restart = True
+
+    def _open(self, mode):
+        return self._h5py.File(self._filename, mode, track_order=True)
+
+    def _attr_list(self, name):
+        with self._open("r") as h5:
+            return [h5[str(i)].attrs[name] for i in range(len(h5.keys()))]
+
+    @property
+    def phi_sequence(self):
+        return self._attr_list("phi")
+
+    @property
+    def mut_ratio_sequence(self):
+        return self._attr_list("mutation_ratio")
+
+    def _step_totals(self):
+        return self._attr_list("total_unnorm_log_weight")
+
+    def __len__(self):
+        return self._len
+
+    def save_step(self, step):
+        rec = _host_record(step)
+        with self._open(self._mode) as h5:
+            self._mode = "a"
+            grp = h5.create_group(str(len(h5.keys())))
+            for k, v in rec["attrs"].items():
+                grp.attrs[k] = v
+            grp.create_dataset("log_likes", data=rec["log_likes"])
+            grp.create_dataset("log_weights", data=rec["log_weights"])
+            pg = grp.create_group("params", track_order=True)
+            for k, v in rec["params"].items():
+                pg.create_dataset(k, data=v)
+            self._len = len(h5.keys())
+
+    def __getitem__(self, idx):
+        idx = self._index(idx)
+        with self._open("r") as h5:
+            grp = h5[str(idx)]
+            rec = {"params": {k: v[:] for k, v in grp["params"].items()}, "log_likes": grp["log_likes"][:],
+                   "log_weights": grp["log_weights"][:], "attrs": {k: v for k, v in grp.attrs.items()}}
+        return _particles_from_record(rec)

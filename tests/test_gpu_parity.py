@@ -753,6 +753,68 @@ def test_wide_native_kernel_proposal_increments(sb, d):
     np.testing.assert_allclose(st.ll.cpu().numpy(), want, rtol=1e-12)
 
 
+def test_pickle_storage_streams_steps_and_restarts(sb, tmp_path):
+    """f3 (utils/storage.py): a file-backed store receives every step as it is produced (nothing kept
+    on the device), reads back equal to the in-memory run, and a new sampler resumes from the file."""
+    problem = configs.linear_problem(60)
+    phis = np.linspace(0, 1, 9)
+
+    def run(storage, seq=phis, seed=3):
+        mcmc, kernel = make_b200(problem, rng=seed)
+        if storage is None:
+            smc = sb.FixedPhiSampler(kernel, show_progress_bar=False)
+        else:
+            with storage:
+                smc = sb.FixedPhiSampler(kernel, show_progress_bar=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return smc.sample(3000, 4, seq, 0.8, resample_rng=sb.stratified)
+    mem_steps, mem_mll = run(None)
+    fn = tmp_path / "run.pkl"
+    file_steps, file_mll = run(sb.PickleStorage(fn, mode="w"))
+    assert isinstance(file_steps, sb.PickleStorage) and len(file_steps) == len(mem_steps) == 9
+    np.testing.assert_array_equal(file_mll, mem_mll)
+    np.testing.assert_array_equal(file_steps[-1].params, mem_steps[-1].params)
+    np.testing.assert_array_equal(file_steps[4].log_likes, mem_steps[4].log_likes)
+    assert file_steps[-1].attrs["phi"] == 1.0
+    np.testing.assert_allclose(file_steps[3].compute_mean(package=False), mem_steps[3].compute_mean(package=False),
+                               rtol=1e-12)
+    # interrupted run: the first five phis, then a new process-like restart on the same file
+    fn2 = tmp_path / "resume.pkl"
+    run(sb.PickleStorage(fn2, mode="w"), seq=phis[:5])
+    store = sb.PickleStorage(fn2)
+    assert store.is_restart and len(store) == 5
+    res_steps, res_mll = run(store, seed=4)
+    assert len(res_steps) == 9 and res_steps.phi_sequence == list(phis)
+    np.testing.assert_array_equal(res_mll[:5], mem_mll[:5])              # the stored part is untouched
+    assert res_mll[-1] == pytest.approx(mem_mll[-1], abs=0.3)
+    np.testing.assert_allclose(res_steps[-1].compute_mean(package=False), mem_steps[-1].compute_mean(package=False),
+                               atol=0.03)
+    # adaptive sampler resumes its phi sequence
+    fn3 = tmp_path / "adaptive.pkl"
+    mcmc, kernel = make_b200(problem, rng=5)
+    with sb.PickleStorage(fn3, mode="w") as stg:
+        smc = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steps, mll = smc.sample(3000, 4, target_ess=0.8)
+    full = list(steps.phi_sequence)
+    # truncate the file to its first four steps and resume
+    with open(fn3, "rb") as f:
+        head = f.read(stg._offsets[4])
+    with open(fn3, "wb") as f:
+        f.write(head)
+    mcmc, kernel = make_b200(problem, rng=6)
+    with sb.PickleStorage(fn3) as stg2:
+        smc2 = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steps2, mll2 = smc2.sample(3000, 4, target_ess=0.8)
+    assert list(smc2.phi_sequence[:4]) == full[:4] and smc2.phi_sequence[-1] == 1.0
+    assert abs(len(steps2) - len(full)) <= 2
+    assert mll2[-1] == pytest.approx(mll[-1], abs=0.3)
+
+
 def test_wide_identity_kernel_tma_path_vs_oracle(sb):
     """2^18 particles x d=32 takes the persistent, TMA-staged (cp.async.bulk + mbarrier) variant
     of the fused Metropolis kernel; replayed draws against the oracle, 1e-10."""
