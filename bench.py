@@ -370,6 +370,8 @@ def run_gpu(args):
                          # FP64 instructions issued (fma, sub, fma per data point) / FMA issue peak
                          "issue_frac": (3.0 * M_DATA * N_PER_GPU / (mh_ms * 1e-3)) / (fp64_peak * 1e12 / 2.0)}}
     other = {"share_of_step": share, "avg_ms": {k: float(np.mean(v)) for k, v in prof.items()},
+             "median_ms": {k: float(np.median(v)) for k, v in prof.items()},
+             "max_ms": {k: float(np.max(v)) for k, v in prof.items()},
              "calls_per_step": {k: len(v) for k, v in prof.items()}}
     if "reweight" in prof:                      # single-GPU entry points (fused calls) only
         rw = float(np.mean(prof["reweight"]))

@@ -197,10 +197,11 @@ def dev(a, dtype=torch.float64):
 
 
 def host(t):
-    """Device tensor -> numpy array.  Large arrays go through page-locked memory (torch caches the
-    pinned blocks) at PCIe speed; the returned array owns that block.  Small reads take the plain
-    synchronous copy."""
-    if t.numel() * t.element_size() < (1 << 20):
+    """Device tensor -> numpy array.  Arrays of 1-128 MB go through page-locked memory (torch caches
+    the pinned blocks) at PCIe speed; the returned array owns that block.  Small reads and very
+    large ones take the plain synchronous copy."""
+    nbytes = t.numel() * t.element_size()
+    if nbytes < (1 << 20) or nbytes > (128 << 20):      # very large reads stay pageable: locked pages are scarce
         return t.cpu().numpy()
     out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     out.copy_(t, non_blocking=True)
