@@ -221,14 +221,6 @@ int smcb_ess_bisect_xchg(int64_t n, const double* ll, const double* lp, const do
 /* u for `count` global slots starting at `first` out of n_global (resampler_rngs.py:4-9) */
 int smcb_resample_uniforms(int32_t kind, int64_t n_global, int64_t first, int64_t count,
                            uint64_t seed, uint64_t stream_id, double* u_out, void* stream);
-/* multinomial uniforms for sharded particles, locality preserving: the N iid uniforms are
- * generated as order-statistic blocks -- interval q = [q/world, (q+1)/world) holds
- * prefix[q+1]-prefix[q] of them (the caller draws those counts ~ Multinomial(N; 1/world), the
- * same on every rank); global sorted position g in interval q, j = g - prefix[q], gets
- * u = (q + U(q, j)) / world.  A rank's own positions [first, first+count) therefore fall mostly
- * into its own CDF segment and few rows cross NVLink.  prefix: device int64[world+1]. */
-int smcb_resample_uniforms_sharded(int32_t world, const int64_t* prefix, int64_t first, int64_t count,
-                                   uint64_t seed, uint64_t stream_id, double* u_out, void* stream);
 /* `standard` uniforms (resampler_rngs.py:4-5) in SORTED order by exponential spacings, for sharded
  * particles: U_(k) = S_k / S_(N+1), S = running sum of i.i.d. unit exponentials.
  *   1. smcb_resample_exponentials: e_out[i] = E / (2 N) of global slot first + i (Philox keyed by the

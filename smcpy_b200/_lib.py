@@ -93,7 +93,6 @@ SIGNATURES = {
     "smcb_ess_bisect_max_iters": [],
     "smcb_ess_bisect_xchg_slot_words": [],
     "smcb_resample_uniforms": [_I32, _I64, _I64, _I64, _U64, _U64, _P, _P],
-    "smcb_resample_uniforms_sharded": [_I32, _P, _I64, _I64, _U64, _U64, _P, _P],
     "smcb_resample_exponentials": [_I64, _I64, _I64, _U64, _U64, _P, _P],
     "smcb_resample_spacings_finish": [_P, _I64, _P, _P, _I64, _U64, _U64, _P, _P],
     "smcb_cdf_scan": [_P, _P, _I64, _I32, _P, _P],

@@ -40,24 +40,6 @@ __global__ void resample_uniforms_kernel(int kind, int64_t n_global, int64_t fir
     }
 }
 
-__global__ void resample_uniforms_sharded_kernel(int world, const int64_t* __restrict__ prefix, int64_t first,
-                                                 int64_t count, uint64_t seed, uint32_t stream_id, double* u) {
-    __shared__ int64_t s_pre[SMCB_MAX_RANKS + 1];
-    if (threadIdx.x <= world) s_pre[threadIdx.x] = prefix[threadIdx.x];
-    __syncthreads();
-    const Philox rng(seed);
-    const double inv_g = 1.0 / (double)world;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        const int64_t g = first + i;
-        int q = 0;
-        while (q + 1 < world && g >= s_pre[q + 1]) ++q;
-        const uint64_t j = (uint64_t)(g - s_pre[q]);
-        const uint4 r = rng(j, 0x5AD0u + (uint32_t)q, stream_id);
-        u[i] = ((double)q + u01_53(r.x, r.y)) * inv_g;
-    }
-}
-
 // ---- sorted multinomial uniforms by exponential spacings ------------------------------------------
 // N i.i.d. uniforms in sorted order are U_(k) = S_k / S_(N+1), S_k = E_1 + ... + E_k with i.i.d.
 // unit exponentials: draw E per global slot (Philox keyed by the slot id: independent of the GPU
@@ -373,14 +355,6 @@ extern "C" int smcb_resample_uniforms(int32_t kind, int64_t n_global, int64_t fi
     resample_uniforms_kernel<<<grid, 256, 0, as_stream(stream)>>>(kind, n_global, first, count, seed,
                                                                    (uint32_t)stream_id, u_out);
     return check_launch("resample_uniforms_kernel");
-}
-
-extern "C" int smcb_resample_uniforms_sharded(int32_t world, const int64_t* prefix, int64_t first, int64_t count,
-                                              uint64_t seed, uint64_t stream_id, double* u_out, void* stream) {
-    SMCB_REQUIRE(world >= 1 && world <= SMCB_MAX_RANKS && prefix && count > 0 && u_out, "bad argument");
-    resample_uniforms_sharded_kernel<<<grid_for(count, 256, 4, 8), 256, 0, as_stream(stream)>>>(
-        world, prefix, first, count, seed, (uint32_t)stream_id, u_out);
-    return check_launch("resample_uniforms_sharded_kernel");
 }
 
 extern "C" int smcb_resample_exponentials(int64_t first, int64_t count, int64_t n_global, uint64_t seed,
