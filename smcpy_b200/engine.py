@@ -396,6 +396,7 @@ class DeviceState:
         self.scalars = torch.zeros(16, dtype=f64, device=dv)
         self.bis = torch.zeros(16, dtype=f64, device=dv)
         self.counts = torch.zeros(4, dtype=torch.int64, device=dv)
+        self.zero = torch.zeros(1, dtype=f64, device=dv)
         self.mean = torch.zeros(d, dtype=f64, device=dv)
         self.cov = torch.zeros((d, d), dtype=f64, device=dv)
         self.chol = torch.zeros((d, d), dtype=f64, device=dv)

@@ -79,10 +79,12 @@ def sorted_uniforms(st, seed, stream_id):
     t = st.w_alt
     call("smcb_resample_exponentials", st.id_offset, n, st.n_global, seed, stream_id, ptr(st.u), s)
     call("smcb_cdf_scan", ptr(st.u), ptr(t), n, _lib.SCAN_LOOKBACK, ptr(st.ws), s)
-    totals = engine._all_gather_rows(t[n - 1:n]).reshape(-1) if world > 1 else t[n - 1:n]
-    off = segment_offsets(totals)
-    call("smcb_resample_spacings_finish", ptr(t), n, ptr(off[rank:rank + 1]), ptr(off[world:world + 1]), st.n_global,
-         seed, stream_id, ptr(st.u), s)
+    if world > 1:
+        off = segment_offsets(engine._all_gather_rows(t[n - 1:n]).reshape(-1))
+        lo, tot = off[rank:rank + 1], off[world:world + 1]
+    else:
+        lo, tot = st.zero, t[n - 1:n]          # one shard: offset 0, total = the last running sum
+    call("smcb_resample_spacings_finish", ptr(t), n, ptr(lo), ptr(tot), st.n_global, seed, stream_id, ptr(st.u), s)
     return st.u
 
 
