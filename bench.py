@@ -62,13 +62,19 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, indices, enabled=True):
+        """One poller per job (rank 0), covering every GPU of the job: eight pollers at 10 Hz, one
+        per rank, measurably slowed the 8-GPU run through the driver's management lock."""
+        self.rows, self.proc = [], None
+        self.index = ",".join(str(i) for i in indices)
+        self.enabled = enabled
 
     def start(self):
+        if not self.enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100" if "," not in self.index else "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -80,6 +86,8 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if not self.enabled:
+            return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -98,8 +106,9 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None, "samples": len(sm),
+                "gpus": self.index, "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -270,7 +279,7 @@ def run_gpu(args):
         one_pass(100 + i, spec)
 
     # ---- timed: device-resident ------------------------------------------------------------
-    sampler_clk = ClockSampler(local)
+    sampler_clk = ClockSampler(range(world) if world > 1 else [local], enabled=(rank == 0))
     barrier()
     sampler_clk.start()
     _lib.launch_count = 0
