@@ -808,10 +808,10 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
         pack[0] = st.counts[1]
         pack[1:] = (st.flags[0].to(torch.int64) >> torch.arange(4, device=st.cols.device)) & 1
         _all_reduce_sum(pack)
-        host = pack.cpu().numpy()
-        st.flags[0] = int(sum((1 << b) for b in range(4) if host[1 + b] > 0))
+        packed = pack.cpu().numpy()
+        st.flags[0] = int(sum((1 << b) for b in range(4) if packed[1 + b] > 0))
         st.check_flags("smc_metropolis")
-        return float(host[0]) / st.n_global
+        return float(packed[0]) / st.n_global
     moved = st.counts[1:2].clone()
     st.check_flags("smc_metropolis")                         # sync; raises on NaN
     return float(moved.item()) / st.n_global

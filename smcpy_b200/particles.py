@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, engine
+from . import engine
 from ._lib import call, ptr, stream_ptr
 
 
