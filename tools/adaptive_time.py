@@ -4,7 +4,7 @@ sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 import smcpy_b200 as sb
 from smcpy_b200 import engine
-from tests.helpers import make_b200
+from tests.golden.b200_build import make_b200
 from tests.golden import configs
 cfg = sys.argv[1]; log2n = int(sys.argv[2]) if len(sys.argv) > 2 else 23; K = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 problem = {"c5": lambda: configs.gauss_problem(32), "c1big": lambda: configs.linear_problem(100),

@@ -9,7 +9,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 import smcpy_b200 as sb
 from smcpy_b200 import engine
-from tests.helpers import make_b200
+from tests.golden.b200_build import make_b200
 from tests.golden import configs
 kind = sys.argv[1] if len(sys.argv) > 1 else "standard"
 log2n = int(sys.argv[2]) if len(sys.argv) > 2 else 23

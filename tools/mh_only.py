@@ -11,7 +11,7 @@ if cfg == "c2":
 else:
     from tests.golden import configs
     problem = configs.gauss_problem(32); n = 1 << 23
-from tests.helpers import make_b200
+from tests.golden.b200_build import make_b200
 mcmc, kernel = make_b200(problem, rng=3)
 from smcpy_b200.initializer import Initializer
 st = Initializer(kernel).initialize_state(n)

@@ -6,7 +6,7 @@ import bench
 import smcpy_b200 as sb
 from smcpy_b200 import engine
 from smcpy_b200.initializer import Initializer
-from tests.helpers import make_b200
+from tests.golden.b200_build import make_b200
 from tests.golden import configs
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 K = 20

@@ -7,7 +7,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 import smcpy_b200 as sb
 from smcpy_b200 import engine
-from tests.helpers import make_b200
+from tests.golden.b200_build import make_b200
 from tests.golden import configs
 problem = configs.gauss_problem(8)
 out = {}
