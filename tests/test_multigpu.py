@@ -70,6 +70,24 @@ def _gloo_worker(rank, world, port, out):
     mism = int((got != want).sum())
     tot_req = torch.tensor([float(recv.sum())])
     dist.all_reduce(tot_req)
+    # sorted multinomial uniforms by exponential spacings, sharded (sharded.sorted_uniforms with the
+    # kernels replaced by torch ops): per-slot exponentials -> local running sums -> rank offsets
+    e_all = torch.tensor(np.random.default_rng(99).exponential(1.0, n_global + 1)) * (0.5 / n_global)
+    t_loc = torch.cumsum(e_all[lo:hi], 0)
+    tots = torch.empty(world, dtype=torch.float64)
+    dist.all_gather_into_tensor(tots, t_loc[-1:].clone())
+    offs = sharded.segment_offsets(tots)
+    u_sorted = (offs[rank] + t_loc) / (offs[world] + e_all[n_global])
+    n_max = -(-n_global // world)                       # equal-size slots for the gather, trimmed after
+    padded = torch.full((n_max,), float("nan"), dtype=torch.float64)
+    padded[:n] = u_sorted
+    allp = torch.empty(world * n_max, dtype=torch.float64)
+    dist.all_gather_into_tensor(allp, padded)
+    sizes = [engine.shard_bounds(n_global, r, world)[1] - engine.shard_bounds(n_global, r, world)[0] for r in range(world)]
+    u_glob = np.concatenate([allp[r * n_max:r * n_max + sizes[r]].numpy() for r in range(world)])
+    want_u = np.cumsum(e_all.numpy()[:n_global]) / e_all.numpy().sum()
+    assert np.all(np.diff(u_glob) >= 0) and u_glob[0] > 0 and u_glob[-1] < 1
+    np.testing.assert_allclose(u_glob, want_u, rtol=1e-12)
     out.put((rank, n, mism, float(tot_req.item())))
     dist.destroy_process_group()
 
