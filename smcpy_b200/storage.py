@@ -215,7 +215,9 @@ class HDF5Storage(BaseStorage):
         super().__init__()
         try:
             import h5py
-        except ImportError as e:              # pragma: no cover - h5py is not in this image
+            if not hasattr(h5py, "File"):
+                raise ImportError("h5py stub without File")
+        except ImportError as e:              # h5py is not in this image
             raise ImportError("HDF5Storage needs h5py; PickleStorage and InMemoryStorage do not") from e
         self._h5py = h5py
         self._filename = _rank_filename(filename)

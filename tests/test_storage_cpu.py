@@ -9,7 +9,7 @@ import types
 import numpy as np
 import pytest
 
-from smcpy_b200.storage import ContextManager, InMemoryStorage, PickleStorage
+from smcpy_b200.storage import ContextManager, HDF5Storage, InMemoryStorage, PickleStorage
 
 
 def _fake_step(phi, total, n=5, seed=0):
@@ -65,3 +65,16 @@ def test_storage_context_stack():
         assert ContextManager.get_context() is a
     with pytest.raises(TypeError):
         ContextManager.get_context()
+
+
+def test_hdf5_storage_needs_h5py(tmp_path):
+    try:
+        import h5py
+        if hasattr(h5py, "File"):
+            pytest.skip("h5py present")
+    except ImportError:
+        pass
+    with pytest.raises(ImportError, match="needs h5py"):
+        HDF5Storage(tmp_path / "s.h5")
+    with pytest.raises(ValueError, match="Available modes"):
+        HDF5Storage(tmp_path / "s.h5", mode="r")
