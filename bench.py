@@ -371,6 +371,8 @@ def run_gpu(args):
                 # the 2^20-particle state is L2 resident, accepted rows are written back lazily)
                 "traffic": 33.63e6, "traffic_source": "profiles/r01_mh_kernels.md (ncu, C2 PPT=4 capture)",
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": mh_ms, "launches_timed": int(mh.size),
+                "timing": "CUDA events on the launch stream around every launch, in one extra pass of the same workload "
+                          "right after the timed region (900 event pairs inside it would perturb the headline)",
                 "share_of_step": share.get("mh_step"),
                 "note": "C2's Metropolis kernel is FP64-pipe bound (SURVEY.md 8d: ~78 flop/B), see fp64",
                 "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
