@@ -150,6 +150,17 @@ typedef struct smcb_xchg {
 int smcb_version(void);
 const char* smcb_last_error(void);
 size_t smcb_workspace_bytes(int64_t n, int32_t d);
+/* Runtime options (tuning and test aids; defaults come from the SMCB_<NAME> environment variables):
+ * they choose between kernel variants that compute the same step, so that the parity tests can pin
+ * every variant the dispatcher may take.  Names: "no_tma", "strict_proposal" (wide identity
+ * Metropolis kernel: fp64 FMAs for sqrt(s) L z instead of the tf32 tensor-core product),
+ * "linear_cfg", "persist", "no_dmma", "cov_two_pass", "no_coop", "coop_tpb", "coop_bps",
+ * "bisect_plain", "spring_ppt".  smcb_get_option returns INT64_MIN for an unknown name. */
+int smcb_set_option(const char* name, int64_t value);
+int64_t smcb_get_option(const char* name);
+/* Text description of the Metropolis kernel instantiation the calling thread launched last
+ * (template arguments, grid, RNG mode): lets a test assert WHICH variant it compared with the oracle. */
+const char* smcb_last_mh_variant(void);
 
 /* measurement aid: `blocks` x 256 threads each run 8 independent chains of `iters` FP64 FMAs
  * (16 * iters flops per thread); out holds blocks*256 doubles. */

@@ -125,7 +125,8 @@ SIGNATURES = {
     "smcb_model_register_nvrtc": [C.c_char_p, _I32, C.POINTER(C.c_int32)],
     "smcb_user_loglike": [_I32, _P, _I64, _I64, _I32, _P, _P, _P, _D, _P, _P, _P, _P],
 }
-OTHER_SYMBOLS = ["smcb_version", "smcb_last_error", "smcb_workspace_bytes"]
+OTHER_SYMBOLS = ["smcb_version", "smcb_last_error", "smcb_workspace_bytes", "smcb_set_option", "smcb_get_option",
+                 "smcb_last_mh_variant"]
 
 
 class SmcbError(RuntimeError):
@@ -150,6 +151,11 @@ def _load():
     lib.smcb_last_error.restype = C.c_char_p
     lib.smcb_workspace_bytes.argtypes = [_I64, _I32]
     lib.smcb_workspace_bytes.restype = C.c_size_t
+    lib.smcb_set_option.argtypes = [C.c_char_p, _I64]
+    lib.smcb_set_option.restype = C.c_int
+    lib.smcb_get_option.argtypes = [C.c_char_p]
+    lib.smcb_get_option.restype = _I64
+    lib.smcb_last_mh_variant.restype = C.c_char_p
     return lib
 
 
@@ -182,6 +188,31 @@ def call(name, *args, launches=None):
         if rc == 3:
             raise NotImplementedError(msg)
         raise SmcbError("%s failed (%d): %s" % (name, rc, msg))
+
+
+def set_option(name, value):
+    """Runtime option of the library (smcb_set_option); returns the previous value."""
+    old = int(lib.smcb_get_option(name.encode()))
+    if lib.smcb_set_option(name.encode(), int(value)) != 0:
+        raise SmcbError(lib.smcb_last_error().decode())
+    return old
+
+
+class option:
+    """with option("no_tma", 1): ...  -- scoped runtime option."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.old = set_option(self.name, self.value)
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.old)
+
+
+def last_mh_variant():
+    return lib.smcb_last_mh_variant().decode()
 
 
 def require_cuda():

@@ -1,5 +1,6 @@
 // api.cu -- library-level entry points: version, error text, workspace sizing.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,7 +22,70 @@ int check_launch(const char* what) {
     return SMCB_ERR_CUDA;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+Options& options() {
+    static Options o = [] {
+        Options v;
+        v.no_tma = getenv("SMCB_NO_TMA") != nullptr;
+        v.strict_proposal = env_int("SMCB_STRICT_PROPOSAL", 0);
+        v.linear_cfg = env_int("SMCB_LINEAR_CFG", -1);
+        v.persist = env_int("SMCB_PERSIST", -1);
+        v.no_dmma = getenv("SMCB_NO_DMMA") != nullptr;
+        v.cov_two_pass = getenv("SMCB_COV_TWO_PASS") != nullptr;
+        v.no_coop = getenv("SMCB_NO_COOP") != nullptr;
+        v.coop_tpb = env_int("SMCB_COOP_TPB", 0);
+        v.coop_bps = env_int("SMCB_COOP_BPS", 0);
+        v.bisect_plain = env_int("SMCB_BISECT_PLAIN", 0);
+        v.spring_ppt = env_int("SMCB_SPRING_PPT", -1);
+        return v;
+    }();
+    return o;
+}
+
+static thread_local char g_variant[256] = "";
+void note_mh_variant(const char* text) {
+    strncpy(g_variant, text, sizeof(g_variant) - 1);
+    g_variant[sizeof(g_variant) - 1] = 0;
+}
+
+struct OptEntry {
+    const char* name;
+    int Options::*field;
+};
+static const OptEntry kOptTable[] = {
+    {"no_tma", &Options::no_tma},           {"strict_proposal", &Options::strict_proposal},
+    {"linear_cfg", &Options::linear_cfg},   {"persist", &Options::persist},
+    {"no_dmma", &Options::no_dmma},         {"cov_two_pass", &Options::cov_two_pass},
+    {"no_coop", &Options::no_coop},         {"coop_tpb", &Options::coop_tpb},
+    {"coop_bps", &Options::coop_bps},       {"bisect_plain", &Options::bisect_plain},
+    {"spring_ppt", &Options::spring_ppt},
+};
+
 }  // namespace smcb
+
+extern "C" int smcb_set_option(const char* name, int64_t value) {
+    if (name)
+        for (const auto& e : smcb::kOptTable)
+            if (strcmp(e.name, name) == 0) {
+                smcb::options().*(e.field) = (int)value;
+                return SMCB_OK;
+            }
+    smcb::set_error("smcb_set_option: unknown option '%s'", name ? name : "(null)");
+    return SMCB_ERR_ARG;
+}
+
+extern "C" int64_t smcb_get_option(const char* name) {
+    if (name)
+        for (const auto& e : smcb::kOptTable)
+            if (strcmp(e.name, name) == 0) return smcb::options().*(e.field);
+    return INT64_MIN;
+}
+
+extern "C" const char* smcb_last_mh_variant(void) { return smcb::g_variant; }
 
 // FP64 FMA throughput probe: 8 independent FMA chains per thread (measurement aid for the
 // FP64-pipe-bound kernels; MEASURED_PEAKS.json has no FP64 figure).

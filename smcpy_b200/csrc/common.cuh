@@ -28,6 +28,24 @@ int check_launch(const char* what);   // cudaGetLastError -> SMCB_ERR_CUDA
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- runtime options (smcb_set_option; defaults from the SMCB_* environment variables) ----
+// Tuning / test aids: they select between kernel variants that compute the same step, so the
+// tests can pin every variant the dispatcher can take.  -1 = automatic.
+struct Options {
+    int no_tma;            // 1: never take the TMA-staged wide identity kernel
+    int strict_proposal;   // 1: wide identity kernel computes sqrt(s) L z with fp64 FMAs (no tf32 mma)
+    int linear_cfg;        // -1 auto; 0..6 force a (threads, particles/thread, dynamic) configuration
+    int persist;           // -1 auto; 0/1 one tile per block / persistent blocks
+    int no_dmma;           // 1: second covariance pass on the FP64 vector pipe
+    int cov_two_pass;      // 1: never take the one-pass shifted covariance
+    int no_coop;           // 1: launch-chain bisection / two-launch reweight
+    int coop_tpb, coop_bps;// cooperative kernels: threads per block, blocks per SM
+    int bisect_plain;      // 1: evaluate every scipy midpoint (no monotone bracketing)
+    int spring_ppt;        // -1 auto; 1/2 particles per thread in the RK4 kernel
+};
+Options& options();
+void note_mh_variant(const char* text);
+
 // grid sized in multiples of the SM count (persistent-style grid-stride kernels)
 inline int grid_for(int64_t n, int threads, int items_per_thread, int max_blocks_per_sm) {
     int64_t per_block = (int64_t)threads * items_per_thread;

@@ -494,8 +494,10 @@ __device__ __forceinline__ double ll_multisource(const MhArgs& a, const double (
 //       DYN: persistent blocks pull tiles from an atomic counter (a.flags[1]; a.flags[2] is the
 //       ticket with which the last block resets both) -- removes the tail of the FP64-bound kernels.
 //       MULTI: MultiSourceNormal likelihood (segment table in the problem).
+//       STRICT (with TMA): the increment sqrt(s) L z is accumulated with fp64 FMAs instead of the tf32
+//       tensor-core product (option "strict_proposal"); same normals, same Philox counters.
 template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
-          bool DYN = false, bool MULTI = false>
+          bool DYN = false, bool MULTI = false, bool STRICT = false>
 __global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT, TMA))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -512,9 +514,9 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         for (int e = threadIdx.x; e < DMAX * DMAX; e += TPB) {
             const int j = e / DMAX, r = e - j * DMAX;
             const double v = (r < d && j <= r) ? a.chol[r * d + j] : 0.0;
-            if (!TMA) sLt[e] = v;
+            if (!TMA || STRICT) sLt[e] = v;
         }
-        if (TMA) {
+        if (TMA && !STRICT) {
             // TMA variant: the increment L z goes through the tensor cores (mma.sync m16n8k8, tf32
             // inputs, fp32 accumulation).  B fragments of the lower-triangular 8x8 blocks of L, in
             // fragment order: block q = (nb, kb <= nb), lane (g, t) holds L[nb*8+g][kb*8+t], [..][kb*8+t+4]
@@ -587,14 +589,15 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             const int64_t i = tile * per_tile + threadIdx.x;
             valid[0] = i < a.n;
             idx[0] = valid[0] ? i : 0;
+            const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[0]);
+            float delta[STRICT ? 1 : DMAX];                              // first sqrt(s) z, then sqrt(s) L z
+            if constexpr (!STRICT) {
             const float* sB = reinterpret_cast<const float*>(sLt);      // tf32 B fragments of L (see above)
             constexpr int NB = DMAX >= 8 ? DMAX / 8 : 1;
             constexpr int kZLd = DMAX + 4;                               // padded row: conflict-free LDS.128 / fragment loads
             float* zb = reinterpret_cast<float*>(stage + (DMAX + 2) * TPB) + (threadIdx.x >> 5) * 16 * kZLd;
             const int lane = threadIdx.x & 31, fg = lane >> 2, ft = lane & 3;
             const float scf = (float)sc;
-            float delta[DMAX];                                           // first sqrt(s) z, then sqrt(s) L z
-            const uint64_t pid = (uint64_t)(a.rng.id_offset + idx[0]);
 #pragma unroll
             for (int c = 0; c + 15 < DMAX; c += 16) {
                 const Float16 zz = gen_normals16(a.rk.k[0], a.rk.k[1], pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
@@ -669,10 +672,12 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                 }
                 __syncwarp();
             }
+            }  // !STRICT
             mbar_wait(&mbar, tma_phase);
             tma_phase ^= 1u;
 #pragma unroll
-            for (int c = 0; c < DMAX; ++c) th[0][c] = stage[c * TPB + threadIdx.x] + (double)delta[c];
+            for (int c = 0; c < DMAX; ++c)
+                th[0][c] = stage[c * TPB + threadIdx.x] + (STRICT ? 0.0 : (double)delta[STRICT ? 0 : c]);
             ll_old[0] = stage[d * TPB + threadIdx.x];
             lp_old[0] = stage[(d + 1) * TPB + threadIdx.x];
             // every thread reports that it has drained the stage; only the issuing thread waits for
@@ -681,6 +686,26 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             if (threadIdx.x == 0) {
                 mbar_wait(&mbar_empty, tma_phase ^ 1u);
                 if (tile + gridDim.x < n_tiles) tma_issue(tile + gridDim.x);
+            }
+            if constexpr (STRICT) {
+                // fp64 accumulation of sqrt(s) L z, column-outer, on the same normals the tf32 variant draws
+#pragma unroll
+                for (int c = 0; c + 15 < DMAX; c += 16) {
+                    const Float16 zz = gen_normals16(a.rk.k[0], a.rk.k[1], pid, (uint32_t)(c >> 2), (uint32_t)a.rng.stream);
+                    const float zq[16] = {zz.a.x, zz.a.y, zz.a.z, zz.a.w, zz.b.x, zz.b.y, zz.b.z, zz.b.w,
+                                          zz.c.x, zz.c.y, zz.c.z, zz.c.w, zz.d.x, zz.d.y, zz.d.z, zz.d.w};
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int j = c + k;
+                        const double zs = sc * (double)zq[k];
+#pragma unroll
+                        for (int r2 = (j & ~1); r2 < DMAX; r2 += 2) {       // above the diagonal: 0
+                            const double2 l2 = *reinterpret_cast<const double2*>(&sLt[j * DMAX + r2]);
+                            th[0][r2] = fma(l2.x, zs, th[0][r2]);
+                            if (r2 + 1 < DMAX) th[0][r2 + 1] = fma(l2.y, zs, th[0][r2 + 1]);
+                        }
+                    }
+                }
             }
         } else {
 #pragma unroll
@@ -1025,7 +1050,7 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
 }
 
 template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
-          bool DYN = false, bool MULTI = false>
+          bool DYN = false, bool MULTI = false, bool STRICT = false>
 static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     const size_t smem = mh_smem_bytes(&a.prob) + (size_t)DMAX * DMAX * sizeof(double) +
                         (TMA ? (size_t)(64 + (DMAX + 2) * TPB) * sizeof(double) +
@@ -1033,7 +1058,7 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     if (TMA) {
         static bool attr = false;
         if (!attr) {
-            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI>,
+            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr = true;
         }
@@ -1042,7 +1067,7 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI>, TPB,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT>, TPB,
                                                           smem) != cudaSuccess || nb < 1)
             nb = 1;
         blocks_per_sm = nb;
@@ -1052,11 +1077,20 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     // persistent blocks (stage L / data once, loop over tiles) for the bandwidth-bound identity
     // model; one tile per block for the FP64-bound models, where the hardware block scheduler
     // balances the tail better than a static tile loop (SMCB_PERSIST overrides: tuning aid)
-    static const int persist_env = getenv("SMCB_PERSIST") ? atoi(getenv("SMCB_PERSIST")) : -1;
+    const int persist_env = options().persist;
     const bool persist = DYN || (persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL));
     const int64_t cap = persist ? (int64_t)kNumSMs * blocks_per_sm : n_tiles;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI><<<grid, TPB, smem, s>>>(a);
+    if (MODE == 1) {
+        char txt[200];
+        snprintf(txt, sizeof(txt),
+                 "mh_kernel<kind=%d,dmax=%d,tpb=%d,ppt=%d,exact=%d,tma=%d,prop=%d,dyn=%d,multi=%d,strict=%d> grid=%u "
+                 "rng=%d n=%lld",
+                 KIND, DMAX, TPB, PPT, (int)EXACT, (int)TMA, (int)PROP, (int)DYN, (int)MULTI, (int)STRICT, grid,
+                 (int)a.rng.mode, (long long)a.n);
+        note_mh_variant(txt);
+    }
+    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT><<<grid, TPB, smem, s>>>(a);
     return check_launch("mh_kernel");
 }
 
@@ -1069,11 +1103,14 @@ static int launch_cfg(const MhArgs& a, cudaStream_t s) {
             // TMA-staged variant for the bandwidth-bound wide identity kernels: needs 16-byte
             // aligned column segments (even n and stride) and enough tiles to pipeline
             if constexpr (KIND == K_IDENTITY_NORMAL && MODE == 1 && DMAX >= 16 && PPT == 1) {
-                static const bool no_tma = getenv("SMCB_NO_TMA") != nullptr;     // tuning aid
+                const bool no_tma = options().no_tma != 0;                       // tuning / test aid
                 const bool aligned = ((((uintptr_t)a.params | (uintptr_t)a.ll | (uintptr_t)a.lp) & 15) == 0) &&
                                      (a.stride % 2 == 0) && (a.n % 2 == 0);
-                if (!no_tma && aligned && a.rng.mode == 0 && a.n >= (int64_t)kNumSMs * 8 * TPB)
+                if (!no_tma && aligned && a.rng.mode == 0 && a.n >= (int64_t)kNumSMs * 8 * TPB) {
+                    if (options().strict_proposal)
+                        return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true, true, false, false, false, true>(a, s);
                     return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true, true>(a, s);
+                }
             }
             return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true>(a, s);
         }
@@ -1099,7 +1136,7 @@ static int launch_one(const MhArgs& a, cudaStream_t s) {
     if constexpr (KIND == K_LINEAR_NORMAL && (MODE == 0 || MODE == 1)) {
         // several particles per thread amortise the shared-memory data reads; keep at least
         // ~4 tiles per SM so small problems still fill the chip
-        static const int cfg = getenv("SMCB_LINEAR_CFG") ? atoi(getenv("SMCB_LINEAR_CFG")) : -1;   // tuning aid
+        const int cfg = options().linear_cfg;                                                      // tuning / test aid
         if (cfg == 0) return launch_cfg<KIND, DMAX, MODE, kMhThreads, 1>(a, s);
         if (cfg == 1) return launch_cfg<KIND, DMAX, MODE, 128, 2>(a, s);
         if (cfg == 2) return launch_cfg<KIND, DMAX, MODE, 128, 4>(a, s);

@@ -540,7 +540,7 @@ extern "C" int smcb_weighted_sums2(const double* params, int64_t stride, const d
     double* partials = (double*)((char*)ws + kWsPartials);
     cudaStream_t s = as_stream(stream);
     int grid;
-    static const bool no_dmma = getenv("SMCB_NO_DMMA") != nullptr;      // tuning aid
+    const bool no_dmma = options().no_dmma != 0;                        // tuning / test aid
     const bool aligned = ((((uintptr_t)params | (uintptr_t)w) & 15) == 0) && (stride % 2 == 0) && (n % 2 == 0);
     if (!no_dmma && d > 8 && aligned && n >= (int64_t)kNumSMs * kWP) {
         const int nb8 = (d + 7) / 8, nbu8 = nb8 * (nb8 + 1) / 2, dp = nb8 * 8;

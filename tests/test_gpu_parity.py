@@ -861,9 +861,11 @@ def test_full_size_c2_step_properties(sb):
     np.testing.assert_array_equal(st2.params_host(), x)
 
 
-def test_wide_identity_kernel_tma_path_vs_oracle(sb):
-    """2^18 particles x d=32 takes the persistent, TMA-staged (cp.async.bulk + mbarrier) variant
-    of the fused Metropolis kernel; replayed draws against the oracle, 1e-10."""
+def test_wide_identity_kernel_replay_vs_oracle(sb):
+    """2^18 particles x d=32 with REPLAYED draws (rng.mode 1): the dispatcher takes the persistent
+    exact-width kernel WITHOUT the TMA stage (the TMA / tf32 variant needs the native generator, see
+    test_tma_wide_kernel_*); against the oracle, 1e-10.  The variant is asserted."""
+    from smcpy_b200 import _lib
     problem = configs.gauss_problem(32)
     n, K = 1 << 18, 2
     rng0 = np.random.default_rng(3)
@@ -875,9 +877,179 @@ def test_wide_identity_kernel_tma_path_vs_oracle(sb):
     mc, kernel = make_b200(problem, rng=np.random.default_rng(77))
     kernel.path.phi = 0.8
     g_theta, g_ll = mc.smc_metropolis(theta, K, cov)
+    v = _lib.last_mh_variant()
+    assert "kind=2,dmax=32" in v and "exact=1,tma=0" in v and "rng=1" in v, v
     np.testing.assert_allclose(g_theta, o_theta, rtol=RTOL, atol=1e-12)
     np.testing.assert_allclose(g_ll, o_ll, rtol=RTOL)
     assert 0.05 * n < accepts[0] < 0.95 * n
+
+
+# ------------------------------------------------------------------ the instantiations bench.py times
+def _chunked_loglike(chunk=1 << 16):
+    """oracle log_likelihood evaluated in row chunks (rows are independent): bounds the (N, M)
+    temporaries of the numpy restatement at 2^20 x 1000."""
+    orig = orc.log_likelihood
+
+    def ll(problem, theta):
+        if theta.shape[0] <= chunk:
+            return orig(problem, theta)
+        return np.vstack([orig(problem, theta[i:i + chunk]) for i in range(0, theta.shape[0], chunk)])
+    return orig, ll
+
+
+@pytest.mark.parametrize("n, cfg, want", [
+    (1 << 20, -1, "tpb=128,ppt=4,exact=1,tma=0,prop=0,dyn=1"),     # what bench.py's C2 pass launches
+    (1 << 18, 3, "tpb=256,ppt=4,exact=1,tma=0,prop=0,dyn=0"),      # static 1024-particle tiles
+    (1 << 18, 2, "tpb=128,ppt=4,exact=1,tma=0,prop=0,dyn=0"),
+    (1 << 18, 1, "tpb=128,ppt=2,exact=1,tma=0,prop=0,dyn=0"),
+    (1 << 18, 5, "tpb=64,ppt=4,exact=1,tma=0,prop=0,dyn=1"),
+])
+def test_c2_timed_instantiations_replay_vs_oracle(sb, monkeypatch, n, cfg, want):
+    """The linear-model Metropolis kernel in the configurations the dispatcher takes at benchmark
+    sizes (several particles per thread, dynamic tiles), on the C2 problem (1000 data points),
+    replayed normals/uniforms, against the oracle's smc_metropolis
+    (smcpy/mcmc/vector_mcmc.py:46-62,168-183): 1e-10.  The launched variant is asserted."""
+    import bench
+    from smcpy_b200 import _lib
+    problem = bench.c2_problem()
+    K = 2
+    rng0 = np.random.default_rng(n + cfg)
+    # a cloud around the posterior mode, wide enough that priors never bind, plus out-of-support proposals
+    theta = np.column_stack([rng0.normal(2.0, 0.3, n), rng0.normal(3.5, 0.5, n)])
+    theta[:7] = [[5.99, 5.99], [-5.99, -5.99], [5.99, -5.99], [0.0, 0.0], [2.0, 3.5], [-5.99, 5.99], [5.0, 5.0]]
+    cov = np.array([[0.02, -0.01], [-0.01, 0.05]])
+    phi = 0.05
+    orig, chunked = _chunked_loglike()
+    monkeypatch.setattr(orc, "log_likelihood", chunked)
+    accepts = []
+    o_theta, o_ll = orc.smc_metropolis(problem, theta, K, cov, phi, np.random.default_rng(5), trace=accepts)
+    monkeypatch.setattr(orc, "log_likelihood", orig)
+    mc, kernel = make_b200(problem, rng=np.random.default_rng(5))
+    kernel.path.phi = phi
+    with _lib.option("linear_cfg", cfg):
+        g_theta, g_ll = mc.smc_metropolis(theta, K, cov)
+        v = _lib.last_mh_variant()
+    assert "kind=0,dmax=2," in v and want in v and "rng=1" in v, v
+    np.testing.assert_allclose(g_theta, o_theta, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(g_ll, o_ll, rtol=RTOL)
+    assert 0.05 * n < accepts[0] < 0.95 * n and 0.05 * n < accepts[1] < 0.95 * n
+
+
+def _wide_state(sb, d, n, seed):
+    """Posterior-like cloud for the d-dim Gaussian target + a proposal factor with ~25-45 % acceptance."""
+    from smcpy_b200 import engine
+    problem = configs.gauss_problem(d)
+    mcmc, kernel = make_b200(problem, rng=seed)
+    rng = np.random.default_rng(1000 + d)
+    x0 = problem["data"][None, :] + rng.normal(0, 1.0, (n, d))
+    x0[:5] = 9.999                                   # next to the prior bound: proposals fall outside
+    a = rng.normal(0, 1, (d, d)) * 0.15 + np.eye(d)
+    chol = np.linalg.cholesky(a @ a.T * (2.38 ** 2 / d) * 0.5)
+    return problem, mcmc, x0, chol
+
+
+def _one_wide_step(sb, mcmc, x0, chol, phi, seed, opts, steps=1):
+    from smcpy_b200 import _lib, engine
+    n, d = x0.shape
+    st = _state(sb, n, d)
+    st.set_params_host(x0)
+    engine.eval_incoming(st, mcmc.spec)
+    st.chol.copy_(engine.dev(chol))
+    saved = [(k, _lib.set_option(k, v)) for k, v in opts.items()]
+    try:
+        ratio = engine.mutate(st, mcmc.spec, steps, engine.make_path(phi, phi, 1.0), engine.PhiloxRNG(seed))
+        variant = _lib.last_mh_variant()
+    finally:
+        for k, v in saved:
+            _lib.set_option(k, v)
+    acc = st.accept_counts[:steps].cpu().numpy().copy()
+    out = dict(x=st.params_host(), ll=st.ll.cpu().numpy().copy(), lp=st.lp.cpu().numpy().copy(),
+               moved=st.moved.cpu().numpy().astype(bool), acc=acc, ratio=ratio, variant=variant)
+    engine.eval_incoming(st, mcmc.spec)               # fresh evaluation of the particles the kernel left
+    out["ll_fresh"], out["lp_fresh"] = st.ll.cpu().numpy().copy(), st.lp.cpu().numpy().copy()
+    return out
+
+
+@pytest.mark.parametrize("phi", [0.3, 1.0])
+@pytest.mark.parametrize("d", [16, 32])
+def test_tma_wide_kernel_accept_reject_vs_plain_kernel(sb, d, phi):
+    """The kernel behind the C5 / north-star numbers -- persistent, TMA-staged, sqrt(s) L z on the
+    tensor cores (tf32) -- at phi > 0 where proposals are accepted AND rejected, n = 2^18 >= its
+    dispatch threshold, native generator.  Checked against (i) a fresh evaluation of the particles it
+    leaves (resident ll / lp columns), (ii) the plain fp64 kernel on the SAME Philox counters: the two
+    draw the same normals, so they must take the same accept/reject decision for all but the rows
+    whose ratio sits within the tf32 perturbation of u, and accepted rows must agree to the tf32
+    rounding of the increment; (iii) the strict variant (fp64 FMAs inside the TMA kernel), which must
+    agree with the plain kernel to the fp32 rounding of the normals.  Reference semantics:
+    smcpy/mcmc/vector_mcmc.py:124-151,168-183."""
+    n = 1 << 18
+    problem, mcmc, x0, chol = _wide_state(sb, d, n, 3)
+    tma = _one_wide_step(sb, mcmc, x0, chol, phi, 11, {})
+    plain = _one_wide_step(sb, mcmc, x0, chol, phi, 11, {"no_tma": 1})
+    strict = _one_wide_step(sb, mcmc, x0, chol, phi, 11, {"strict_proposal": 1})
+    assert "tma=1" in tma["variant"] and "strict=0" in tma["variant"] and "dmax=%d" % d in tma["variant"]
+    assert "tma=0" in plain["variant"] and "exact=1" in plain["variant"]
+    assert "tma=1" in strict["variant"] and "strict=1" in strict["variant"]
+    scale = np.sqrt(np.diag(chol @ chol.T))
+    for r in (tma, plain, strict):
+        assert 0.05 * n < r["acc"][0] < 0.85 * n, r["acc"]
+        assert int(r["moved"].sum()) == int(r["acc"][0]) and r["ratio"] == r["acc"][0] / n
+        np.testing.assert_allclose(r["ll"], r["ll_fresh"], rtol=1e-12)     # resident == fresh (both fp64 of x)
+        np.testing.assert_array_equal(r["lp"], r["lp_fresh"])
+        assert np.all(np.isfinite(r["lp"])) and not r["moved"][:5].all()   # nothing accepted outside the support
+        np.testing.assert_array_equal(r["x"][~r["moved"]], x0[~r["moved"]])  # rejected rows untouched
+    # (ii) tf32 variant against the plain kernel
+    flips = float(np.mean(tma["moved"] != plain["moved"]))
+    assert flips < 5e-3, flips                      # ratio within ~1e-3 relative of u: a few per thousand
+    both = tma["moved"] & plain["moved"]
+    assert np.max(np.abs(tma["x"][both] - plain["x"][both]) / scale) < 2e-2
+    assert np.sqrt(np.mean(((tma["x"][both] - plain["x"][both]) / scale) ** 2)) < 1.5e-3
+    sigma = np.sqrt(n * 0.25)
+    assert abs(float(tma["acc"][0]) - float(plain["acc"][0])) < 3 * sigma
+    # (iii) strict variant: fp64 L z on the same fp32 normals (two Box-Muller codings: 1e-6)
+    assert float(np.mean(strict["moved"] != plain["moved"])) < 2e-4
+    both = strict["moved"] & plain["moved"]
+    assert np.max(np.abs(strict["x"][both] - plain["x"][both]) / scale) < 1e-4
+
+
+def test_tma_wide_kernel_detailed_balance_many_steps(sb):
+    """50 steps of the TMA / tf32 kernel at phi = 1 started IN the posterior N(y, I) must leave it
+    invariant (Metropolis detailed balance with a symmetric proposal): mean, variance and the
+    log-likelihood column stay put; an asymmetric or biased increment would drift."""
+    n, d = 1 << 18, 32
+    problem, mcmc, x0, chol = _wide_state(sb, d, n, 4)
+    x0[:5] = x0[5:10]
+    r = _one_wide_step(sb, mcmc, x0, chol, 1.0, 23, {}, steps=50)
+    assert "tma=1" in r["variant"]
+    y = problem["data"]
+    assert np.max(np.abs(r["x"].mean(axis=0) - y)) < 6 / np.sqrt(n) * 1.5
+    assert np.max(np.abs(r["x"].var(axis=0) - 1.0)) < 0.015
+    assert float(r["moved"].mean()) > 0.999
+    np.testing.assert_allclose(r["ll"], r["ll_fresh"], rtol=1e-12)
+
+
+def test_c5_adaptive_runs_vs_analytic_evidence(sb):
+    """Eight seeded full AdaptiveSampler runs of the C5 model at 2^18 particles (the size class whose
+    mutation kernel is the TMA / tf32 variant) against the closed forms of SURVEY.md appendix B:
+    log-evidence -32 log 20, posterior N(y, I).  Reference loop: smcpy/smc/samplers.py:194-248."""
+    from smcpy_b200 import _lib
+    problem = configs.gauss_problem(32)
+    mlls, means, stds = [], [], []
+    for seed in range(8):
+        mcmc, kernel = make_b200(problem, rng=100 + seed)
+        smc = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+        smc._result = sb.InMemoryStorage(retain=1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            steps, mll = smc.sample(1 << 18, 10, target_ess=0.8, resample_rng=sb.standard if seed % 2 else sb.stratified)
+        assert "tma=1" in _lib.last_mh_variant() and smc.phi_sequence[-1] == 1.0
+        mlls.append(mll[-1])
+        means.append(steps[-1].compute_mean(package=False))
+        stds.append(steps[-1].compute_std_dev(package=False))
+    assert np.mean(mlls) == pytest.approx(-32 * np.log(20.0), abs=0.06), mlls
+    assert np.std(mlls) < 0.12
+    assert np.max(np.abs(np.mean(means, axis=0) - problem["data"])) < 0.01
+    assert np.max(np.abs(np.mean(stds, axis=0) - 1.0)) < 0.01
 
 
 # ------------------------------------------------------------------ host phi policies / step operators
