@@ -15,7 +15,15 @@
  *     device scalars and read at step boundaries;
  *   - return value 0 = ok, otherwise an SMCB_ERR_* code; smcb_last_error() gives text;
  *   - particles are structure-of-arrays: parameter c of particle i is
- *     params[c * stride + i]; all arithmetic is IEEE fp64; indices are int64.
+ *     params[c * stride + i]; indices are int64.
+ *   - precision: every quantity the reference computes -- priors, model, log-likelihood, path
+ *     arithmetic, acceptance ratio, weights, ESS, phi, CDF, covariance, Cholesky -- is IEEE fp64.
+ *     The only narrower arithmetic is inside the NATIVE proposal generator (rng.mode 0), which has no
+ *     counterpart in the reference (its draws come from numpy): standard normals are Box-Muller in
+ *     fp32 (24-bit radius uniform, |z| <= 5.9), and the wide identity kernels (d >= 16) form the
+ *     increment sqrt(s) L z on the tensor cores with tf32 inputs / fp32 accumulation unless the
+ *     option "strict_proposal" selects fp64 FMAs.  A Metropolis proposal only has to be symmetric,
+ *     which both keep exactly; replay mode (rng.mode 1) uses the host's fp64 normals throughout.
  */
 #ifndef SMCB200_H
 #define SMCB200_H
@@ -185,6 +193,18 @@ int smcb_fill_f64(double* dst, int64_t n, double value, void* stream);
 int smcb_reweight(int64_t n, const double* ll, const double* lp, const double* lq,
                   const double* log_w_in, int64_t n_global, const smcb_path_t* path,
                   double* log_w_out, double* w_out, double* scalars_out, void* ws, void* stream);
+/* The same update in ONE cooperative launch (updater.py:97-133 incl. the resampling test :106):
+ * partial sums -> grid barrier -> [world > 1: rank triples exchanged over NVLink peer memory inside
+ * the kernel, x as for smcb_ess_search] -> scalars_out; log_w_out / w_out are written by the same
+ * launch ONLY IF the step will not resample (ESS >= ess_threshold * n_global; ess_threshold < 0:
+ * always) -- a resampling step takes its weights from smcb_cdf_scan_weights instead and never
+ * materialises them.  lp may be NULL when the summed log-prior is one constant (lp_const).
+ * scalars_out[6] = 1 if the weights were written, [7] = -1 if a peer never answered.
+ * Algorithmic bytes per particle: 8 (ll) + 8 per optional input column, + 16 when weights are written. */
+int smcb_reweight_fused(int64_t n, const double* ll, const double* lp, double lp_const, const double* lq,
+                        const double* log_w_in, int64_t n_global, const smcb_path_t* path, double ess_threshold,
+                        double* log_w_out, double* w_out, double* scalars_out, void* ws,
+                        const smcb_xchg_t* x /* NULL: single GPU */, void* stream);
 /* elementwise path values (host-facing GeometricPath wrappers): mode 0 = logpdf at phi
  * (paths.py:81-84), mode 1 = inc_log_weights phi_prev -> phi (paths.py:86-91) */
 int smcb_path_eval(int64_t n, const double* ll, const double* lp, const double* lq,
@@ -209,6 +229,31 @@ int smcb_reweight_finalize(int64_t n, const double* ll, const double* lp, const 
 int smcb_ess_bisect(int64_t n, const double* ll, const double* lp, const double* lq,
                     double lp_const, double phi_old, double lambda, double target_ess,
                     int64_t n_global, double* state, void* ws, void* stream);
+/* The search as the samplers call it.  Same result as smcb_ess_bisect -- scipy's decision sequence --
+ * in ~8-12 passes over the particles instead of ~43: ESS(phi) is non-increasing in phi, so the sign
+ * scipy would compute at a midpoint is known without evaluating it whenever an evaluated point with a
+ * clearly positive margin (> 1e-12 target N) lies above it, or one with a clearly negative margin
+ * below it.  The kernel first closes such a bracket around the root (safeguarded Newton on log ESS in
+ * log(phi - phi_old), started from hint_dphi = the previous step's phi increment when > 0, then two
+ * probes either side of the converged estimate), then replays bisect.c midpoint by midpoint and
+ * evaluates only the midpoints inside the bracket.  Paths with a proposal column (lq != NULL: the
+ * increment is not one exponential family in phi) and option "bisect_plain" evaluate every midpoint.
+ * x != NULL: multi-GPU form -- after every pass the ranks exchange their partial sums over NVLink
+ * peer memory inside the one cooperative launch (x->peer_slots[r]: rank r's symmetric buffer of
+ * smcb_xchg_slot_words() uint64, zero-initialised once; x->gen must increase with every call that uses
+ * the buffer; global_counts / ticket unused).  state[2] = -1 if a peer never answered (time-out option
+ * "xchg_timeout_s", default 30 s); state[10] = passes over the particles; state[11..12] = the bracket. */
+int smcb_ess_search(int64_t n, const double* ll, const double* lp, const double* lq, double lp_const,
+                    double phi_old, double lambda, double target_ess, int64_t n_global, double hint_dphi,
+                    double* state, void* ws, const smcb_xchg_t* x, void* stream);
+int smcb_xchg_slot_words(void);
+/* TEST HOOKS (no product path calls them): the search's state machine -- the same C++ the kernel runs --
+ * driven on the HOST with sums computed by plain CPU loops over a host array ll, so that its decisions
+ * can be compared with scipy.optimize.bisect on smcb_test_search_margin without a GPU.
+ * trace_out (optional, host): the phi evaluated in each pass. */
+double smcb_test_search_margin(const double* ll_host, int64_t n, double phi_old, double x, double target);
+int smcb_test_search_host(const double* ll_host, int64_t n, double phi_old, double target, double hint,
+                          int32_t plain, double* state_out, double* trace_out, int32_t trace_len);
 /* multi-GPU pieces: begin -> { partial -> [all-gather] -> update } x smcb_ess_bisect_max_iters */
 int smcb_ess_bisect_begin(double phi_old, double* state, void* stream);
 int smcb_ess_partial(int64_t n, const double* ll, const double* lp, const double* lq,
@@ -245,6 +290,45 @@ int smcb_resample_exponentials(int64_t first, int64_t count, int64_t n_global, u
 int smcb_resample_spacings_finish(const double* t, int64_t n, const double* offset, const double* total,
                                   int64_t n_global, uint64_t seed, uint64_t stream_id, double* u_out,
                                   void* stream);
+/* running sums of the same exponentials without the intermediate array: t_out[i] = sum_{j<=i} e_j over
+ * this rank's `count` slots (steps 1 + 2 above in one scan whose inputs are generated in registers) */
+int smcb_resample_exponential_sums(int64_t first, int64_t count, int64_t n_global, uint64_t seed,
+                                   uint64_t stream_id, double* t_out, double* total_out /* or NULL: t_out[count-1] */,
+                                   void* ws, void* stream);
+/* CDF of the normalised weights of a step that resamples, straight from the resident columns: the
+ * look-back scan recomputes w_i = exp((log_w_in_i + inc_i - max) - log S1) (arguments as for
+ * smcb_reweight_fused, scalars = its scalars_out) instead of reading a weight array
+ * (particles.py:141-150 + np.cumsum, updater.py:152) */
+int smcb_cdf_scan_weights(int64_t n, const double* ll, const double* lp, double lp_const, const double* lq,
+                          const double* log_w_in, int64_t n_global, const smcb_path_t* path,
+                          const double* scalars, double* cdf, double* total_out /* or NULL: cdf[n-1] */, void* ws,
+                          void* stream);
+/* Resampling with sorted uniforms in one pass (updater.py:135-165 for the native generator): uniforms of
+ * the global output slots evaluated on the fly (resampler_rngs.py:4-9; STANDARD: U_(k) = S_k / S_(N+1)
+ * from the running sums t), ancestor search confined to the CDF window of each 1024-slot tile
+ * (merge-path style partition), gather of all n_cols columns, distinct-ancestor count -- no uniform,
+ * index or flag arrays.  Sharded particles (world > 1, equal contiguous blocks): this rank OWNS the
+ * slots whose uniform falls into its CDF segment [O_r, O_r+1) -- a contiguous slot range it derives from
+ * `totals` -- and writes the selected rows straight into the SoA buffer of the rank holding each slot
+ * (dst_peer[q], peer-mapped over NVLink); STANDARD reads the running sums of the slot's rank through
+ * t_peer[q].  The caller all-gathers `totals` before and synchronises the ranks after. */
+typedef struct smcb_resample {
+    int32_t kind;                           /* SMCB_RESAMPLE_* */
+    int32_t world, rank, n_cols;
+    int64_t n_local, n_global;              /* n_global == world * n_local */
+    uint64_t seed, stream_id;
+    const double* cdf;                      /* local inclusive scan of the globally normalised weights */
+    const double* totals;                   /* device, world x 2, rank order: (cdf[n_local-1], t[n_local-1]); may be
+                                               NULL when world == 1 */
+    const double* t_peer[SMCB_MAX_RANKS];   /* STANDARD: every rank's running sums of the exponentials */
+    const double* src;                      /* local SoA columns */
+    int64_t src_stride;
+    double* dst_peer[SMCB_MAX_RANKS];       /* every rank's destination SoA buffer */
+    int64_t dst_stride;
+    int64_t* idx_out;                       /* optional, world == 1: ancestor of every slot */
+    int64_t* n_unique_out;                  /* device: distinct local ancestors selected by this rank */
+} smcb_resample_t;
+int smcb_resample_fused(const smcb_resample_t* r, void* ws, void* stream);
 /* inclusive prefix sum of normalised weights -> CDF (np.cumsum, updater.py:152) */
 int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mode, void* ws, void* stream);
 /* idx_k = #{j : cdf_j <= u_k}  (np.digitize / searchsorted side='right', updater.py:152),
@@ -270,6 +354,20 @@ int smcb_gather_p2p(const double* src, int64_t src_stride, const int64_t* idx, i
 /* number of distinct ancestors (updater.py:154-165); flags = n_src bytes of scratch */
 int smcb_count_unique(const int64_t* idx, int64_t n_idx, int64_t n_src, int64_t* count_out,
                       void* ws, void* stream);
+
+/* ---- small rank records over NVLink peer memory (multi-GPU plumbing of the path) ---------------- */
+/* All-gather (reduce = 0: dst[r * n_vals + k] = rank r's src[k]) or all-reduce (reduce = 1: dst[k] = sum over
+ * ranks in rank order, bit-identical on every rank) of n_vals <= smcb_xchg_max_vals() doubles in ONE
+ * single-block kernel: every rank stores its record into a slot of every peer's symmetric buffer
+ * (x->peer_slots[r]: smcb_xchg_big_slot_words() uint64 each, zero-initialised once), fences, stores the
+ * flag x->gen (must increase by one with every call on this buffer) and waits for the `world` flags in
+ * its own memory.  Replaces the MPI allgather / bcast of the reference's parallel path
+ * (smcpy/mcmc/parallel_vector_mcmc.py:36-47, smcpy/utils/mpi_utils.py) and the small NCCL collectives for
+ * weight totals, covariance partial sums, counts and error flags.  *status |= 1 on time-out. */
+int smcb_xchg_big_slot_words(void);
+int smcb_xchg_max_vals(void);
+int smcb_xchg_allgather(const smcb_xchg_t* x, const double* src, int32_t n_vals, double* dst, int32_t reduce,
+                        int32_t* status, void* stream);
 
 /* ---- weighted mean / covariance (particles.py:189-198, np.cov ddof=0 aweights) ---- */
 /* mean_out[d], cov_out[d*d] (device).  sums_out (device, 1+d+d*d doubles) receives the raw

@@ -63,6 +63,14 @@ class Xchg(C.Structure):
                 ("peer_slots", C.c_void_p * MAX_RANKS), ("global_counts", C.c_void_p), ("ticket", C.c_void_p)]
 
 
+class Resample(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("n_cols", C.c_int32),
+                ("n_local", C.c_int64), ("n_global", C.c_int64), ("seed", C.c_uint64), ("stream_id", C.c_uint64),
+                ("cdf", C.c_void_p), ("totals", C.c_void_p), ("t_peer", C.c_void_p * MAX_RANKS),
+                ("src", C.c_void_p), ("src_stride", C.c_int64), ("dst_peer", C.c_void_p * MAX_RANKS),
+                ("dst_stride", C.c_int64), ("idx_out", C.c_void_p), ("n_unique_out", C.c_void_p)]
+
+
 class Rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("seed", C.c_uint64), ("stream", C.c_uint64),
                 ("id_offset", C.c_int64), ("z", C.c_void_p), ("u", C.c_void_p)]
@@ -122,11 +130,21 @@ SIGNATURES = {
     "smcb_mh_accept": [_PP(Path), _P, _P, _I64, _I32, _I64, _P, _P, _P, _P, _P, _P, _I32, _PP(Rng), _P],
     "smcb_ess_bisect_xchg": [_I64, _P, _P, _P, _D, _D, _D, _D, _I64, _P, _P, _PP(Xchg), _P],
     "smcb_exp_probe": [_P, _P, _I64, _P],
+    "smcb_reweight_fused": [_I64, _P, _P, _D, _P, _P, _I64, _PP(Path), _D, _P, _P, _P, _P, _PP(Xchg), _P],
+    "smcb_ess_search": [_I64, _P, _P, _P, _D, _D, _D, _D, _I64, _D, _P, _P, _PP(Xchg), _P],
+    "smcb_xchg_slot_words": [],
+    "smcb_test_search_host": [_P, _I64, _D, _D, _D, _I32, _P, _P, _I32],
+    "smcb_resample_exponential_sums": [_I64, _I64, _I64, _U64, _U64, _P, _P, _P, _P],
+    "smcb_cdf_scan_weights": [_I64, _P, _P, _D, _P, _P, _I64, _PP(Path), _P, _P, _P, _P, _P],
+    "smcb_xchg_big_slot_words": [],
+    "smcb_xchg_max_vals": [],
+    "smcb_xchg_allgather": [_PP(Xchg), _P, _I32, _P, _I32, _P, _P],
+    "smcb_resample_fused": [_PP(Resample), _P, _P],
     "smcb_model_register_nvrtc": [C.c_char_p, _I32, C.POINTER(C.c_int32)],
     "smcb_user_loglike": [_I32, _P, _I64, _I64, _I32, _P, _P, _P, _D, _P, _P, _P, _P],
 }
 OTHER_SYMBOLS = ["smcb_version", "smcb_last_error", "smcb_workspace_bytes", "smcb_set_option", "smcb_get_option",
-                 "smcb_last_mh_variant"]
+                 "smcb_last_mh_variant", "smcb_test_search_margin"]
 
 
 class SmcbError(RuntimeError):
@@ -156,6 +174,8 @@ def _load():
     lib.smcb_get_option.argtypes = [C.c_char_p]
     lib.smcb_get_option.restype = _I64
     lib.smcb_last_mh_variant.restype = C.c_char_p
+    lib.smcb_test_search_margin.argtypes = [_P, _I64, _D, _D, _D]
+    lib.smcb_test_search_margin.restype = _D
     return lib
 
 
@@ -172,7 +192,8 @@ class _LazyLib:
 
 lib = _LazyLib()
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
-LAUNCHES = {"smcb_reweight": 2, "smcb_cdf_scan": 2, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
+LAUNCHES = {"smcb_reweight": 2, "smcb_cdf_scan": 2, "smcb_cdf_scan_weights": 2, "smcb_resample_exponential_sums": 2,
+            "smcb_resample_fused": 3, "smcb_xchg_slot_words": 0, "smcb_xchg_big_slot_words": 0, "smcb_xchg_max_vals": 0, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
             "smcb_weighted_sums1": 2, "smcb_weighted_moments_shifted": 3, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0,
             "smcb_ess_bisect_xchg_slot_words": 0}
 launch_count = 0

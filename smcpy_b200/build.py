@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsmcb200.so")
-SOURCES = ["api.cu", "reweight.cu", "resample.cu", "moments.cu", "metropolis.cu", "usermodel.cu"]
+SOURCES = ["api.cu", "reweight.cu", "resample.cu", "moments.cu", "metropolis.cu", "usermodel.cu", "xchg.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
 

@@ -41,6 +41,8 @@ Options& options() {
         v.coop_bps = env_int("SMCB_COOP_BPS", 0);
         v.bisect_plain = env_int("SMCB_BISECT_PLAIN", 0);
         v.spring_ppt = env_int("SMCB_SPRING_PPT", -1);
+        v.xchg_timeout_s = env_int("SMCB_XCHG_TIMEOUT_S", 0);
+        v.no_fused_resample = env_int("SMCB_NO_FUSED_RESAMPLE", 0);
         return v;
     }();
     return o;
@@ -62,7 +64,8 @@ static const OptEntry kOptTable[] = {
     {"no_dmma", &Options::no_dmma},         {"cov_two_pass", &Options::cov_two_pass},
     {"no_coop", &Options::no_coop},         {"coop_tpb", &Options::coop_tpb},
     {"coop_bps", &Options::coop_bps},       {"bisect_plain", &Options::bisect_plain},
-    {"spring_ppt", &Options::spring_ppt},
+    {"spring_ppt", &Options::spring_ppt},   {"xchg_timeout_s", &Options::xchg_timeout_s},
+    {"no_fused_resample", &Options::no_fused_resample},
 };
 
 }  // namespace smcb

@@ -42,6 +42,8 @@ struct Options {
     int coop_tpb, coop_bps;// cooperative kernels: threads per block, blocks per SM
     int bisect_plain;      // 1: evaluate every scipy midpoint (no monotone bracketing)
     int spring_ppt;        // -1 auto; 1/2 particles per thread in the RK4 kernel
+    int xchg_timeout_s;    // peer-exchange time-out inside kernels (seconds; 0 = default 30)
+    int no_fused_resample; // 1: separate uniforms / search / count / gather kernels (native mode)
 };
 Options& options();
 void note_mh_variant(const char* text);
@@ -238,6 +240,47 @@ __device__ __forceinline__ double path_inc(double ll, double lp, double lq, cons
     t = __dadd_rn(t, c.pe0 > 0.0 ? -__dmul_rn(lp, c.pe0) : -0.0);
     t = __dadd_rn(t, c.qe0 > 0.0 ? -__dmul_rn(lq, c.qe0) : -0.0);
     return (t != t) ? kNegInf : t;
+}
+
+// ---- un-normalised log-weight of one particle (updater.py:122-133) -------------------------------
+struct RwIn {
+    const double* ll;
+    const double* lp;
+    const double* lq;      // nullptr -> lp
+    const double* lw;      // nullptr -> uniform
+    double lw_uniform;     // log(1/n_global)
+    double lp_const;       // used when lp == nullptr (flat priors: the summed log-prior is one constant)
+    PathCoef c;
+};
+
+__device__ __forceinline__ double rw_value(const RwIn& in, int64_t i) {
+    const double ll = in.ll[i];
+    const double lp = in.lp ? in.lp[i] : in.lp_const;
+    const double lq = in.lq ? in.lq[i] : lp;
+    const double inc = path_inc(ll, lp, lq, in.c);
+    const double lw = in.lw ? in.lw[i] : in.lw_uniform;
+    return __dadd_rn(lw, inc);
+}
+
+// incremental weight only (adaptive search: previous weights are ignored, samplers.py:264-276)
+__device__ __forceinline__ double inc_value(const RwIn& in, int64_t i) {
+    const double ll = in.ll[i];
+    const double lp = in.lp ? in.lp[i] : in.lp_const;
+    const double lq = in.lq ? in.lq[i] : lp;
+    return path_inc(ll, lp, lq, in.c);
+}
+
+inline RwIn make_rw_in(const double* ll, const double* lp, const double* lq, const double* lw, int64_t n_global,
+                       const smcb_path_t* path, double lp_const = 0.0) {
+    RwIn in;
+    in.ll = ll;
+    in.lp = lp;
+    in.lq = lq;
+    in.lw = lw;
+    in.lw_uniform = log(1.0 / (double)n_global);
+    in.lp_const = lp_const;
+    in.c = make_path_coef(path->phi, path->phi_prev, path->lambda);
+    return in;
 }
 
 // ---- Philox4x32-10 counter-based generator ---------------------------------------------

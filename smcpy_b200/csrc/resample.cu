@@ -120,10 +120,64 @@ __global__ void scan_reset_kernel(unsigned long long* state, int64_t n_tiles, un
     if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const double* __restrict__ w,
+// Scan inputs.  LoadArr: an array of weights.  LoadRw: the normalised weights recomputed from the resident
+// log-likelihood (and log-prior / previous log-weight) columns with the scalars of the reweight pass --
+// w = exp((un_lw - max) - log S1), exactly rw_finalize_body's arithmetic -- so a step that resamples never
+// writes or re-reads log_w / w.  LoadExp: the scaled unit exponentials of resample_exponentials_kernel,
+// generated in registers.
+struct LoadArr {
+    const double* w;
+    __device__ __forceinline__ void load8(int64_t base, int64_t n, double (&v)[8]) const {
+        if (base + 8 <= n) {
+            const double2* p = reinterpret_cast<const double2*>(w + base);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double2 t = p[j];
+                v[2 * j] = t.x;
+                v[2 * j + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (base + j < n) ? w[base + j] : 0.0;
+        }
+    }
+};
+struct LoadRw {
+    RwIn in;
+    const double* sc;        // scalars of the reweight pass: [0] max, [5] log S1
+    __device__ __forceinline__ void load8(int64_t base, int64_t n, double (&v)[8]) const {
+        const double m = sc[0], ls = sc[5];
+        double x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (base + j < n) ? rw_value(in, base + j) : kNegInf;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (base + j < n) ? exp((x[j] - m) - ls) : 0.0;
+    }
+};
+struct LoadExp {
+    int64_t first, n_global;
+    uint64_t seed;
+    uint32_t stream_id;
+    __device__ __forceinline__ void load8(int64_t base, int64_t n, double (&v)[8]) const {
+        const Philox rng(seed);
+        const double scale = 0.5 / (double)n_global;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double e = 0.0;
+            if (base + j < n) {
+                const uint4 r = rng((uint64_t)(first + base + j), 0xE590u, stream_id);
+                e = -log1p(-u01_53(r.x, r.y)) * scale;
+            }
+            v[j] = e;
+        }
+    }
+};
+
+template <class Loader>
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const Loader ld,
                                                                      double* __restrict__ cdf, int64_t n,
                                                                      unsigned long long* state,
-                                                                     unsigned int* counter) {
+                                                                     unsigned int* counter, double* total_out) {
     __shared__ double sh_warp[kScanThreads / 32];
     __shared__ double sh_wmax[kScanThreads / 32];
     __shared__ unsigned int sh_tile;
@@ -136,19 +190,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const doubl
     const int64_t tile = sh_tile;
     const int64_t base = tile * kScanTile + (int64_t)tid * kScanItems;
 
+    static_assert(kScanItems == 8, "loaders fetch eight values per thread");
     double v[kScanItems];
-    if (base + kScanItems <= n) {
-        const double2* p = reinterpret_cast<const double2*>(w + base);
-#pragma unroll
-        for (int j = 0; j < kScanItems / 2; ++j) {
-            const double2 t = p[j];
-            v[2 * j] = t.x;
-            v[2 * j + 1] = t.y;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kScanItems; ++j) v[j] = (base + j < n) ? w[base + j] : 0.0;
-    }
+    ld.load8(base, n, v);
     // thread-local inclusive scan
 #pragma unroll
     for (int j = 1; j < kScanItems; ++j) v[j] += v[j - 1];
@@ -225,6 +269,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const doubl
         if (k < wid) lower = fmax(lower, sh_wmax[k]);
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) v[j] = fmax(v[j], lower);
+    if (total_out && base <= n - 1 && n - 1 < base + kScanItems) {       // the running sum of the whole shard
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j)
+            if (base + j == n - 1) *total_out = v[j];
+    }
     if (base + kScanItems <= n) {
         double2* q = reinterpret_cast<double2*>(cdf + base);
 #pragma unroll
@@ -344,6 +393,225 @@ __global__ void __launch_bounds__(256) count_bytes_kernel(const uint8_t* __restr
     }
 }
 
+// ---- fused resampling for sorted uniforms (native generator) -------------------------------------------------
+// All three built-in resamplers produce their uniforms in non-decreasing slot order (stratified and
+// systematic by construction, multinomial by exponential spacings), so
+//   * slot k's ancestor index is found by a binary search confined to the CDF window that the first
+//     slots of this tile and of the next one select (merge-path style partition, rs_tile_bounds_kernel):
+//     ~log2(tile) probes that stay in L1 instead of ~23 probes through L2;
+//   * the uniforms themselves are evaluated on the fly (Philox keyed by the global slot, or the running
+//     sums of the exponentials), the ancestor rows are gathered in the same pass, and the number of distinct
+//     ancestors is the number of index changes between neighbouring slots.
+// One rank of `world` (particles sharded in equal contiguous blocks): the rank OWNS the global slots whose
+// uniform falls into its segment [O_r, O_r+1) of the global CDF -- a contiguous slot range [K_lo, K_hi)
+// that it derives itself from the all-gathered rank totals (rs_plan_kernel) -- searches its own CDF and
+// writes every selected row column by column straight into the SoA buffer of the rank that holds the slot
+// (peer-mapped pointers over NVLink; its own buffer when world == 1).  No request routing, no host
+// round trip.
+constexpr int kRsThreads = 256;
+constexpr int kRsPpt = 4;
+constexpr int kRsTile = kRsThreads * kRsPpt;
+
+struct RsDev {
+    int32_t kind, world, rank, n_cols;
+    int64_t n_local, n_global;
+    const double* cdf;
+    const double* totals;                    // world x 2
+    const double* t_peer[SMCB_MAX_RANKS];
+    const double* src;
+    int64_t src_stride;
+    double* dst_peer[SMCB_MAX_RANKS];
+    int64_t dst_stride;
+    int64_t* idx_out;
+    int64_t* n_unique_out;
+    uint64_t seed;
+    uint32_t stream_id;
+    // workspace
+    double* w_off;                           // world + 1 CDF segment offsets
+    double* e_off;                           // world + 1 offsets of the exponential running sums, [world + 1] = S_(N+1)
+    int64_t* krange;                         // [0] K_lo, [1] K_hi
+    int64_t* tb;                             // per tile: ancestor index of its first slot (+ one closing entry)
+    int64_t* tp;                             // per tile: ancestor index of the slot before its first
+    unsigned long long* uniq;
+    unsigned int* ticket;
+};
+
+__device__ __forceinline__ double rs_slot_u(const RsDev& a, const Philox& rng, double u_sys, double s_all, int64_t k) {
+    const double inv_n = 1.0 / (double)a.n_global;          // resampler_rngs.py:9: 1 / N * (...)
+    if (a.kind == SMCB_RESAMPLE_SYSTEMATIC) return __dmul_rn(inv_n, __dadd_rn((double)k, u_sys));
+    if (a.kind == SMCB_RESAMPLE_STRATIFIED) {
+        const uint4 r = rng((uint64_t)k, 0, a.stream_id);
+        return __dmul_rn(inv_n, __dadd_rn((double)k, u01_53(r.x, r.y)));
+    }
+    const int64_t q = k / a.n_local, j = k - q * a.n_local;  // standard: U_(k) = S_k / S_(N+1)
+    return fmin((a.e_off[q] + a.t_peer[q][j]) / s_all, 1.0 - 0x1p-53);
+}
+__device__ __forceinline__ double rs_u_sys(const RsDev& a, const Philox& rng) {
+    if (a.kind != SMCB_RESAMPLE_SYSTEMATIC) return 0.0;
+    const uint4 r = rng(0, 0, a.stream_id);
+    return u01_53(r.x, r.y);
+}
+// first j in [lo, hi) with off + cdf_j > x; hi if none
+__device__ __forceinline__ int64_t rs_search(const double* __restrict__ cdf, double off, double x, int64_t lo, int64_t hi) {
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const double c = __dadd_rn(off, __ldg(cdf + mid));
+        if (c <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// offsets from the gathered totals (rank order, one add chain: identical on every rank), S_(N+1), and the
+// slot range this rank owns
+__global__ void rs_plan_kernel(const RsDev a) {
+    const int t = threadIdx.x;
+    if (t == 0) {
+        double o = 0.0, e = 0.0;
+        a.w_off[0] = 0.0;
+        a.e_off[0] = 0.0;
+        for (int r = 0; r < a.world; ++r) {
+            // single GPU without a totals record: the running sums' last entries
+            const double tw = a.totals ? a.totals[2 * r] : a.cdf[a.n_local - 1];
+            const double te = a.totals ? a.totals[2 * r + 1]
+                                       : (a.kind == SMCB_RESAMPLE_STANDARD ? a.t_peer[0][a.n_local - 1] : 0.0);
+            o = __dadd_rn(o, tw);
+            e = __dadd_rn(e, te);
+            a.w_off[r + 1] = o;
+            a.e_off[r + 1] = e;
+        }
+        const Philox rng(a.seed);
+        const uint4 r4 = rng((uint64_t)a.n_global, 0xE590u, a.stream_id);      // E_(N+1): same value on every rank
+        a.e_off[a.world + 1] = e + -log1p(-u01_53(r4.x, r4.y)) * (0.5 / (double)a.n_global);
+    }
+    __syncthreads();
+    if (t < 2) {
+        const Philox rng(a.seed);
+        const double u_sys = rs_u_sys(a, rng);
+        const double s_all = a.e_off[a.world + 1];
+        const int seg = a.rank + t;                            // boundary O_seg: slots with u < O_seg lie below it
+        int64_t k;
+        if (seg == 0) k = 0;
+        else if (seg == a.world) k = a.n_global;
+        else {
+            const double bound = a.w_off[seg];
+            int64_t lo = 0, hi = a.n_global;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (rs_slot_u(a, rng, u_sys, s_all, mid) < bound) lo = mid + 1; else hi = mid;
+            }
+            k = lo;
+        }
+        a.krange[t] = k;
+    }
+}
+
+__global__ void __launch_bounds__(256) rs_tile_bounds_kernel(const RsDev a, int64_t max_tiles) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k_lo = a.krange[0], k_hi = a.krange[1];
+    const int64_t cnt = k_hi - k_lo;
+    const int64_t n_tiles = (cnt + kRsTile - 1) / kRsTile;
+    if (cnt <= 0 || t > n_tiles || t > max_tiles) return;
+    const Philox rng(a.seed);
+    const double u_sys = rs_u_sys(a, rng);
+    const double s_all = a.e_off[a.world + 1];
+    const double off = a.w_off[a.rank];
+    int64_t slot = k_lo + t * kRsTile;
+    if (slot >= k_hi) slot = k_hi - 1;
+    a.tb[t] = rs_search(a.cdf, off, rs_slot_u(a, rng, u_sys, s_all, slot), 0, a.n_local);
+    int64_t prev = -1;                                         // the slot before the range belongs to another owner
+    if (t > 0 && t < n_tiles) {
+        prev = rs_search(a.cdf, off, rs_slot_u(a, rng, u_sys, s_all, k_lo + t * kRsTile - 1), 0, a.n_local);
+        if (prev > a.n_local - 1) prev = a.n_local - 1;
+    }
+    a.tp[t] = prev;
+}
+
+__global__ void __launch_bounds__(kRsThreads) rs_fused_kernel(const RsDev a) {
+    __shared__ int64_t sidx[kRsTile];
+    __shared__ unsigned int s_cnt;
+    const int tid = threadIdx.x;
+    const int64_t k_lo = a.krange[0], k_hi = a.krange[1];
+    const int64_t cnt = k_hi - k_lo;
+    const int64_t n_tiles = cnt > 0 ? (cnt + kRsTile - 1) / kRsTile : 0;
+    const Philox rng(a.seed);
+    const double u_sys = rs_u_sys(a, rng);
+    const double s_all = a.e_off[a.world + 1];
+    const double off = a.w_off[a.rank];
+    unsigned int my_unique = 0;
+    if (tid == 0) s_cnt = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t lo = a.tb[tile], hi = a.tb[tile + 1];
+        const int64_t base = k_lo + tile * kRsTile;
+        int64_t idx[kRsPpt];
+        bool valid[kRsPpt];
+        double* dstp[kRsPpt];
+#pragma unroll
+        for (int p = 0; p < kRsPpt; ++p) {
+            const int s = p * kRsThreads + tid;
+            const int64_t k = base + s;
+            valid[p] = k < k_hi;
+            int64_t j = -2;
+            dstp[p] = nullptr;
+            if (valid[p]) {
+                const double x = rs_slot_u(a, rng, u_sys, s_all, k);
+                j = rs_search(a.cdf, off, x, lo, hi);
+                if (j > a.n_local - 1) j = a.n_local - 1;       // clamp (quirk Q4)
+                const int64_t q = k / a.n_local;
+                dstp[p] = a.dst_peer[q] + (k - q * a.n_local);
+                if (a.idx_out) a.idx_out[k - (int64_t)a.rank * a.n_local] = j;    // world == 1 only
+            }
+            idx[p] = j;
+            sidx[s] = j;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < kRsPpt; ++p) {
+            const int s = p * kRsThreads + tid;
+            const int64_t prev = (s == 0) ? a.tp[tile] : sidx[s - 1];
+            if (valid[p] && idx[p] != prev) ++my_unique;
+        }
+        // gather: two columns x kRsPpt slots in flight
+        int c = 0;
+        for (; c + 2 <= a.n_cols; c += 2) {
+            double v0[kRsPpt], v1[kRsPpt];
+            const double* s0 = a.src + (int64_t)c * a.src_stride;
+            const double* s1 = s0 + a.src_stride;
+#pragma unroll
+            for (int p = 0; p < kRsPpt; ++p) {
+                v0[p] = valid[p] ? __ldg(s0 + idx[p]) : 0.0;
+                v1[p] = valid[p] ? __ldg(s1 + idx[p]) : 0.0;
+            }
+#pragma unroll
+            for (int p = 0; p < kRsPpt; ++p) {
+                if (valid[p]) {
+                    dstp[p][(int64_t)c * a.dst_stride] = v0[p];
+                    dstp[p][(int64_t)(c + 1) * a.dst_stride] = v1[p];
+                }
+            }
+        }
+        if (c < a.n_cols) {
+            const double* s0 = a.src + (int64_t)c * a.src_stride;
+#pragma unroll
+            for (int p = 0; p < kRsPpt; ++p)
+                if (valid[p]) dstp[p][(int64_t)c * a.dst_stride] = __ldg(s0 + idx[p]);
+        }
+        __syncthreads();                                        // sidx is reused by the next tile
+    }
+    // distinct ancestors: block sum, one integer atomic per block; the last block publishes and resets
+    my_unique = __reduce_add_sync(0xffffffffu, my_unique);
+    if ((tid & 31) == 0 && my_unique) atomicAdd(&s_cnt, my_unique);
+    __syncthreads();
+    if (tid == 0) {
+        if (s_cnt) atomicAdd(a.uniq, (unsigned long long)s_cnt);
+        __threadfence();
+        if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {
+            *a.n_unique_out = (int64_t)atomicAdd(a.uniq, 0ull);
+            *a.uniq = 0ull;
+            *a.ticket = 0u;
+        }
+    }
+}
+
 }  // namespace smcb
 
 using namespace smcb;
@@ -387,7 +655,8 @@ extern "C" int smcb_cdf_scan(const double* w, double* cdf, int64_t n, int32_t mo
     unsigned int* counter = (unsigned int*)(base + kWsTickets) + 1;
     const int64_t n_tiles = (n + kScanTile - 1) / kScanTile;
     scan_reset_kernel<<<grid_for(n_tiles, 256, 1, 4), 256, 0, as_stream(stream)>>>(state, n_tiles, counter);
-    scan_lookback_kernel<<<(unsigned)n_tiles, kScanThreads, 0, as_stream(stream)>>>(w, cdf, n, state, counter);
+    scan_lookback_kernel<LoadArr><<<(unsigned)n_tiles, kScanThreads, 0, as_stream(stream)>>>(LoadArr{w}, cdf, n, state,
+                                                                                               counter, nullptr);
     return check_launch("scan_lookback_kernel");
 }
 
@@ -451,4 +720,91 @@ extern "C" int smcb_count_moved(const uint8_t* moved, int64_t n, int64_t* count_
         moved, n, (unsigned long long*)(base + kWsSmall + 64), (unsigned int*)(base + kWsTickets) + 2,
         count_out);
     return check_launch("count_bytes_kernel");
+}
+
+extern "C" int smcb_cdf_scan_weights(int64_t n, const double* ll, const double* lp, double lp_const, const double* lq,
+                                     const double* log_w_in, int64_t n_global, const smcb_path_t* path,
+                                     const double* scalars, double* cdf, double* total_out, void* ws, void* stream) {
+    SMCB_REQUIRE(n > 0 && ll && path && scalars && cdf && ws, "bad argument");
+    SMCB_REQUIRE(((uintptr_t)cdf & 15) == 0, "cdf must be 16-byte aligned");
+    char* base = (char*)ws;
+    unsigned long long* state = (unsigned long long*)(base + kWsLarge);
+    unsigned int* counter = (unsigned int*)(base + kWsTickets) + 1;
+    const int64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+    LoadRw ld;
+    ld.in = make_rw_in(ll, lp, lq, log_w_in, n_global, path, lp_const);
+    ld.sc = scalars;
+    scan_reset_kernel<<<grid_for(n_tiles, 256, 1, 4), 256, 0, as_stream(stream)>>>(state, n_tiles, counter);
+    scan_lookback_kernel<LoadRw><<<(unsigned)n_tiles, kScanThreads, 0, as_stream(stream)>>>(ld, cdf, n, state, counter,
+                                                                                              total_out);
+    return check_launch("scan_lookback_kernel<LoadRw>");
+}
+
+extern "C" int smcb_resample_exponential_sums(int64_t first, int64_t count, int64_t n_global, uint64_t seed,
+                                              uint64_t stream_id, double* t_out, double* total_out, void* ws,
+                                              void* stream) {
+    SMCB_REQUIRE(first >= 0 && count > 0 && n_global >= first + count && t_out && ws, "bad argument");
+    SMCB_REQUIRE(((uintptr_t)t_out & 15) == 0, "t_out must be 16-byte aligned");
+    char* base = (char*)ws;
+    unsigned long long* state = (unsigned long long*)(base + kWsLarge);
+    unsigned int* counter = (unsigned int*)(base + kWsTickets) + 1;
+    const int64_t n_tiles = (count + kScanTile - 1) / kScanTile;
+    LoadExp ld{first, n_global, seed, (uint32_t)stream_id};
+    scan_reset_kernel<<<grid_for(n_tiles, 256, 1, 4), 256, 0, as_stream(stream)>>>(state, n_tiles, counter);
+    scan_lookback_kernel<LoadExp><<<(unsigned)n_tiles, kScanThreads, 0, as_stream(stream)>>>(ld, t_out, count, state,
+                                                                                               counter, total_out);
+    return check_launch("scan_lookback_kernel<LoadExp>");
+}
+
+extern "C" int smcb_resample_fused(const smcb_resample_t* r, void* ws, void* stream) {
+    SMCB_REQUIRE(r && ws, "bad argument");
+    SMCB_REQUIRE(r->kind >= 0 && r->kind <= 2, "unknown resampler kind");
+    SMCB_REQUIRE(r->world >= 1 && r->world <= SMCB_MAX_RANKS && r->rank >= 0 && r->rank < r->world, "bad ranks");
+    SMCB_REQUIRE(r->n_local > 0 && r->n_global == r->n_local * r->world, "shards must be equal: n_global = world * n_local");
+    SMCB_REQUIRE(r->cdf && r->src && r->n_cols > 0 && r->n_unique_out, "NULL argument");
+    SMCB_REQUIRE(r->totals || r->world == 1, "totals are required on several GPUs");
+    SMCB_REQUIRE(r->world == 1 || r->idx_out == nullptr, "idx_out is single-GPU only");
+    RsDev a;
+    memset(&a, 0, sizeof(a));
+    a.kind = r->kind;
+    a.world = r->world;
+    a.rank = r->rank;
+    a.n_cols = r->n_cols;
+    a.n_local = r->n_local;
+    a.n_global = r->n_global;
+    a.cdf = r->cdf;
+    a.totals = r->totals;
+    a.src = r->src;
+    a.src_stride = r->src_stride;
+    a.dst_stride = r->dst_stride;
+    a.idx_out = r->idx_out;
+    a.n_unique_out = r->n_unique_out;
+    a.seed = r->seed;
+    a.stream_id = (uint32_t)r->stream_id;
+    for (int q = 0; q < r->world; ++q) {
+        SMCB_REQUIRE(r->dst_peer[q] != nullptr, "destination pointer is NULL");
+        SMCB_REQUIRE(r->kind != SMCB_RESAMPLE_STANDARD || r->t_peer[q] != nullptr, "running-sum pointer is NULL");
+        a.dst_peer[q] = r->dst_peer[q];
+        a.t_peer[q] = r->t_peer[q];
+    }
+    char* base = (char*)ws;
+    a.w_off = (double*)(base + kWsSmall + 1024);
+    a.e_off = a.w_off + 16;
+    a.krange = (int64_t*)(a.e_off + 16);
+    a.uniq = (unsigned long long*)(base + kWsSmall + 64);
+    a.ticket = (unsigned int*)(base + kWsTickets) + 2;
+    const int64_t max_tiles = (r->n_global + kRsTile - 1) / kRsTile;
+    a.tb = (int64_t*)(base + kWsLarge);
+    a.tp = a.tb + (max_tiles + 2);
+    cudaStream_t s = as_stream(stream);
+    rs_plan_kernel<<<1, 32, 0, s>>>(a);
+    rs_tile_bounds_kernel<<<(unsigned)((max_tiles + 1 + 255) / 256), 256, 0, s>>>(a, max_tiles);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    const int64_t local_tiles = (r->n_local + kRsTile - 1) / kRsTile;
+    // an owner's slot range is ~n_local slots on average but may be all of n_global: persistent tiles
+    int64_t grid = r->world == 1 ? local_tiles : 2 * local_tiles;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    rs_fused_kernel<<<(unsigned)grid, kRsThreads, 0, s>>>(a);
+    return check_launch("rs_fused_kernel");
 }

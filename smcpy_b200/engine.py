@@ -47,10 +47,14 @@ class Runtime:
         return self._ws
 
 
-class AcceptExchange:
-    """Symmetric-memory buffers for the accept-count exchange fused into the Metropolis kernel
-    (smcb_xchg_t).  One per process; falls back to NCCL all-reduce (None) if symmetric memory
-    cannot be set up."""
+class PeerExchange:
+    """Symmetric-memory buffers for the collectives that are fused into kernels (one per process):
+    * `slots`     -- accept-count exchange inside the Metropolis kernel (smcb_mh_step_xchg);
+    * `bis_slots` -- rank sums exchanged inside the cooperative phi search and reweight kernels
+                     (smcb_ess_search, smcb_reweight_fused);
+    * `big_slots` -- small all-gather / all-reduce kernel (smcb_xchg_allgather: weight totals,
+                     covariance sums, counts, error flags).
+    get() returns None when symmetric memory cannot be set up (then NCCL collectives are used)."""
     _inst = None
     _failed = False
 
@@ -59,35 +63,34 @@ class AcceptExchange:
         import torch.distributed._symmetric_memory as symm_mem
         rank, world = dist_info()
         dv = Runtime.get().device
-        self.slots = symm_mem.empty(_lib.MAX_MCMC_STEPS * _lib.MAX_RANKS, dtype=torch.int64, device=dv)
-        self.slots.zero_()
-        self.handle = symm_mem.rendezvous(self.slots, dist.group.WORLD)
+        self.rank, self.world = rank, world
+
+        def sym(words):
+            t = symm_mem.empty(int(words), dtype=torch.int64, device=dv)
+            t.zero_()
+            h = symm_mem.rendezvous(t, dist.group.WORLD)
+            x = _lib.Xchg()
+            x.world, x.rank = world, rank
+            for r, p in enumerate(peer_pointers(t, h)):
+                x.peer_slots[r] = p
+            return t, h, x
+        self.slots, self.handle, self.x = sym(_lib.MAX_MCMC_STEPS * _lib.MAX_RANKS)
         self.global_counts = torch.zeros(_lib.MAX_MCMC_STEPS, dtype=torch.int64, device=dv)
         self.ticket = torch.zeros(4, dtype=torch.int32, device=dv)
+        self.x.global_counts = self.global_counts.data_ptr()
+        self.x.ticket = self.ticket.data_ptr()
         self.gen = 0
-        # second symmetric buffer: the (max, S1, S2) exchange of the fused bisection (smcb_ess_bisect_xchg)
-        self.bis_slots = symm_mem.empty(int(_lib.lib.smcb_ess_bisect_xchg_slot_words()), dtype=torch.int64, device=dv)
-        self.bis_slots.zero_()
-        self.bis_handle = symm_mem.rendezvous(self.bis_slots, dist.group.WORLD)
+        self.bis_slots, self.bis_handle, self.xb = sym(_lib.lib.smcb_xchg_slot_words())
         self.bis_gen = 0
-        xb = _lib.Xchg()
-        xb.world, xb.rank = world, rank
-        for r, p in enumerate(peer_pointers(self.bis_slots, self.bis_handle)):
-            xb.peer_slots[r] = p
-        self.xb = xb
-        x = _lib.Xchg()
-        x.world, x.rank = world, rank
-        for r, p in enumerate(peer_pointers(self.slots, self.handle)):
-            x.peer_slots[r] = p
-        x.global_counts = self.global_counts.data_ptr()
-        x.ticket = self.ticket.data_ptr()
-        self.x = x
+        self.big_slots, self.big_handle, self.xg = sym(_lib.lib.smcb_xchg_big_slot_words())
+        self.big_gen = 0
+        self.max_vals = int(_lib.lib.smcb_xchg_max_vals())
+        self.status = torch.zeros(1, dtype=torch.int32, device=dv)
         torch.cuda.synchronize()
         dist.barrier()                       # every rank's slots are zeroed before anyone publishes
 
     @classmethod
     def get(cls):
-        import os
         if cls._failed or os.environ.get("SMCB_NO_XCHG"):
             return None
         _, world = dist_info()
@@ -95,17 +98,17 @@ class AcceptExchange:
             return None
         if cls._inst is None:
             try:
-                cls._inst = AcceptExchange()
+                cls._inst = PeerExchange()
             except Exception as e:            # pragma: no cover - depends on the box
-                warnings.warn("symmetric-memory accept-count exchange unavailable (%s); using NCCL all-reduce" % e)
+                warnings.warn("symmetric-memory exchange unavailable (%s); using NCCL collectives" % e)
                 cls._failed = True
                 return None
         return cls._inst
 
     def next_bisect_gen(self):
         self.bis_gen += 1
-        if self.bis_gen >= (1 << 56):
-            raise RuntimeError("bisection exchange generation overflow")
+        if self.bis_gen >= (1 << 48):
+            raise RuntimeError("exchange generation overflow")
         self.xb.gen = self.bis_gen
         return self.xb
 
@@ -115,6 +118,27 @@ class AcceptExchange:
             raise RuntimeError("accept-count exchange generation overflow")
         self.x.gen = self.gen
         return self.x
+
+    def gather(self, src, reduce=False, out=None):
+        """All-gather (rows in rank order) or all-reduce (rank-order sum) of a small float64 device
+        vector through smcb_xchg_allgather; asynchronous on the current stream."""
+        n = int(src.numel())
+        if n > self.max_vals:
+            raise ValueError("record too large for the peer exchange")
+        if out is None:
+            out = torch.empty(n if reduce else (self.world, n), dtype=torch.float64, device=src.device)
+        self.big_gen += 1
+        self.xg.gen = self.big_gen
+        call("smcb_xchg_allgather", C.byref(self.xg), ptr(src), n, ptr(out), 1 if reduce else 0, ptr(self.status),
+             stream_ptr())
+        return out
+
+    def check(self):
+        if int(self.status.item()) != 0:
+            raise RuntimeError("peer exchange: a rank never answered")
+
+
+AcceptExchange = PeerExchange
 
 
 def peer_pointers(t, handle):
@@ -131,38 +155,60 @@ def peer_pointers(t, handle):
 class SymmetricPool:
     """Peer-mapped (symmetric-memory) particle buffers for the multi-GPU resampler, cached per
     shape so that repeated sample() calls do not rendezvous again.  get() returns
-    [(tensor, [peer pointers])] x 2 (the ping-pong pair) or None when symmetric memory is
-    unavailable (then the NCCL all-to-all path is used)."""
+    [(tensor, [peer pointers], handle)] x 2 (the ping-pong pair) or None when symmetric memory is
+    unavailable (then the NCCL all-to-all path is used).  A pair is LEASED to one live DeviceState:
+    a second state of the same shape gets its own pair (every rank allocates in the same order)."""
     _cache = {}
     _failed = False
 
     @classmethod
-    def get(cls, rows, n_max):
-        import os
+    def get(cls, rows, n_max, owner=None):
+        import weakref
         if cls._failed or os.environ.get("SMCB_NO_P2P"):
             return None
         key = (int(rows), int(n_max))
-        if key not in cls._cache:
-            try:
-                import torch.distributed as dist
-                import torch.distributed._symmetric_memory as symm_mem
-                dv = Runtime.get().device
-                pair = []
-                for _ in range(2):
-                    t = symm_mem.empty((rows, n_max), dtype=torch.float64, device=dv)
-                    h = symm_mem.rendezvous(t, dist.group.WORLD)
-                    pair.append((t, peer_pointers(t, h), h))
-                cls._cache[key] = pair
-            except Exception as e:            # pragma: no cover - depends on the box
-                warnings.warn("symmetric particle buffers unavailable (%s); using NCCL all-to-all" % e)
-                cls._failed = True
-                return None
-        return cls._cache[key]
+        leases = cls._cache.setdefault(key, [])
+        for lease in leases:
+            holder = lease[1]() if lease[1] is not None else None
+            if holder is None or holder is owner:
+                lease[1] = weakref.ref(owner) if owner is not None else None
+                return lease[0]
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            dv = Runtime.get().device
+            pair = []
+            for _ in range(2):
+                t = symm_mem.empty((rows, n_max), dtype=torch.float64, device=dv)
+                h = symm_mem.rendezvous(t, dist.group.WORLD)
+                pair.append((t, peer_pointers(t, h), h))
+        except Exception as e:            # pragma: no cover - depends on the box
+            warnings.warn("symmetric particle buffers unavailable (%s); using NCCL all-to-all" % e)
+            cls._failed = True
+            return None
+        leases.append([pair, weakref.ref(owner) if owner is not None else None])
+        return pair
+
+
+_SOLO = False
+
+
+class solo:
+    """with solo(): ... -- run as a single-GPU job inside a multi-rank process (bench.py's N-GPU
+    self-check compares the sharded run with a one-GPU run of the same global problem)."""
+
+    def __enter__(self):
+        global _SOLO
+        self.old, _SOLO = _SOLO, True
+
+    def __exit__(self, *exc):
+        global _SOLO
+        _SOLO = self.old
 
 
 def dist_info():
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
+    if not _SOLO and dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
 
@@ -182,6 +228,13 @@ class PhiloxRNG:
     def __init__(self, seed=None):
         if seed is None:
             seed = int(np.random.SeedSequence().entropy) & ((1 << 63) - 1)
+            rank, world = dist_info()
+            if world > 1:
+                # one seed for the whole job: the sharded resampler and the global particle ids assume it
+                import torch.distributed as dist
+                box = [seed]
+                dist.broadcast_object_list(box, src=0)
+                seed = int(box[0])
         self.seed = int(seed) & ((1 << 64) - 1)
         self._stream = 0
 
@@ -241,7 +294,11 @@ class ProblemSpec:
         self.d = d
         self.n_priors = len(descs)
         # summed log-prior of any particle inside the support (all device priors are flat)
-        self.lp_const = float(np.sum([lpin for (_, _, _, _, lpin) in descs]))
+        # (one add chain in prior order, as build_col_priors does on the library side)
+        self.lp_const = 0.0
+        for (k, _, _, _, lpin) in descs:
+            if k != _lib.PRIOR_IMPROPER_COV:
+                self.lp_const += float(lpin)
         data = np.asarray(data, dtype=np.float64)
         self._data_dev = dev(data.reshape(-1))
         c.data = self._data_dev.data_ptr()
@@ -368,17 +425,25 @@ class DeviceState:
         self.with_lq = bool(with_lq)            # third resident column: proposal log-pdf
         rows = d + 3 if with_lq else d + 2
         self.peer_cols = self.peer_cols_alt = None      # peer pointers of cols / cols_alt (multi-GPU)
+        self.extra = self.extra_alt = None              # spare symmetric row after the columns (resampler scratch)
+        self.peer_extra = self.peer_extra_alt = None
         self.col_stride = self.n
         pool = None
         if symmetric:
             _, world = dist_info()
             n_max = -(-self.n_global // world)
-            pool = SymmetricPool.get(rows, n_max)
+            pool = SymmetricPool.get(rows + 1, n_max, owner=self)
         if pool is not None:
-            (self.cols, self.peer_cols, _), (self.cols_alt, self.peer_cols_alt, _) = pool
-            self.col_stride = int(self.cols.shape[1])
+            (full, peers, _), (full_alt, peers_alt, _) = pool
+            self.col_stride = int(full.shape[1])
             if self.col_stride != self.n:
                 raise NotImplementedError("multi-GPU runs need the particle count to be a multiple of the GPU count")
+            self.cols, self.cols_alt = full[:rows], full_alt[:rows]
+            self.extra, self.extra_alt = full[rows], full_alt[rows]
+            self.peer_cols, self.peer_cols_alt = list(peers), list(peers_alt)
+            off = rows * self.col_stride * 8
+            self.peer_extra = [q + off for q in peers]
+            self.peer_extra_alt = [q + off for q in peers_alt]
         else:
             self.cols = torch.empty((rows, self.n), dtype=f64, device=dv)
             self.cols_alt = torch.empty((rows, self.n), dtype=f64, device=dv)
@@ -405,6 +470,13 @@ class DeviceState:
         self.uniform_weights = False
         self.total_unnorm_log_weight = None
         self.shift = None                       # previous mean: shift of the one-pass covariance (d > 8)
+        self.rs_tot = torch.zeros(2, dtype=f64, device=dv)   # running-sum totals of the resampler's scans
+        # reweight of a step that resamples: the new weights exist only as (inputs, scalars) until the CDF
+        # scan recomputes them; log_w / w still hold the PREVIOUS weights then
+        self.pending = None
+        self.lp_const = None                    # summed log-prior when it is one constant over the shard
+        self.last_dphi = 0.0                    # previous adaptive step (start of the next phi search)
+        self.deferred = []                      # device scalars to check at the end of the step
 
     @property
     def params(self):
@@ -429,6 +501,8 @@ class DeviceState:
     def swap_cols(self):
         self.cols, self.cols_alt = self.cols_alt, self.cols
         self.peer_cols, self.peer_cols_alt = self.peer_cols_alt, self.peer_cols
+        self.extra, self.extra_alt = self.extra_alt, self.extra
+        self.peer_extra, self.peer_extra_alt = self.peer_extra_alt, self.peer_extra
 
     def set_params_host(self, params):
         """(n, d) host array -> SoA columns."""
@@ -477,6 +551,13 @@ def _all_gather_rows(t):
 
 
 def _all_reduce_sum(t):
+    """In-place sum over ranks.  Small float64 records go through the peer-memory exchange kernel
+    (rank-order add chain: bit-identical on every rank), everything else through NCCL."""
+    px = PeerExchange.get()
+    if px is not None and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= px.max_vals:
+        src = t.clone()
+        px.gather(src, reduce=True, out=t)
+        return t
     import torch.distributed as dist
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
@@ -485,13 +566,33 @@ def _all_reduce_sum(t):
 # ---------------------------------------------------------------------------------------------
 # (a) reweight
 # ---------------------------------------------------------------------------------------------
-def reweight(st, path):
-    """Updater._compute_new_weights + Particles normalisation (updater.py:122-133,
-    particles.py:141-162).  Returns (ess, total_unnorm_log_weight) after one host sync."""
-    _, world = dist_info()
+def _rw_inputs(st):
+    """(lp pointer, lp_const, lw_in) of the reweight / search kernels: the summed log-prior column is
+    skipped when it is one constant over the shard and the path has no proposal column."""
     lw_in = None if st.uniform_weights else st.log_w
+    if st.lp_const is not None and st.lq is None:
+        return None, float(st.lp_const), lw_in
+    return st.lp, 0.0, lw_in
+
+
+def reweight(st, path, ess_threshold=-1.0):
+    """Updater._compute_new_weights + Particles normalisation (updater.py:97-133,
+    particles.py:141-162) in one cooperative launch.  Returns (ess, total_unnorm_log_weight) after
+    one host sync.  With ess_threshold >= 0 a step whose ESS falls below threshold * N does not
+    materialise its weights (st.pending; resample() scans them straight from the columns)."""
+    _, world = dist_info()
+    lp, lpc, lw_in = _rw_inputs(st)
     s = stream_ptr()
-    if world == 1:
+    px = PeerExchange.get() if world > 1 else None
+    fused = (world == 1 or px is not None) and not _lib.lib.smcb_get_option(b"no_coop")
+    st.pending = None
+    if fused:
+        with _timed("reweight"):
+            x = C.byref(px.next_bisect_gen()) if px is not None else None
+            call("smcb_reweight_fused", st.n, ptr(st.ll), ptr(lp), lpc, ptr(st.lq), ptr(lw_in), st.n_global,
+                 C.byref(path), float(ess_threshold), ptr(st.log_w_alt), ptr(st.w_alt), ptr(st.scalars), ptr(st.ws),
+                 x, s)
+    elif world == 1:
         with _timed("reweight"):
             call("smcb_reweight", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
                  C.byref(path), ptr(st.log_w_alt), ptr(st.w_alt), ptr(st.scalars), ptr(st.ws), s)
@@ -504,12 +605,26 @@ def reweight(st, path):
             call("smcb_lse_merge", ptr(parts), world, ptr(st.scalars), s)
             call("smcb_reweight_finalize", st.n, ptr(st.ll), ptr(st.lp), ptr(st.lq), ptr(lw_in), st.n_global,
                  C.byref(path), ptr(st.scalars), ptr(st.log_w_alt), ptr(st.w_alt), s)
-    st.log_w, st.log_w_alt = st.log_w_alt, st.log_w
-    st.w, st.w_alt = st.w_alt, st.w
-    st.uniform_weights = False
-    sc = st.scalars[:6].cpu().numpy()                        # step-boundary sync
+    sc = st.scalars[:8].cpu().numpy()                        # step-boundary sync
+    if fused and sc[7] < 0:
+        raise RuntimeError("fused multi-GPU reweight: a peer rank never answered")
+    if fused and sc[6] != 1.0:
+        st.pending = dict(path=path, lp=lp, lp_const=lpc, lw_in=lw_in)
+    else:
+        st.log_w, st.log_w_alt = st.log_w_alt, st.log_w
+        st.w, st.w_alt = st.w_alt, st.w
+        st.uniform_weights = False
     st.total_unnorm_log_weight = float(sc[3])
     return float(sc[4]), float(sc[3])
+
+
+def materialize_weights(st):
+    """Writes the weights of a pending reweight (the step did not resample after all): the same
+    launch again with the resampling test switched off.  Collective on several GPUs."""
+    p = st.pending
+    if p is None:
+        return
+    reweight(st, p["path"], ess_threshold=-1.0)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -524,21 +639,19 @@ def bisect_iters(phi_old):
 
 
 def find_phi(st, spec, phi_old, target_ess, lam=1.0):
-    """AdaptiveSampler.optimize_step's root search (samplers.py:250-259) on the device."""
+    """AdaptiveSampler.optimize_step's root search (samplers.py:250-259) on the device: one
+    cooperative launch (smcb_ess_search), on several GPUs with the rank sums exchanged over NVLink
+    inside it.  st.search_info = (passes over the particles, evaluations scipy would have made)."""
     _, world = dist_info()
     s = stream_ptr()
     lp = None if (st.lq is None and spec is not None) else st.lp
     lp_const = spec.lp_const if spec is not None else 0.0
-    if world == 1:
+    px = PeerExchange.get() if world > 1 else None
+    if world == 1 or (px is not None and not os.environ.get("SMCB_NO_BISECT_XCHG")):
         with _timed("bisect"):
-            call("smcb_ess_bisect", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
-                 float(target_ess), st.n_global, ptr(st.bis), ptr(st.ws), s, launches=1)
-    elif AcceptExchange.get() is not None and not os.environ.get("SMCB_NO_BISECT_XCHG"):
-        # one cooperative launch per rank, partials exchanged over NVLink peer memory in the kernel
-        with _timed("bisect"):
-            xb = AcceptExchange.get().next_bisect_gen()
-            call("smcb_ess_bisect_xchg", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
-                 float(target_ess), st.n_global, ptr(st.bis), ptr(st.ws), C.byref(xb), s, launches=1)
+            x = C.byref(px.next_bisect_gen()) if px is not None else None
+            call("smcb_ess_search", st.n, ptr(st.ll), ptr(lp), ptr(st.lq), lp_const, float(phi_old), float(lam),
+                 float(target_ess), st.n_global, float(st.last_dphi), ptr(st.bis), ptr(st.ws), x, s, launches=1)
     else:
         with _timed("bisect"):
             call("smcb_ess_bisect_begin", float(phi_old), ptr(st.bis), s)
@@ -549,11 +662,13 @@ def find_phi(st, spec, phi_old, target_ess, lam=1.0):
                 parts = _all_gather_rows(part)
                 call("smcb_ess_bisect_update", ptr(parts), world, float(phi_old), float(target_ess), st.n_global,
                      ptr(st.bis), s)
-    b = st.bis[:10].cpu().numpy()
+    b = st.bis[:13].cpu().numpy()
     if b[2] < 0.0:
-        raise RuntimeError("fused multi-GPU bisection: a peer rank never answered")
+        raise RuntimeError("fused multi-GPU phi search: a peer rank never answered")
     if b[2] == 0.0:
-        raise RuntimeError("device bisection did not converge")
+        raise RuntimeError("device phi search did not converge")
+    st.search_info = (int(b[10]), int(b[1]))
+    st.last_dphi = float(b[0]) - float(phi_old)
     return float(b[0])
 
 
@@ -601,21 +716,82 @@ def gather_particles(st, idx):
     st.set_uniform_weights()
 
 
-def resample(st, kernel, resample_rng, warn_threshold):
+def weights_cdf(st, total_out=None):
+    """st.cdf <- inclusive scan of the step's normalised weights: recomputed from the resident columns
+    when the reweight left them pending (a resampling step never writes log_w / w), else from st.w."""
+    s = stream_ptr()
+    p = st.pending
+    if p is not None:
+        call("smcb_cdf_scan_weights", st.n, ptr(st.ll), ptr(p["lp"]), p["lp_const"], ptr(st.lq), ptr(p["lw_in"]),
+             st.n_global, C.byref(p["path"]), ptr(st.scalars), ptr(st.cdf), ptr(total_out), ptr(st.ws), s)
+    else:
+        call("smcb_cdf_scan", ptr(st.w), ptr(st.cdf), st.n, _lib.SCAN_LOOKBACK, ptr(st.ws), s)
+        if total_out is not None:
+            total_out.copy_(st.cdf[st.n - 1:st.n])
+
+
+def warn_collapsed(n_unique, n_global, warn_threshold):
+    if n_unique <= max(1, warn_threshold * n_global):
+        warnings.warn(f"Resampled to less than {warn_threshold * 100}% of particles; ", UserWarning)
+
+
+def run_deferred(st):
+    """Host-side checks whose device scalars were left unread during the step (one copy)."""
+    if not st.deferred:
+        return
+    items, st.deferred = st.deferred, []
+    vals = torch.stack([t.reshape(()).to(torch.float64) for t, _ in items]).cpu().numpy()
+    for v, (_, fn) in zip(vals, items):
+        fn(float(v))
+
+
+def resample(st, kernel, resample_rng, warn_threshold, defer=False):
     """Updater._resample (updater.py:135-165).  Replay mode (numpy Generator): both uniform
     draws of the reference (quirk Q1) are made on the host, the sequential scan gives
-    bit-exact indices.  Native mode: uniforms on the device, look-back scan, the distinct
-    ancestors are counted from the indices actually used."""
+    bit-exact indices.  Native mode: all built-in resamplers have sorted uniforms, so ONE fused pass
+    evaluates them, searches, gathers and counts the distinct ancestors (smcb_resample_fused).
+    defer=True leaves the collapse warning to run_deferred() (no host sync here)."""
     _, world = dist_info()
+    host_rng = isinstance(kernel.rng, np.random.Generator)
+    kind = getattr(resample_rng, "kind", None)
     if world > 1:
         from .sharded import resample_sharded
         with _timed("resample"):
-            return resample_sharded(st, kernel, resample_rng, warn_threshold)
+            return resample_sharded(st, kernel, resample_rng, warn_threshold, defer)
     n = st.n
-    host_rng = isinstance(kernel.rng, np.random.Generator)
-    kind = getattr(resample_rng, "kind", None)
     with _timed("resample"):
-        return _resample_local(st, kernel, resample_rng, warn_threshold, n, host_rng, kind)
+        if host_rng or kind is None or _lib.lib.smcb_get_option(b"no_fused_resample"):
+            materialize_weights(st)
+            return _resample_local(st, kernel, resample_rng, warn_threshold, n, host_rng, kind)
+        return _resample_fused(st, kernel, kind, warn_threshold, defer)
+
+
+def _resample_fused(st, kernel, kind, warn_threshold, defer):
+    rng = kernel.rng
+    s = stream_ptr()
+    stream_id = rng.next_stream()
+    weights_cdf(st)
+    r = _lib.Resample()
+    if kind == _lib.RESAMPLE_STANDARD:
+        # multinomial uniforms in sorted order: running sums of per-slot exponentials (st.u)
+        call("smcb_resample_exponential_sums", st.id_offset, st.n, st.n_global, rng.seed, stream_id, ptr(st.u),
+             None, ptr(st.ws), s)
+        r.t_peer[0] = st.u.data_ptr()
+    r.kind, r.world, r.rank, r.n_cols = int(kind), 1, 0, int(st.cols.shape[0])
+    r.n_local, r.n_global, r.seed, r.stream_id = st.n, st.n_global, rng.seed, stream_id
+    r.cdf, r.totals = st.cdf.data_ptr(), None
+    r.src, r.src_stride = st.cols.data_ptr(), st.col_stride
+    r.dst_peer[0], r.dst_stride = st.cols_alt.data_ptr(), st.col_stride
+    r.idx_out, r.n_unique_out = st.idx.data_ptr(), st.counts.data_ptr()
+    call("smcb_resample_fused", C.byref(r), ptr(st.ws), s)
+    st.swap_cols()
+    st.set_uniform_weights()
+    n_global = st.n_global
+    if defer:
+        st.deferred.append((st.counts[0:1].clone(), lambda v: warn_collapsed(v, n_global, warn_threshold)))
+    else:
+        warn_collapsed(int(st.counts[0].item()), n_global, warn_threshold)
+    return st.idx
 
 
 def _resample_local(st, kernel, resample_rng, warn_threshold, n, host_rng, kind):
@@ -642,8 +818,7 @@ def _resample_local(st, kernel, resample_rng, warn_threshold, n, host_rng, kind)
         idx = resample_indices(st, st.u, _lib.SCAN_LOOKBACK)
         n_unique = count_unique(st, idx)
     gather_particles(st, idx)
-    if int(n_unique.item()) <= max(1, warn_threshold * st.n_global):
-        warnings.warn(f"Resampled to less than {warn_threshold * 100}% of particles; ", UserWarning)
+    warn_collapsed(int(n_unique.item()), st.n_global, warn_threshold)
     return idx
 
 
@@ -671,8 +846,10 @@ def covariance(st, two_pass=False):
     s = stream_ptr()
     d = st.d
     st._cov_one_pass = False
+    if getattr(st, "pending", None) is not None:
+        materialize_weights(st)
     if (not two_pass and d > 8 and st.n >= 148 * 128 and getattr(st, "shift", None) is not None
-            and not os.environ.get("SMCB_COV_TWO_PASS")):
+            and not _lib.lib.smcb_get_option(b"cov_two_pass")):
         try:
             with _timed("cov"):
                 call("smcb_weighted_moments_shifted", ptr(st.params), st.col_stride if hasattr(st, "col_stride") else st.n,
@@ -705,9 +882,14 @@ def covariance(st, two_pass=False):
     return st.cov
 
 
-def cholesky(st, cov_dev=None):
+def cholesky(st, cov_dev=None, lazy=False):
+    """Cholesky factor of the proposal covariance.  lazy=True (native generator): no host sync here --
+    a failed factorisation leaves L = 0, under which the Metropolis steps are the identity, and
+    mutate() repairs and repeats when it reads the flags at the end of the step."""
     call("smcb_cholesky", ptr(st.cov if cov_dev is None else cov_dev), st.d, ptr(st.chol), ptr(st.flags),
          stream_ptr())
+    if lazy:
+        return st.chol
     f = int(st.flags[0].item())
     if f & _lib.FLAG_COV_RESHIFT:
         # one-pass covariance taken about a shift too far from the mean: redo it in two passes
@@ -758,11 +940,12 @@ class _timed:
             PROFILE.setdefault(self.name, []).append((self.a, self.b))
 
 
-def mutate(st, spec, num_samples, path, rng, check_incoming=False):
+def mutate(st, spec, num_samples, path, rng, check_incoming=False, lazy_chol=False):
     """VectorMCMC.smc_metropolis (vector_mcmc.py:46-62): `num_samples` fused Metropolis steps in
     place, proposal covariance rescaled from the global accept count after every step.
-    st.chol must hold the Cholesky factor of the proposal covariance.  Returns the list of
-    per-step accept counts lazily (device tensor)."""
+    st.chol must hold the Cholesky factor of the proposal covariance.  Returns the mutation ratio
+    after the ONE host sync of the call, which also reads the error flags, the checks deferred during
+    the step (st.deferred) and, with lazy_chol, the outcome of the factorisation."""
     if num_samples > _lib.MAX_MCMC_STEPS:
         raise ValueError("num_mcmc_samples > %d" % _lib.MAX_MCMC_STEPS)
     _, world = dist_info()
@@ -774,7 +957,7 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
     r.id_offset = st.id_offset
     keep = []
     lq = ptr(st.lq) if (spec.fused and spec.has_device_proposal) else None
-    xchg = AcceptExchange.get() if (world > 1 and spec.fused) else None
+    xchg = PeerExchange.get() if (world > 1 and spec.fused) else None
     xs = xchg.next_gen() if xchg is not None else None
     for k in range(num_samples):
         if host_rng:
@@ -801,20 +984,37 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False):
         if world > 1:
             _all_reduce_sum(st.accept_counts[k:k + 1])
     call("smcb_count_moved", ptr(st.moved), st.n, ptr(st.counts[1:]), ptr(st.ws), s)
+    # one record for the host: [moved, flag bits 0..4, deferred scalars...]; summed over the ranks so
+    # that every rank raises (or none does)
+    items, st.deferred = st.deferred, []
+    extra = [t.reshape(1).to(torch.float64) for t, _ in items]
     if world > 1:
-        # one collective for the moved count and the error flags, so that every rank raises
-        # (or none does): [moved, flag bit 0..3 set on this rank]
-        pack = torch.zeros(5, dtype=torch.int64, device=st.cols.device)
-        pack[0] = st.counts[1]
-        pack[1:] = (st.flags[0].to(torch.int64) >> torch.arange(4, device=st.cols.device)) & 1
+        bits = (st.flags[0].to(torch.int64) >> torch.arange(5, device=st.cols.device)) & 1
+        pack = torch.cat([st.counts[1:2].to(torch.float64), bits.to(torch.float64)] + extra)
         _all_reduce_sum(pack)
-        packed = pack.cpu().numpy()
-        st.flags[0] = int(sum((1 << b) for b in range(4) if packed[1 + b] > 0))
+        packed = pack.cpu().numpy()                          # the step's host sync
+        flags = int(sum((1 << b) for b in range(5) if packed[1 + b] > 0))
+        rest = packed[6:]
+    else:
+        packed = torch.cat([st.counts[1:2].to(torch.float64), st.flags[0:1].to(torch.float64)] + extra).cpu().numpy()
+        flags = int(packed[1])
+        rest = packed[2:]
+    for v, (_, fn) in zip(rest, items):
+        fn(float(v))
+    if lazy_chol and (flags & (_lib.FLAG_CHOL_FAIL | _lib.FLAG_COV_RESHIFT)):
+        st.flags[0] = flags & ~(_lib.FLAG_CHOL_FAIL | _lib.FLAG_COV_RESHIFT)
+        if flags & _lib.FLAG_CHOL_FAIL:
+            # the steps above ran with L = 0 (identity): factorise properly and repeat them
+            if getattr(st, "_cov_one_pass", False):
+                covariance(st, two_pass=True)
+            cholesky(st)
+            return mutate(st, spec, num_samples, path, rng, check_incoming, lazy_chol=False)
+        st.shift = None                                      # one-pass covariance drifted: two passes next time
+        flags &= ~(_lib.FLAG_CHOL_FAIL | _lib.FLAG_COV_RESHIFT)
+    if flags:
+        st.flags[0] = flags
         st.check_flags("smc_metropolis")
-        return float(packed[0]) / st.n_global
-    moved = st.counts[1:2].clone()
-    st.check_flags("smc_metropolis")                         # sync; raises on NaN
-    return float(moved.item()) / st.n_global
+    return float(packed[0]) / st.n_global
 
 
 # ---------------------------------------------------------------------------------------------

@@ -45,6 +45,8 @@ class Initializer:
             rng = kernel.rng
             call("smcb_sample_priors", C.byref(spec.c), ptr(st.cols), st.n, st.n, rng.seed, rng.next_stream(),
                  st.id_offset, stream_ptr())
+        if not kernel.has_proposal():
+            st.lp_const = spec.lp_const      # drawn from the (flat) priors: every particle is inside the support
         engine.eval_incoming(st, spec)
         # the reference's Initializer does not test the priors (initializer.py:66-73): particles
         # drawn from a proposal may lie outside the prior support and simply get zero weight

@@ -25,11 +25,13 @@ class Mutator:
         if kernel.has_proposal() and not (kernel.spec.has_device_proposal and st.with_lq):
             raise NotImplementedError("mutation under GeometricPath(proposal=...) needs a MultivarIndependent "
                                       "of scipy norm / uniform components (device log q)")
+        import numpy as np
+        native = not isinstance(kernel.rng, np.random.Generator)
         engine.covariance(st)
-        engine.cholesky(st)
+        engine.cholesky(st, lazy=native)
         p = kernel.path
         path = engine.make_path(p.phi, p.phi, p.lam)
-        return engine.mutate(st, kernel.spec, num_samples, path, kernel.rng)
+        return engine.mutate(st, kernel.spec, num_samples, path, kernel.rng, lazy_chol=native)
 
     def mutate(self, particles, num_samples):
         st = particles.to_state()

@@ -82,8 +82,8 @@ class SamplerBase:
     def _do_smc_step(self, phi, num_mcmc_samples):
         """samplers.py:94-98 on the live device working set."""
         self._mcmc_kernel.path.phi = phi
-        st = self._updater.update_state(self._st)
-        ratio = self._mutator.mutate_state(st, num_mcmc_samples)
+        st = self._updater.update_state(self._st, defer=True)
+        ratio = self._mutator.mutate_state(st, num_mcmc_samples)      # reads the deferred checks with its one sync
         attrs = {"total_unnorm_log_weight": st.total_unnorm_log_weight, "phi": self._mcmc_kernel.path.phi,
                  "mutation_ratio": ratio}
         self.step = Particles.from_state(st, self._mcmc_kernel.param_order, attrs)

@@ -88,7 +88,68 @@ def sorted_uniforms(st, seed, stream_id):
     return st.u
 
 
-def resample_sharded(st, kernel, resample_rng, warn_threshold):
+def resample_sharded(st, kernel, resample_rng, warn_threshold, defer=False):
+    """Owner-computes resampling of sharded particles (reference semantics
+    smcpy/smc/updater.py:135-165): no request routing, no NCCL payload, no host round trip.
+      1. local look-back scan of the (globally normalised) weights, straight from the resident
+         columns when the reweight left them pending                    [smcb_cdf_scan_weights]
+         (+ running sums of the slot exponentials for multinomial)       [smcb_resample_exponential_sums]
+      2. rank totals exchanged through peer memory                       [smcb_xchg_allgather]
+      3. every rank derives the contiguous range of GLOBAL output slots whose (sorted) uniform falls
+         into its CDF segment, searches its own CDF and writes each selected row straight into the
+         SoA buffer of the rank that holds the slot over NVLink          [smcb_resample_fused]
+      4. distinct-ancestor counts summed through peer memory; the same exchange orders every rank's
+         row writes before anyone reads its new particles               [smcb_xchg_allgather]
+    Falls back to the routed NCCL form when symmetric memory is unavailable."""
+    rank, world = engine.dist_info()
+    rng = kernel.rng
+    kind = getattr(resample_rng, "kind", None)
+    if isinstance(rng, np.random.Generator) or kind is None:
+        raise NotImplementedError("multi-GPU resampling needs the native Philox generator and a built-in "
+                                  "resampler (replay parity mode is single-GPU)")
+    px = engine.PeerExchange.get()
+    if px is None or st.peer_cols_alt is None or st.peer_extra_alt is None or _lib.lib.smcb_get_option(b"no_fused_resample"):
+        return _resample_sharded_routed(st, kernel, resample_rng, warn_threshold)
+    import ctypes as C
+    n = st.n
+    s = stream_ptr()
+    ph = _Phases()
+    stream_id = rng.next_stream()
+    ph("rs_scan")
+    engine.weights_cdf(st, total_out=st.rs_tot[0:1])
+    r = _lib.Resample()
+    if kind == _lib.RESAMPLE_STANDARD:
+        call("smcb_resample_exponential_sums", st.id_offset, n, st.n_global, rng.seed, stream_id, ptr(st.extra_alt),
+             ptr(st.rs_tot[1:2]), ptr(st.ws), s)
+        for q in range(world):
+            r.t_peer[q] = st.peer_extra_alt[q]
+    ph("rs_totals")
+    totals = px.gather(st.rs_tot)                         # (world, 2) in rank order, identical on every rank
+    ph("rs_fused")
+    r.kind, r.world, r.rank, r.n_cols = int(kind), world, rank, int(st.cols.shape[0])
+    r.n_local, r.n_global, r.seed, r.stream_id = n, st.n_global, rng.seed, stream_id
+    r.cdf, r.totals = st.cdf.data_ptr(), totals.data_ptr()
+    r.src, r.src_stride = st.cols.data_ptr(), st.col_stride
+    for q in range(world):
+        r.dst_peer[q] = st.peer_cols_alt[q]
+    r.dst_stride = st.col_stride
+    r.idx_out, r.n_unique_out = None, st.counts.data_ptr()
+    call("smcb_resample_fused", C.byref(r), ptr(st.ws), s)
+    ph("rs_tail")
+    st.swap_cols()
+    n_unique = px.gather(st.counts[0:1].to(torch.float64), reduce=True)     # also the completion barrier
+    st.set_uniform_weights()
+    n_global = st.n_global
+    if defer:
+        # already global: scaled so that the step record's sum over ranks gives it back
+        st.deferred.append((n_unique / world, lambda v: engine.warn_collapsed(round(v), n_global, warn_threshold)))
+    else:
+        engine.warn_collapsed(int(n_unique.item()), n_global, warn_threshold)
+    ph(None)
+    return None
+
+
+def _resample_sharded_routed(st, kernel, resample_rng, warn_threshold):
     rank, world = engine.dist_info()
     rng = kernel.rng
     kind = getattr(resample_rng, "kind", None)
@@ -102,7 +163,7 @@ def resample_sharded(st, kernel, resample_rng, warn_threshold):
     ph = _Phases()
     # 1-2: local CDF and segment offsets
     ph("rs_scan")
-    call("smcb_cdf_scan", ptr(st.w), ptr(st.cdf), n, _lib.SCAN_LOOKBACK, ptr(st.ws), s)
+    engine.weights_cdf(st)
     totals = engine._all_gather_rows(st.cdf[n - 1:n]).reshape(-1)
     off = segment_offsets(totals)
     # 3: uniforms of my output slots, routed to the owning rank

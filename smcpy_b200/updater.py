@@ -46,20 +46,27 @@ class Updater:
     def resampled(self):
         return self._resampled
 
-    def update_state(self, st):
+    def update_state(self, st, defer=False):
         """In-place update of a device working set: reweight with the kernel path's
-        (phi_prev -> phi), then resample if ESS < threshold * N."""
+        (phi_prev -> phi), then resample if ESS < threshold * N.  The reweight launch applies the same
+        test on the device and leaves the weights of a resampling step unmaterialised (the CDF scan
+        recomputes them); the replay / parity mode always writes them.  defer=True (samplers): the
+        collapse warning is raised at the end of the step without a host sync of its own."""
         kernel = self._mcmc_kernel
         if kernel.has_proposal() and not st.with_lq:   # no device log q: evaluate it on the host
             st.lq = engine.dev(np.asarray(kernel.path.proposal.logpdf(st.params_host()),
                                           dtype=np.float64).reshape(-1))
-        ess, _ = engine.reweight(st, kernel.device_path())
+        native = not isinstance(kernel.rng, np.random.Generator)
+        ess, _ = engine.reweight(st, kernel.device_path(), self.ess_threshold if native else -1.0)
         self._ess = ess
         self._resampled = False
         self.last_indices = None
         if ess < self.ess_threshold * st.n_global:
             self._resampled = True
-            self.last_indices = engine.resample(st, kernel, self.resample_rng, self.particles_warn_threshold)
+            self.last_indices = engine.resample(st, kernel, self.resample_rng, self.particles_warn_threshold,
+                                                defer=defer)
+        else:
+            engine.materialize_weights(st)             # (never taken: host and device apply the same test)
         return st
 
     def update(self, particles):
