@@ -173,6 +173,9 @@ const char* smcb_last_mh_variant(void);
 /* measurement aid: `blocks` x 256 threads each run 8 independent chains of `iters` FP64 FMAs
  * (16 * iters flops per thread); out holds blocks*256 doubles. */
 int smcb_fp64_probe(double* out, int32_t blocks, int32_t iters, void* stream);
+/* the same for the FP64 tensor-core path: every warp runs 16 * iters mma.sync.m8n8k4.f64 (512 flops each)
+ * on 4 independent accumulator pairs; out holds blocks*256 doubles */
+int smcb_dmma_probe(double* out, int32_t blocks, int32_t iters, void* stream);
 /* out[i] = the streaming log-sum-exp loops' exp for x[i] <= 0 (table + degree-6 polynomial, ~1 ulp;
  * 0 below -708): accuracy probe for the tests, not part of the reference's path */
 int smcb_exp_probe(const double* x, double* out, int64_t n, void* stream);

@@ -88,6 +88,7 @@ SIGNATURES = {
     "smcb_aos_to_soa": [_P, _P, _I64, _I32, _I64, _P],
     "smcb_soa_to_aos": [_P, _P, _I64, _I32, _I64, _P],
     "smcb_fp64_probe": [_P, _I32, _I32, _P],
+    "smcb_dmma_probe": [_P, _I32, _I32, _P],
     "smcb_fill_f64": [_P, _I64, _D, _P],
     "smcb_reweight": [_I64, _P, _P, _P, _P, _I64, _PP(Path), _P, _P, _P, _P, _P],
     "smcb_path_eval": [_I64, _P, _P, _P, _PP(Path), _I32, _P, _P],

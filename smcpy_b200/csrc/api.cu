@@ -112,6 +112,41 @@ extern "C" int smcb_fp64_probe(double* out, int32_t blocks, int32_t iters, void*
     return smcb::check_launch("fp64_probe_kernel");
 }
 
+// FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) throughput probe: 4 independent accumulator pairs per warp,
+// 4 x 4 DMMAs per iteration and warp, 512 flops each.  The larger of the two probes is the FP64 roof
+// bench.py reports against (tools/probe/dmma_probe.cu: the two share one pipe).
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters, double a, double b) {
+    double m0[4], m1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m0[i] = threadIdx.x * 1e-3 + i;
+        m1[i] = i;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(m0[i]), "+d"(m1[i])
+                             : "d"(a), "d"(b));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += m0[i] + m1[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int smcb_dmma_probe(double* out, int32_t blocks, int32_t iters, void* stream) {
+    if (!out || blocks < 1 || iters < 1) {
+        smcb::set_error("smcb_dmma_probe: bad argument");
+        return SMCB_ERR_ARG;
+    }
+    dmma_probe_kernel<<<blocks, 256, 0, smcb::as_stream(stream)>>>(out, iters, 0.999, 1e-9);
+    return smcb::check_launch("dmma_probe_kernel");
+}
+
 __global__ void exp_probe_kernel(const double* x, double* out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = smcb::exp_nonpos(x[i]);

@@ -523,6 +523,7 @@ class DeviceState:
         call("smcb_fill_f64", ptr(self.log_w), self.n, lw, stream_ptr())
         call("smcb_fill_f64", ptr(self.w), self.n, w, stream_ptr())
         self.uniform_weights = True
+        self.pending = None
 
     def check_flags(self, where, allow_oob=False):
         f = int(self.flags[0].item())

@@ -403,8 +403,8 @@ def test_sampler_internals_replay_vs_reference_fixture(sb):
         orig_update = sbm.updater.Updater.update_state
         orig_cov = engine.covariance
 
-        def update_state(self, st):
-            out = orig_update(self, st)
+        def update_state(self, st, **kw):
+            out = orig_update(self, st, **kw)
             rec["ess"].append(self.ess)
             rec["res"].append(self.resampled)
             rec["idx"].append(None if self.last_indices is None else self.last_indices.cpu().numpy().copy())
