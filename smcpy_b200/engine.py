@@ -616,6 +616,9 @@ def reweight(st, path, ess_threshold=-1.0):
         st.w, st.w_alt = st.w_alt, st.w
         st.uniform_weights = False
     st.total_unnorm_log_weight = float(sc[3])
+    # ll + every optional input column read once; log_w and w written only when materialised
+    cols_in = 1 + (lp is not None if fused else 1) + (st.lq is not None) + (lw_in is not None)
+    _note_bytes("reweight", st.n * (8.0 * cols_in * (1 if fused else 2) + (16.0 if st.pending is None else 0.0)))
     return float(sc[4]), float(sc[3])
 
 
@@ -669,6 +672,7 @@ def find_phi(st, spec, phi_old, target_ess, lam=1.0):
     if b[2] == 0.0:
         raise RuntimeError("device phi search did not converge")
     st.search_info = (int(b[10]), int(b[1]))
+    _note_bytes("bisect", st.n * 8.0 * (1 + (lp is not None) + (st.lq is not None)) * max(1, int(b[10])))
     st.last_dphi = float(b[0]) - float(phi_old)
     return float(b[0])
 
@@ -921,8 +925,15 @@ def eval_incoming(st, spec, lp_cols=None):
         eval_incoming_callable(st, spec, lp_cols)
 
 
-# optional kernel timing (bench.py): name -> list of (start, end) CUDA events on the launch stream
+# optional kernel timing (bench.py): name -> list of (start, end) CUDA events on the launch stream;
+# PROFILE_BYTES: name -> algorithmic HBM bytes of each of those calls on this rank (include/smcb200.h)
 PROFILE = None
+PROFILE_BYTES = {}
+
+
+def _note_bytes(name, nbytes):
+    if PROFILE is not None:
+        PROFILE_BYTES.setdefault(name, []).append(float(nbytes))
 
 
 class _timed:

@@ -11,7 +11,7 @@ from tests.golden import configs
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 K = 20
 if cfg == "c2":
-    problem = bench.c2_problem(); n = 1 << 20
+    problem = configs.linear_problem(1000, sigma=0.5, data_seed=0); n = 1 << 20
 elif cfg == "c5":
     problem = configs.gauss_problem(32); n = 1 << 23
 elif cfg == "c3":
