@@ -40,6 +40,7 @@ extern "C" {
 #define SMCB_MAX_PRIORS 32
 #define SMCB_MAX_COV_ARGS 6         /* MVNormal: F <= 3 features -> F(F+1)/2 packed terms */
 #define SMCB_MAX_MCMC_STEPS 4096    /* accept-count history length per mutate call */
+#define SMCB_MVN_STATS 12           /* MVNormal snapshot statistics: mean[3] + scatter[3][3] (smcb_mvn_scatter) */
 
 enum { SMCB_OK = 0, SMCB_ERR_ARG = 1, SMCB_ERR_CUDA = 2, SMCB_ERR_UNSUPPORTED = 3 };
 
@@ -57,7 +58,13 @@ enum { SMCB_LL_NORMAL = 1 /* :22-49 */, SMCB_LL_MVNORMAL = 2 /* :121-192 */, SMC
 enum {
     SMCB_PRIOR_UNIFORM = 1,           /* scipy.stats.uniform(loc=a, scale=b) */
     SMCB_PRIOR_IMPROPER_UNIFORM = 2,  /* smcpy/priors.py:6-35, bounds [a, b] inclusive */
-    SMCB_PRIOR_IMPROPER_COV = 3       /* smcpy/priors.py:93-147, ncols x ncols PD test */
+    SMCB_PRIOR_IMPROPER_COV = 3,      /* smcpy/priors.py:93-147, ncols x ncols PD test; a = inverse-Wishart dof of
+                                         its rvs (:118-123), scale factor in smcb_problem_t::iw_chol */
+    SMCB_PRIOR_EXTERNAL = 4           /* any other prior object (InvWishart :38-90, ImproperConstrainedUniform
+                                         :150-247, user classes): `ncols` parameter columns whose log-pdf the HOST
+                                         evaluates and adds to the log-prior column of the un-fused route
+                                         (smcb_mh_propose / smcb_mh_accept); the device treats it as 0 and the
+                                         fused kernels refuse it */
 };
 /* device error-flag bits (checked by the host at step boundaries) */
 enum {
@@ -119,6 +126,11 @@ typedef struct smcb_problem {
     int32_t seg_sigma_col[SMCB_MAX_SEGMENTS]; /* -1 = fixed (seg_sigma), else parameter column */
     int32_t pad2;
     double seg_sigma[SMCB_MAX_SEGMENTS];
+    /* MVNormal: device, SMCB_MVN_STATS doubles written by smcb_mvn_scatter(data, S, F, ...) once per problem */
+    const double* mvn_stats;
+    /* IMPROPER_COV priors, in prior order (at most 2): lower Cholesky factor of the inverse-Wishart scale
+     * matrix of their rvs, packed row-major (l00, l10, l11, l20, l21, l22); used by smcb_sample_priors only */
+    double iw_chol[2][6];
 } smcb_problem_t;
 
 /* GeometricPath state (smcpy/paths.py:64-112): exponents are derived inside the
@@ -163,7 +175,8 @@ size_t smcb_workspace_bytes(int64_t n, int32_t d);
  * every variant the dispatcher may take.  Names: "no_tma", "strict_proposal" (wide identity
  * Metropolis kernel: fp64 FMAs for sqrt(s) L z instead of the tf32 tensor-core product),
  * "linear_cfg", "persist", "no_dmma", "cov_two_pass", "no_coop", "coop_tpb", "coop_bps",
- * "bisect_plain", "spring_ppt".  smcb_get_option returns INT64_MIN for an unknown name. */
+ * "bisect_plain", "spring_ppt" (-1 auto, 1 / 2 interleaved RK4 chains per thread), "no_mvn3" (generic MVNormal
+ * kernel instead of the static 3-feature layout), "no_fused_resample", "xchg_timeout_s".  smcb_get_option returns INT64_MIN for an unknown name. */
 int smcb_set_option(const char* name, int64_t value);
 int64_t smcb_get_option(const char* name);
 /* Text description of the Metropolis kernel instantiation the calling thread launched last
@@ -399,6 +412,11 @@ int smcb_cov_from_shifted_sums(const double* sums, double* shift, int32_t d, dou
 int smcb_cholesky(const double* cov, int32_t d, double* chol_out, int32_t* flags, void* stream);
 
 /* ---- (d) vectorised Metropolis ------------------------------------------------------ */
+/* MVNormal (smcpy/log_likelihoods.py:150-192): the model output is the same for every snapshot, so the
+ * kernels need the S x F data only through its mean and scatter matrix.  stats_out (device,
+ * SMCB_MVN_STATS doubles) = mean[3], sum_s (y_s - mean)(y_s - mean)^T [3][3] (zero padded for F < 3);
+ * set smcb_problem_t::mvn_stats to it.  data: device, S x F row-major, F <= 3. */
+int smcb_mvn_scatter(const double* data, int32_t n_snapshots, int32_t n_features, double* stats_out, void* stream);
 /* log-priors + log-likelihood of incoming particles
  * (vector_mcmc.py:162-166 _initialize_probabilities, initializer.py:66-73).
  * lp_cols_out (optional, n_priors x stride) = un-summed log priors (vector_mcmc.py:98-111).

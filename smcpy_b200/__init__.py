@@ -10,11 +10,12 @@ __version__ = "0.1.0"
 
 from .engine import PhiloxRNG                                               # noqa: F401
 from .kernel import KernelBase, VectorMCMCKernel                            # noqa: F401
-from .log_likelihoods import MultiSourceNormal, MVNormal, Normal                               # noqa: F401
+from .hierarch_log_likelihoods import ApproxHierarch, MVNHierarchModel      # noqa: F401
+from .log_likelihoods import MultiSourceNormal, MVNormal, Normal            # noqa: F401
 from .models import IdentityModel, LinearModel, NvrtcModel, SpringMassModel             # noqa: F401
 from .particles import Particles                                            # noqa: F401
 from .paths import GeometricPath                                            # noqa: F401
-from .priors import ImproperCov, ImproperUniform                            # noqa: F401
+from .priors import ImproperConstrainedUniform, ImproperCov, ImproperUniform, InvWishart  # noqa: F401
 from .proposals import MultivarIndependent                                  # noqa: F401
 from .resampler_rngs import standard, stratified, systematic                # noqa: F401
 from .samplers import AdaptiveSampler, FixedPhiSampler, FixedTimeSampler, MaxStepSampler  # noqa: F401

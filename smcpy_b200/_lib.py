@@ -17,11 +17,12 @@ MAX_PARAMS = 32
 MAX_PRIORS = 32
 MAX_COV_ARGS = 6
 MAX_MCMC_STEPS = 4096
+MVN_STATS = 12
 
 MODEL_LINEAR, MODEL_SPRING_MASS, MODEL_IDENTITY = 1, 2, 3
 LL_NORMAL, LL_MVNORMAL, LL_MULTISOURCE = 1, 2, 3
 MAX_SEGMENTS = 8
-PRIOR_UNIFORM, PRIOR_IMPROPER_UNIFORM, PRIOR_IMPROPER_COV = 1, 2, 3
+PRIOR_UNIFORM, PRIOR_IMPROPER_UNIFORM, PRIOR_IMPROPER_COV, PRIOR_EXTERNAL = 1, 2, 3, 4
 FLAG_PRIOR_OOB, FLAG_MODEL_NAN, FLAG_COV_NOT_PD, FLAG_CHOL_FAIL, FLAG_COV_RESHIFT = 1, 2, 4, 8, 16
 RESAMPLE_STANDARD, RESAMPLE_STRATIFIED, RESAMPLE_SYSTEMATIC = 0, 1, 2
 SCAN_SEQUENTIAL, SCAN_LOOKBACK = 0, 1
@@ -48,7 +49,8 @@ class Problem(C.Structure):
                 ("priors", Prior * MAX_PRIORS), ("has_proposal", C.c_int32), ("pad", C.c_int32),
                 ("proposal", ProposalCol * MAX_PARAMS), ("n_segments", C.c_int32),
                 ("seg_len", C.c_int32 * MAX_SEGMENTS), ("seg_sigma_col", C.c_int32 * MAX_SEGMENTS),
-                ("pad2", C.c_int32), ("seg_sigma", C.c_double * MAX_SEGMENTS)]
+                ("pad2", C.c_int32), ("seg_sigma", C.c_double * MAX_SEGMENTS), ("mvn_stats", C.c_void_p),
+                ("iw_chol", (C.c_double * 6) * 2)]
 
 
 class Path(C.Structure):
@@ -88,6 +90,7 @@ SIGNATURES = {
     "smcb_aos_to_soa": [_P, _P, _I64, _I32, _I64, _P],
     "smcb_soa_to_aos": [_P, _P, _I64, _I32, _I64, _P],
     "smcb_fp64_probe": [_P, _I32, _I32, _P],
+    "smcb_mvn_scatter": [_P, _I32, _I32, _P, _P],
     "smcb_dmma_probe": [_P, _I32, _I32, _P],
     "smcb_fill_f64": [_P, _I64, _D, _P],
     "smcb_reweight": [_I64, _P, _P, _P, _P, _I64, _PP(Path), _P, _P, _P, _P, _P],

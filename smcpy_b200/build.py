@@ -32,7 +32,8 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(PKG), "include", "smcb200.h")]
+    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(PKG), "include", "smcb200.h"))
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()

@@ -41,6 +41,7 @@ Options& options() {
         v.coop_bps = env_int("SMCB_COOP_BPS", 0);
         v.bisect_plain = env_int("SMCB_BISECT_PLAIN", 0);
         v.spring_ppt = env_int("SMCB_SPRING_PPT", -1);
+        v.no_mvn3 = env_int("SMCB_NO_MVN3", 0);
         v.xchg_timeout_s = env_int("SMCB_XCHG_TIMEOUT_S", 0);
         v.no_fused_resample = env_int("SMCB_NO_FUSED_RESAMPLE", 0);
         return v;
@@ -66,6 +67,7 @@ static const OptEntry kOptTable[] = {
     {"coop_bps", &Options::coop_bps},       {"bisect_plain", &Options::bisect_plain},
     {"spring_ppt", &Options::spring_ppt},   {"xchg_timeout_s", &Options::xchg_timeout_s},
     {"no_fused_resample", &Options::no_fused_resample},
+    {"no_mvn3", &Options::no_mvn3},
 };
 
 }  // namespace smcb

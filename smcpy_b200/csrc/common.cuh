@@ -42,6 +42,7 @@ struct Options {
     int coop_tpb, coop_bps;// cooperative kernels: threads per block, blocks per SM
     int bisect_plain;      // 1: evaluate every scipy midpoint (no monotone bracketing)
     int spring_ppt;        // -1 auto; 1/2 particles per thread in the RK4 kernel
+    int no_mvn3;           // 1: never take the static-layout MVNormal kernel (K_LINEAR_MVN3)
     int xchg_timeout_s;    // peer-exchange time-out inside kernels (seconds; 0 = default 30)
     int no_fused_resample; // 1: separate uniforms / search / count / gather kernels (native mode)
 };

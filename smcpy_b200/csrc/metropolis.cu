@@ -22,8 +22,14 @@ namespace smcb {
 
 constexpr int kMhThreads = 128;
 constexpr int kChunk = 1024;          // data points staged per shared-memory chunk
+constexpr int kMvnStats = SMCB_MVN_STATS;   // MVNormal: snapshot mean (3) + scatter matrix (3 x 3)
 
-enum Kind { K_LINEAR_NORMAL = 0, K_SPRING_NORMAL = 1, K_IDENTITY_NORMAL = 2, K_LINEAR_MVN = 3 };
+// K_LINEAR_MVN3: the MVNormal layout of config C4 -- 3 features, all six covariance terms sampled in the
+// trailing columns 2..7 (and, if present, one 3 x 3 ImproperCov prior over the same columns): every column
+// index is a compile-time constant, so the parameter registers never spill to an indexable local array
+// (profiles/r01_c3_c4_kernels.md: STL.64 in the hot loop of the generic kind).
+enum Kind { K_LINEAR_NORMAL = 0, K_SPRING_NORMAL = 1, K_IDENTITY_NORMAL = 2, K_LINEAR_MVN = 3, K_LINEAR_MVN3 = 4 };
+__host__ __device__ constexpr bool is_mvn(int kind) { return kind == K_LINEAR_MVN || kind == K_LINEAR_MVN3; }
 
 // per-column view of the prior table (host-built from smcb_problem_t::priors).  Scalar priors
 // share one branch-free support test:  t = x - a;  lo <= t <= hi.
@@ -35,6 +41,7 @@ struct ColPriors {
     int8_t prior_of_col[SMCB_MAX_PARAMS];   // -1: column belongs to a matrix prior
     double a[SMCB_MAX_PARAMS], lo[SMCB_MAX_PARAMS], hi[SMCB_MAX_PARAMS], logp[SMCB_MAX_PARAMS];
     double logp_total;                      // sum of logp in column order
+    int32_t n_external;                     // number of EXTERNAL (host-evaluated) priors
     int32_t n_cov;                          // number of IMPROPER_COV priors (<= 2)
     int32_t cov_c0[2], cov_ncols[2], cov_prior[2];
 };
@@ -143,6 +150,27 @@ __device__ __noinline__ Float16 gen_normals16(uint32_t k0, uint32_t k1, uint64_t
     return z;
 }
 
+// Cholesky pivots and inverse diagonal of a symmetric 3 x 3 matrix (unblocked, LAPACK dpotf2 failure rule:
+// pivot <= 0 or NaN).  One rsqrt per pivot, no division: l_ij = c_ij * (1 / sqrt(pivot)).
+struct Chol3 {
+    double i00, i11, i22, l10, l20, l21, p00, p11, p22;
+    bool pd;
+};
+__device__ __forceinline__ Chol3 chol3(const double (&c)[3][3]) {
+    Chol3 f;
+    f.p00 = c[0][0];
+    f.i00 = rsqrt(f.p00);
+    f.l10 = c[1][0] * f.i00;
+    f.l20 = c[2][0] * f.i00;
+    f.p11 = c[1][1] - f.l10 * f.l10;
+    f.i11 = rsqrt(f.p11);
+    f.l21 = (c[2][1] - f.l20 * f.l10) * f.i11;
+    f.p22 = c[2][2] - f.l20 * f.l20 - f.l21 * f.l21;
+    f.i22 = rsqrt(f.p22);
+    f.pd = (f.p00 > 0.0) && (f.p11 > 0.0) && (f.p22 > 0.0);
+    return f;
+}
+
 template <int KIND, int DMAX, bool EXACT>
 __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th)[DMAX], double* lp_cols_row,
                                               int64_t col_stride) {
@@ -170,7 +198,7 @@ __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th
     // matrix priors: packed upper-triangular columns must form a Cholesky-PD matrix.
     // Compiled for the MVNormal kind only: the runtime column selects would otherwise push
     // th[] into local memory for every kernel.
-    if constexpr (KIND == K_LINEAR_MVN)
+    if constexpr (is_mvn(KIND))
     for (int q = 0; q < a.cp.n_cov; ++q) {
         const int c0 = a.cp.cov_c0[q], nc = a.cp.cov_ncols[q];
         double m[3][3];
@@ -180,7 +208,10 @@ __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th
 #pragma unroll
             for (int s = r; s < 3; ++s) {
                 double v = (r == s) ? 1.0 : 0.0;
-                if (r < nc && s < nc) {
+                if constexpr (KIND == K_LINEAR_MVN3) {
+                    v = th[(2 + e < DMAX) ? 2 + e : 0];
+                    ++e;
+                } else if (r < nc && s < nc) {
                     v = 0.0;
 #pragma unroll
                     for (int c = 0; c < DMAX; ++c) v = (c == c0 + e) ? th[c] : v;
@@ -189,18 +220,7 @@ __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th
                 m[r][s] = v;
                 m[s][r] = v;
             }
-        // unblocked Cholesky pivots (LAPACK dpotf2 failure rule: pivot <= 0 or NaN)
-        bool pd = true;
-        const double l00 = m[0][0];
-        pd = pd && (l00 > 0.0);
-        const double r00 = sqrt(l00);
-        const double l10 = m[1][0] / r00, l20 = m[2][0] / r00;
-        const double p11 = m[1][1] - l10 * l10;
-        pd = pd && (p11 > 0.0);
-        const double r11 = sqrt(p11);
-        const double l21 = (m[2][1] - l20 * l10) / r11;
-        const double p22 = m[2][2] - l20 * l20 - l21 * l21;
-        pd = pd && (p22 > 0.0);
+        const bool pd = chol3(m).pd;
         const double v = pd ? 0.0 : kNegInf;
         lps += v;
         if (lp_cols_row) lp_cols_row[(int64_t)a.cp.cov_prior[q] * col_stride] = v;
@@ -246,10 +266,11 @@ __device__ __forceinline__ void stage_data(const MhArgs& a, double* sdata, int b
         double2* sxy = reinterpret_cast<double2*>(sdata);
         for (int j = threadIdx.x; j < cnt; j += blockDim.x)
             sxy[j] = make_double2(a.prob.xgrid[base + j], a.prob.data[base + j]);
-    } else if (KIND == K_LINEAR_MVN) {
-        const int F = a.prob.n_data, S = a.prob.n_snapshots;
-        for (int j = threadIdx.x; j < S * F; j += blockDim.x) sdata[j] = a.prob.data[j];
-        for (int j = threadIdx.x; j < F; j += blockDim.x) sdata[S * F + j] = a.prob.xgrid[j];
+    } else if (is_mvn(KIND)) {
+        // [0..2] mean of the snapshots, [3..11] their scatter matrix (3 x 3, zero padded), [12..14] X
+        const int F = a.prob.n_data;
+        for (int j = threadIdx.x; j < kMvnStats; j += blockDim.x) sdata[j] = a.prob.mvn_stats[j];
+        for (int j = threadIdx.x; j < 3; j += blockDim.x) sdata[kMvnStats + j] = (j < F) ? a.prob.xgrid[j] : 0.0;
     } else {
         for (int j = threadIdx.x; j < cnt; j += blockDim.x) sdata[j] = a.prob.data[base + j];
         if (KIND == K_IDENTITY_NORMAL && threadIdx.x == 0) {       // constants of normal_ll, slots past DMAX <= 32
@@ -308,16 +329,26 @@ __device__ __forceinline__ void ll_linear_normal(const MhArgs& a, const double (
     }
 }
 
-template <int DMAX>
-__device__ __forceinline__ double ll_spring_normal(const MhArgs& a, const double (&th)[DMAX], bool run,
-                                                   bool resident, double* sy) {
+// Spring-mass ODE (classical RK4 on (x, v), nsub sub-steps per output point) + Normal likelihood for PPT
+// particles per thread: the sub-steps of one particle are a dependent DFMA/DADD chain, so PPT independent
+// chains are interleaved to keep the FP64 pipe fed (profiles/r01_c3_c4_kernels.md: 35 % `math` stalls at
+// PPT = 1).  Per particle the arithmetic (operations and their order) does not depend on PPT.
+template <int DMAX, int PPT>
+__device__ __forceinline__ void ll_spring_normal(const MhArgs& a, const double (&th)[PPT][DMAX], bool run_any,
+                                                 bool resident, double* sy, double (&ll)[PPT]) {
     const int m = a.prob.n_data;
-    const double K = th[0], g = th[1];
-    double x = a.prob.model_args[0], v = a.prob.model_args[1];
+    double K[PPT], g[PPT], x[PPT], v[PPT], ssq[PPT];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        K[p] = th[p][0];
+        g[p] = th[p][1];
+        x[p] = a.prob.model_args[0];
+        v[p] = a.prob.model_args[1];
+        ssq[p] = 0.0;
+    }
     const int nsub = (int)a.prob.model_args[3];
     const double h = a.prob.model_args[2] / (double)nsub;
     const double hh = 0.5 * h, h6 = h / 6.0;
-    double ssq = 0.0;
     for (int base = 0; base < m; base += kChunk) {
         const int cnt = (m - base < kChunk) ? (m - base) : kChunk;
         if (!resident) {
@@ -325,28 +356,38 @@ __device__ __forceinline__ double ll_spring_normal(const MhArgs& a, const double
             stage_data<K_SPRING_NORMAL>(a, sy, base, cnt);
             __syncthreads();
         }
-        if (run) {
+        if (run_any) {
             for (int j = 0; j < cnt; ++j) {
                 if (base + j > 0) {
-                    for (int s = 0; s < nsub; ++s) {       // classical RK4 on (x, v)
-                        const double k1x = v, k1v = g - K * x;
-                        const double x2 = x + hh * k1x, v2 = v + hh * k1v;
-                        const double k2x = v2, k2v = g - K * x2;
-                        const double x3 = x + hh * k2x, v3 = v + hh * k2v;
-                        const double k3x = v3, k3v = g - K * x3;
-                        const double x4 = x + h * k3x, v4 = v + h * k3v;
-                        const double k4x = v4, k4v = g - K * x4;
-                        x = x + h6 * (k1x + 2.0 * k2x + 2.0 * k3x + k4x);
-                        v = v + h6 * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
+                    for (int s = 0; s < nsub; ++s) {
+#pragma unroll
+                        for (int p = 0; p < PPT; ++p) {
+                            const double k1x = v[p], k1v = g[p] - K[p] * x[p];
+                            const double x2 = x[p] + hh * k1x, v2 = v[p] + hh * k1v;
+                            const double k2x = v2, k2v = g[p] - K[p] * x2;
+                            const double x3 = x[p] + hh * k2x, v3 = v[p] + hh * k2v;
+                            const double k3x = v3, k3v = g[p] - K[p] * x3;
+                            const double x4 = x[p] + h * k3x, v4 = v[p] + h * k3v;
+                            const double k4x = v4, k4v = g[p] - K[p] * x4;
+                            x[p] = x[p] + h6 * (k1x + 2.0 * k2x + 2.0 * k3x + k4x);
+                            v[p] = v[p] + h6 * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
+                        }
                     }
                 }
-                const double dd = x - sy[j];
-                ssq = fma(dd, dd, ssq);
+                const double y = sy[j];
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    const double dd = x[p] - y;
+                    ssq[p] = fma(dd, dd, ssq[p]);
+                }
             }
         }
     }
-    const double sigma = a.prob.sigma_is_param ? th[DMAX > 2 ? 2 : 0] : a.prob.sigma;
-    return normal_ll(ssq, sigma, m);
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const double sigma = a.prob.sigma_is_param ? th[p][DMAX > 2 ? 2 : 0] : a.prob.sigma;
+        ll[p] = normal_ll(ssq[p], sigma, m);
+    }
 }
 
 // sy[m] = term1 = -log(2 pi var) * (M/2), sy[m+1] = -1/(2 var): computed once per block by
@@ -367,13 +408,18 @@ __device__ __forceinline__ double ll_identity_normal(const MhArgs& a, const doub
 }
 
 // MVNormal (log_likelihoods.py:150-192) with one Cholesky per particle:
-//   sum_s [ -F/2 log 2pi - 1/2 log det C - 1/2 e_s^T C^-1 e_s ],  e_s = model - data_s
-template <int DMAX>
+//   sum_s [ -F/2 log 2pi - 1/2 log det C - 1/2 e_s^T C^-1 e_s ],  e_s = model - data_s.
+// The model output is the same for every snapshot, so with ybar = mean_s data_s and the scatter matrix
+// W = sum_s (data_s - ybar)(data_s - ybar)^T (smcb_mvn_scatter, once per problem)
+//   sum_s e_s^T C^-1 e_s = S (model - ybar)^T C^-1 (model - ybar) + tr(C^-1 W):
+// O(F^2) per particle instead of O(S F^2), whatever the model.
+template <int KIND, int DMAX>
 __device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&th)[DMAX], bool run,
                                                 const double* sdat, bool& not_pd) {
-    const int F = a.prob.n_data, S = a.prob.n_snapshots;
+    const int F = (KIND == K_LINEAR_MVN3) ? 3 : a.prob.n_data, S = a.prob.n_snapshots;
     if (!run) return 0.0;
-    const double* X = sdat + S * F;
+    const double* W = sdat + 3;
+    const double* X = sdat + kMvnStats;
     double c[3][3];
     int e = 0;
 #pragma unroll
@@ -381,7 +427,10 @@ __device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&
 #pragma unroll
         for (int s = r; s < 3; ++s) {
             double v = (r == s) ? 1.0 : 0.0;
-            if (r < F && s < F) {
+            if constexpr (KIND == K_LINEAR_MVN3) {
+                v = th[(2 + e < DMAX) ? 2 + e : 0];
+                ++e;
+            } else if (r < F && s < F) {
                 v = a.prob.cov_fixed[e];
                 const int col = a.prob.cov_param_col[e];
 #pragma unroll
@@ -391,43 +440,52 @@ __device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&
             c[r][s] = v;
             c[s][r] = v;
         }
-    const double p00 = c[0][0];
-    const double r00 = sqrt(p00);
-    const double l10 = c[1][0] / r00, l20 = c[2][0] / r00;
-    const double p11 = c[1][1] - l10 * l10;
-    const double r11 = sqrt(p11);
-    const double l21 = (c[2][1] - l20 * l10) / r11;
-    const double p22 = c[2][2] - l20 * l20 - l21 * l21;
-    const double r22 = sqrt(p22);
-    if (!(p00 > 0.0 && p11 > 0.0 && p22 > 0.0)) not_pd = true;
-    const double logdet = 2.0 * (log(r00) + log(r11) + log(r22));
-    const double i00 = 1.0 / r00, i11 = 1.0 / r11, i22 = 1.0 / r22;
-    double out[3];
+    const Chol3 f = chol3(c);
+    if (!f.pd) not_pd = true;
+    const double i00 = f.i00, i11 = f.i11, i22 = f.i22, l10 = f.l10, l20 = f.l20, l21 = f.l21;
+    // log det C = log of the product of the pivots (one log; the sum of three when the product leaves the
+    // normal range)
+    const double pprod = f.p00 * f.p11 * f.p22;
+    const double logdet = (pprod > 1e-280 && pprod < 1e280) ? log(pprod) : (log(f.p00) + log(f.p11) + log(f.p22));
+    // S (model - ybar)^T C^-1 (model - ybar): one forward substitution
+    const double e0 = fma(th[0], X[0], th[1]) - sdat[0];
+    const double e1 = (F > 1) ? fma(th[0], X[1], th[1]) - sdat[1] : 0.0;
+    const double e2 = (F > 2) ? fma(th[0], X[2], th[1]) - sdat[2] : 0.0;
+    const double y0 = e0 * i00;
+    const double y1 = (e1 - l10 * y0) * i11;
+    const double y2 = (e2 - l20 * y0 - l21 * y1) * i22;
+    double quad = (double)S * (y0 * y0 + y1 * y1 + y2 * y2);
+    // tr(C^-1 W) = tr(L^-1 W L^-T): Z = L^-1 W column by column, then the diagonal of L^-1 Z^T
+    double z[3][3];
 #pragma unroll
-    for (int f = 0; f < 3; ++f) out[f] = (f < F) ? fma(th[0], X[f < F ? f : 0], th[1]) : 0.0;
-    double quad = 0.0;
-    for (int s = 0; s < S; ++s) {
-        const double e0 = out[0] - sdat[s * F];
-        const double e1 = (F > 1) ? out[1] - sdat[s * F + 1] : 0.0;
-        const double e2 = (F > 2) ? out[2] - sdat[s * F + 2] : 0.0;
-        const double y0 = e0 * i00;
-        const double y1 = (e1 - l10 * y0) * i11;
-        const double y2 = (e2 - l20 * y0 - l21 * y1) * i22;
-        quad += y0 * y0 + y1 * y1 + y2 * y2;
+    for (int k = 0; k < 3; ++k) {
+        z[0][k] = W[k] * i00;
+        z[1][k] = (W[3 + k] - l10 * z[0][k]) * i11;
+        z[2][k] = (W[6 + k] - l20 * z[0][k] - l21 * z[1][k]) * i22;
     }
+    const double m00 = z[0][0] * i00;
+    const double v10 = z[1][0] * i00;
+    const double m11 = (z[1][1] - l10 * v10) * i11;
+    const double v20 = z[2][0] * i00;
+    const double v21 = (z[2][1] - l10 * v20) * i11;
+    const double m22 = (z[2][2] - l20 * v20 - l21 * v21) * i22;
+    quad += m00 + m11 + m22;
     const double term1 = -(double)F / 2 * log(2 * 3.141592653589793);
     return (double)S * (term1 - 0.5 * logdet) - 0.5 * quad;
 }
 
 // register budget per thread -> minimum resident blocks per SM (keeps ptxas from trading
 // occupancy for unrolling: profiles/r01_mh_kernels.md)
-__host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt, bool tma = false) {
+__host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt, bool tma = false, int kind = -1) {
 #ifdef SMCB_TMA_REGS
     const int tma_regs = SMCB_TMA_REGS;
 #else
     const int tma_regs = 128;
 #endif
-    const int regs = dmax >= 32 ? (tma ? tma_regs : 128) : (dmax >= 16 ? 96 : (ppt >= 4 ? 84 : 64));
+    // MVNormal (3 x 3 factorisation + solves) and two interleaved RK4 chains need ~80 registers to stay
+    // out of local memory; both are FP64-bound, so 6 blocks of 128 threads per SM are plenty
+    const bool wide = (is_mvn(kind) && dmax >= 8) || (kind == K_SPRING_NORMAL && ppt >= 2);
+    const int regs = dmax >= 32 ? (tma ? tma_regs : 128) : (dmax >= 16 ? 96 : (wide ? 80 : (ppt >= 4 ? 84 : 64)));
     return 65536 / (tpb * regs) > 0 ? 65536 / (tpb * regs) : 1;
 }
 
@@ -498,7 +556,7 @@ __device__ __forceinline__ double ll_multisource(const MhArgs& a, const double (
 //       tensor-core product (option "strict_proposal"); same normals, same Philox counters.
 template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
           bool DYN = false, bool MULTI = false, bool STRICT = false>
-__global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT, TMA))
+__global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT, TMA, KIND))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double sh_scale;
@@ -509,7 +567,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
     double* sLt = smem;
     double* sdata = smem + DMAX * DMAX;      // 16-byte aligned data staging area
 
-    const bool resident = (KIND == K_IDENTITY_NORMAL) || (KIND == K_LINEAR_MVN) || (a.prob.n_data <= kChunk);
+    const bool resident = (KIND == K_IDENTITY_NORMAL) || is_mvn(KIND) || (a.prob.n_data <= kChunk);
     if (MODE == 1 || MODE == 2) {
         for (int e = threadIdx.x; e < DMAX * DMAX; e += TPB) {
             const int j = e / DMAX, r = e - j * DMAX;
@@ -816,12 +874,13 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             for (int p = 0; p < PPT; ++p) ll_new[p] = ll_multisource<KIND, DMAX>(a, th[p], run[p], sdata);
         } else if (KIND == K_LINEAR_NORMAL) {
             ll_linear_normal<DMAX, PPT>(a, th, run_any, resident, sdata, ll_new);
+        } else if (KIND == K_SPRING_NORMAL) {
+            ll_spring_normal<DMAX, PPT>(a, th, run_any, resident, sdata, ll_new);
         } else {
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
-                if (KIND == K_SPRING_NORMAL) ll_new[p] = ll_spring_normal<DMAX>(a, th[p], run[p], resident, sdata);
-                else if (KIND == K_IDENTITY_NORMAL) ll_new[p] = ll_identity_normal<DMAX, EXACT>(a, th[p], run[p], sdata);
-                else ll_new[p] = ll_linear_mvn<DMAX>(a, th[p], run[p], sdata, not_pd[p]);
+                if (KIND == K_IDENTITY_NORMAL) ll_new[p] = ll_identity_normal<DMAX, EXACT>(a, th[p], run[p], sdata);
+                else ll_new[p] = ll_linear_mvn<KIND, DMAX>(a, th[p], run[p], sdata, not_pd[p]);
             }
         }
 #pragma unroll
@@ -980,17 +1039,106 @@ __global__ void __launch_bounds__(256) mh_accept_kernel(const AcceptArgs a) {
 }
 
 // initial particles from uniform priors: x = loc + scale * U  (scipy uniform.rvs)
-__global__ void __launch_bounds__(256) sample_priors_kernel(ColPriors cp, int d, double* params, int64_t stride,
+// two standard normals in full fp64 (Box-Muller on 53-bit uniforms): prior draws, not proposals
+__device__ __forceinline__ void normal_pair53(const uint4 r, double& z0, double& z1) {
+    const double u1 = 1.0 - u01_53(r.x, r.y);              // (0, 1]
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u01_53(r.z, r.w), &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+// Initial particles from the priors (vector_mcmc.py:91-96 sample_from_priors on the device): scipy
+// uniform(loc, scale).rvs = loc + scale * U; ImproperCov.rvs = inverse-Wishart(dof, S) draws
+// (smcpy/priors.py:118-123) by the Bartlett decomposition -- A lower triangular with
+// A_ii = sqrt(chi2(dof - i)) (integer dof: a sum of squared normals), A_ij ~ N(0, 1), W = A A^T ~
+// Wishart(dof, I), X = C W^-1 C^T with S = C C^T -- written as packed upper-triangular row-major columns.
+struct IwArgs {
+    int n_cov;
+    int c0[2], ncols[2], dof[2];
+    double chol[2][6];
+};
+__global__ void __launch_bounds__(256) sample_priors_kernel(ColPriors cp, IwArgs iw, int d, double* params, int64_t stride,
                                                             int64_t n, uint64_t seed, uint32_t stream_id,
                                                             int64_t id_offset) {
     const Philox rng(seed);
     const int64_t gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const uint64_t pid = (uint64_t)(id_offset + i);
         for (int c = 0; c < d; c += 2) {
-            const uint4 r = rng((uint64_t)(id_offset + i), (uint32_t)(c >> 1), stream_id);
-            params[(int64_t)c * stride + i] = cp.a[c] + cp.hi[c] * u01_53(r.x, r.y);
-            if (c + 1 < d) params[(int64_t)(c + 1) * stride + i] = cp.a[c + 1] + cp.hi[c + 1] * u01_53(r.z, r.w);
+            const uint4 r = rng(pid, (uint32_t)(c >> 1), stream_id);
+            if (cp.prior_of_col[c] >= 0) params[(int64_t)c * stride + i] = cp.a[c] + cp.hi[c] * u01_53(r.x, r.y);
+            if (c + 1 < d && cp.prior_of_col[c + 1] >= 0)
+                params[(int64_t)(c + 1) * stride + i] = cp.a[c + 1] + cp.hi[c + 1] * u01_53(r.z, r.w);
         }
+        for (int q = 0; q < iw.n_cov; ++q) {
+            const int p = iw.ncols[q];
+            uint32_t call = 64u + 64u * (uint32_t)q;
+            double spare = 0.0;
+            bool have = false;
+            auto next_normal = [&]() {
+                if (have) { have = false; return spare; }
+                double z0;
+                normal_pair53(rng(pid, call++, stream_id), z0, spare);
+                have = true;
+                return z0;
+            };
+            double A[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+            for (int r = 0; r < p; ++r) {
+                for (int c = 0; c < r; ++c) A[r][c] = next_normal();
+                double chi = 0.0;
+                for (int k = 0; k < iw.dof[q] - r; ++k) { const double z = next_normal(); chi = fma(z, z, chi); }
+                A[r][r] = sqrt(chi);
+            }
+            // B = A^-1 (lower), M = C B^T ... X = C (A A^T)^-1 C^T = (C A^-T)(C A^-T)^T; A^-T = B^T upper
+            const double b00 = 1.0 / A[0][0], b11 = 1.0 / A[1][1], b22 = 1.0 / A[2][2];
+            const double b10 = -A[1][0] * b00 * b11;
+            const double b21 = -A[2][1] * b11 * b22;
+            const double b20 = -(A[2][0] * b00 + A[2][1] * b10) * b22;
+            const double B[3][3] = {{b00, 0, 0}, {b10, b11, 0}, {b20, b21, b22}};
+            const double* L = iw.chol[q];
+            const double C[3][3] = {{L[0], 0, 0}, {L[1], L[2], 0}, {L[3], L[4], L[5]}};
+            double M[3][3];                                   // M = C B^T  (M[r][c] = sum_k C[r][k] B[c][k])
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    double v = 0.0;
+                    for (int k = 0; k < 3; ++k) v = fma(C[r][k], B[c][k], v);
+                    M[r][c] = v;
+                }
+            int e = 0;
+            for (int r = 0; r < p; ++r)
+                for (int c = r; c < p; ++c) {
+                    double v = 0.0;
+                    for (int k = 0; k < 3; ++k) v = fma(M[r][k], M[c][k], v);
+                    params[(int64_t)(iw.c0[q] + e) * stride + i] = v;
+                    ++e;
+                }
+        }
+    }
+}
+
+// snapshot mean and scatter matrix of the MVNormal data: one thread per output entry, sequential sums
+// over the snapshots (deterministic; S is small)
+__global__ void mvn_scatter_kernel(const double* __restrict__ data, int S, int F, double* out) {
+    __shared__ double mean[3];
+    const int t = threadIdx.x;
+    if (t < 3) {
+        double m = 0.0;
+        if (t < F) {
+            for (int s = 0; s < S; ++s) m += data[s * F + t];
+            m /= (double)S;
+        }
+        mean[t] = m;
+        out[t] = m;
+    }
+    __syncthreads();
+    if (t < 9) {
+        const int j = t / 3, k = t - 3 * j;
+        double w = 0.0;
+        if (j < F && k < F)
+            for (int s = 0; s < S; ++s) w = fma(data[s * F + j] - mean[j], data[s * F + k] - mean[k], w);
+        out[3 + t] = w;
     }
 }
 
@@ -1030,6 +1178,15 @@ static int build_col_priors(const smcb_problem_t* p, ColPriors* cp) {
             cp->n_cov += 1;
             col += pr.ncols * (pr.ncols + 1) / 2;
             if (col > SMCB_MAX_PARAMS) return -1;
+        } else if (pr.kind == SMCB_PRIOR_EXTERNAL) {
+            // host-evaluated prior: flat (0) on the device over its ncols columns
+            if (pr.ncols < 1 || col + pr.ncols > SMCB_MAX_PARAMS) return -1;
+            for (int k = 0; k < pr.ncols; ++k) {
+                cp->prior_of_col[col + k] = (int8_t)q;
+                cp->a[col + k] = 0.0;
+            }
+            col += pr.ncols;
+            cp->n_external += 1;
         } else {
             return -1;
         }
@@ -1041,7 +1198,7 @@ static int build_col_priors(const smcb_problem_t* p, ColPriors* cp) {
 static size_t mh_smem_bytes(const smcb_problem_t* p) {
     const int d = p->n_params;
     size_t data = 0;
-    if (p->loglike_id == SMCB_LL_MVNORMAL) data = (size_t)(p->n_snapshots * p->n_data + p->n_data) * 8;
+    if (p->loglike_id == SMCB_LL_MVNORMAL) data = (size_t)(kMvnStats + 3 + 1) * 8;
     else if (p->model_id == SMCB_MODEL_LINEAR) data = (size_t)kChunk * 16;
     else if (p->model_id == SMCB_MODEL_SPRING_MASS) data = (size_t)kChunk * 8;
     else data = (size_t)(SMCB_MAX_PARAMS + 2) * 8;
@@ -1097,7 +1254,8 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
 template <int KIND, int DMAX, int MODE, int TPB, int PPT>
 static int launch_cfg(const MhArgs& a, cudaStream_t s) {
     // exact-width instantiations (no per-column bounds checks) where they pay
-    constexpr bool kHasExact = (KIND == K_IDENTITY_NORMAL && DMAX >= 8) || (KIND != K_LINEAR_MVN && DMAX == 2);
+    constexpr bool kHasExact = (KIND == K_IDENTITY_NORMAL && DMAX >= 8) || (!is_mvn(KIND) && DMAX == 2) ||
+                               (KIND == K_LINEAR_MVN3);
     if constexpr (kHasExact) {
         if (a.prob.n_params == DMAX) {
             // TMA-staged variant for the bandwidth-bound wide identity kernels: needs 16-byte
@@ -1121,7 +1279,7 @@ static int launch_cfg(const MhArgs& a, cudaStream_t s) {
 template <int KIND, int DMAX, int MODE>
 static int launch_one(const MhArgs& a, cudaStream_t s) {
     if constexpr (MODE == 0 || MODE == 1) {
-        if constexpr (KIND != K_LINEAR_MVN) {
+        if constexpr (!is_mvn(KIND)) {
             if (a.prob.loglike_id == SMCB_LL_MULTISOURCE) {
                 if (a.prob.has_proposal) {
                     set_error("MultiSourceNormal with a path proposal has no device kernel");
@@ -1152,6 +1310,11 @@ static int launch_one(const MhArgs& a, cudaStream_t s) {
         if (a.n >= (int64_t)kNumSMs * 4 * 1024) return launch_cfg<KIND, DMAX, MODE, 256, 4>(a, s);
         if (a.n >= (int64_t)kNumSMs * 4 * 512) return launch_cfg<KIND, DMAX, MODE, 128, 4>(a, s);
         if (a.n >= (int64_t)kNumSMs * 4 * 256) return launch_cfg<KIND, DMAX, MODE, 128, 2>(a, s);
+    }
+    if constexpr (KIND == K_SPRING_NORMAL && (MODE == 0 || MODE == 1)) {
+        // two interleaved RK4 chains per thread once there are enough tiles to fill the chip
+        const int ppt = options().spring_ppt;                                                      // tuning / test aid
+        if (ppt == 2 || (ppt < 0 && a.n >= (int64_t)kNumSMs * 8 * 256)) return launch_cfg<KIND, DMAX, MODE, 128, 2>(a, s);
     }
     return launch_cfg<KIND, DMAX, MODE, kMhThreads, 1>(a, s);
 }
@@ -1198,6 +1361,12 @@ static int dispatch(const MhArgs& a, cudaStream_t s) {
         if (d <= 16) SMCB_CASE(K_IDENTITY_NORMAL, 16);
         if (d <= 32) SMCB_CASE(K_IDENTITY_NORMAL, 32);
     } else if (p.loglike_id == SMCB_LL_MVNORMAL && p.model_id == SMCB_MODEL_LINEAR) {
+        if constexpr (MODE == 0 || MODE == 1) {
+            bool std3 = d == 8 && p.n_data == 3 && p.n_model_params == 2 && !p.has_proposal && !options().no_mvn3 &&
+                        (a.cp.n_cov == 0 || (a.cp.n_cov == 1 && a.cp.cov_c0[0] == 2 && a.cp.cov_ncols[0] == 3));
+            for (int e = 0; e < 6; ++e) std3 = std3 && p.cov_param_col[e] == 2 + e;
+            if (std3) SMCB_CASE(K_LINEAR_MVN3, 8);
+        }
         if (d <= 4) SMCB_CASE(K_LINEAR_MVN, 4);
         if (d <= 8) SMCB_CASE(K_LINEAR_MVN, 8);
     }
@@ -1216,6 +1385,10 @@ static int validate_problem(const smcb_problem_t* p, ColPriors* cp) {
         return SMCB_ERR_ARG;
     }
     if (!p->data) { set_error("data pointer is NULL"); return SMCB_ERR_ARG; }
+    if (cp->n_external > 0) {
+        set_error("host-evaluated (EXTERNAL) priors go through the un-fused route (smcb_mh_propose / smcb_mh_accept)");
+        return SMCB_ERR_UNSUPPORTED;
+    }
     if (p->has_proposal) {
         for (int c = 0; c < p->n_params; ++c) {
             const smcb_proposal_col_t& q = p->proposal[c];
@@ -1253,7 +1426,8 @@ static int validate_problem(const smcb_problem_t* p, ColPriors* cp) {
         if (cp->n_cov > 0) { set_error("ImproperCov priors are fused for the MVNormal likelihood only"); return SMCB_ERR_UNSUPPORTED; }
     } else if (p->loglike_id == SMCB_LL_MVNORMAL) {
         if (p->model_id != SMCB_MODEL_LINEAR || !p->xgrid || p->n_model_params != 2) { set_error("MVNormal is built in for the linear model only"); return SMCB_ERR_ARG; }
-        if (p->n_data < 1 || p->n_data > 3 || p->n_snapshots < 1 || p->n_snapshots * p->n_data > 4096) { set_error("MVNormal: 1..3 features, S*F <= 4096"); return SMCB_ERR_ARG; }
+        if (p->n_data < 1 || p->n_data > 3 || p->n_snapshots < 1) { set_error("MVNormal: 1..3 features"); return SMCB_ERR_ARG; }
+        if (!p->mvn_stats) { set_error("MVNormal: mvn_stats is NULL (fill it with smcb_mvn_scatter)"); return SMCB_ERR_ARG; }
     } else {
         set_error("unknown loglike_id");
         return SMCB_ERR_ARG;
@@ -1264,6 +1438,16 @@ static int validate_problem(const smcb_problem_t* p, ColPriors* cp) {
 }  // namespace smcb
 
 using namespace smcb;
+
+extern "C" int smcb_mvn_scatter(const double* data, int32_t n_snapshots, int32_t n_features, double* stats_out,
+                                void* stream) {
+    if (!data || !stats_out || n_snapshots < 1 || n_features < 1 || n_features > 3) {
+        set_error("smcb_mvn_scatter: bad argument (1..3 features)");
+        return SMCB_ERR_ARG;
+    }
+    mvn_scatter_kernel<<<1, 32, 0, as_stream(stream)>>>(data, n_snapshots, n_features, stats_out);
+    return check_launch("mvn_scatter_kernel");
+}
 
 extern "C" int smcb_mh_init(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
                             double* ll_out, double* lp_out, double* lp_cols_out, double* lq_out, int32_t* flags,
@@ -1444,13 +1628,35 @@ extern "C" int smcb_sample_priors(const smcb_problem_t* prob, double* params, in
         set_error("Num prior distributions != num input params");
         return SMCB_ERR_ARG;
     }
+    IwArgs iw;
+    memset(&iw, 0, sizeof(iw));
     for (int q = 0; q < prob->n_priors; ++q) {
-        if (prob->priors[q].kind != SMCB_PRIOR_UNIFORM) {
-            set_error("device prior sampling supports scipy-uniform priors only (prior %d)", q);
-            return SMCB_ERR_UNSUPPORTED;
+        const smcb_prior_t& pr = prob->priors[q];
+        if (pr.kind == SMCB_PRIOR_UNIFORM) continue;
+        if (pr.kind == SMCB_PRIOR_IMPROPER_COV) {
+            const int k = iw.n_cov;
+            const double dof = pr.a;
+            if (!(dof >= pr.ncols && dof <= 256 && dof == (double)(int)dof)) {
+                set_error("device inverse-Wishart sampling needs an integer dof in [ncols, 256] (prior %d)", q);
+                return SMCB_ERR_UNSUPPORTED;
+            }
+            iw.c0[k] = cp.cov_c0[k];
+            iw.ncols[k] = pr.ncols;
+            iw.dof[k] = (int)dof;
+            for (int e = 0; e < 6; ++e) iw.chol[k][e] = prob->iw_chol[k][e];
+            if (pr.ncols < 3) iw.chol[k][5] = 1.0;                      // padding rows / columns: identity
+            if (pr.ncols < 2) iw.chol[k][2] = 1.0;
+            if (!(iw.chol[k][0] > 0.0)) {
+                set_error("device inverse-Wishart sampling: iw_chol of prior %d is not set", q);
+                return SMCB_ERR_ARG;
+            }
+            iw.n_cov = k + 1;
+            continue;
         }
+        set_error("device prior sampling supports scipy-uniform and ImproperCov priors only (prior %d)", q);
+        return SMCB_ERR_UNSUPPORTED;
     }
-    sample_priors_kernel<<<grid_for(n, 256, 1, 8), 256, 0, as_stream(stream)>>>(cp, cols, params, stride, n, seed,
+    sample_priors_kernel<<<grid_for(n, 256, 1, 8), 256, 0, as_stream(stream)>>>(cp, iw, cols, params, stride, n, seed,
                                                                                   (uint32_t)stream_id, id_offset);
     return check_launch("sample_priors_kernel");
 }

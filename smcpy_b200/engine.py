@@ -271,39 +271,67 @@ def make_path(phi, phi_prev, lam):
 # ---------------------------------------------------------------------------------------------
 class ProblemSpec:
     """Model + data + priors + likelihood bound to device buffers (the VectorMCMC constructor
-    arguments, smcpy/mcmc/vector_mcmc.py:11-34, as an smcb_problem_t)."""
+    arguments, smcpy/mcmc/vector_mcmc.py:11-34, as an smcb_problem_t).
 
-    def __init__(self, model, data, priors, log_like_args, kind):
-        from .models import DeviceModel
+    fused = True: built-in device model, device priors, Normal / MultiSourceNormal / (linear, <= 3
+    features) MVNormal -- the whole Metropolis step is one kernel.  Otherwise the un-fused route
+    (callable_route.py): proposal kernel -> [host-evaluated priors] -> model / log-likelihood as torch
+    callables on device tensors (or a registered CUDA model) -> accept kernel."""
+
+    def __init__(self, model, data, priors, log_like_args, kind, loglike=None):
+        from .models import DeviceModel, LinearModel, NvrtcModel
         from .priors import describe_prior
         rt = Runtime.get()
         self.model = model
         self.kind = kind
         self.priors = list(priors)
-        self.fused = isinstance(model, DeviceModel)
+        self.loglike = loglike
         c = _lib.Problem()
         descs = [describe_prior(p) for p in self.priors]
         if len(descs) > _lib.MAX_PRIORS:
             raise NotImplementedError("at most %d priors" % _lib.MAX_PRIORS)
         d = 0
+        n_cov = 0
+        self.external = []                      # (prior object, first column, columns): host-evaluated log-pdf
         for i, (k, ncols, a, b, lpin) in enumerate(descs):
             c.priors[i] = _lib.Prior(k, ncols, a, b, lpin)
-            d += ncols * (ncols + 1) // 2 if k == _lib.PRIOR_IMPROPER_COV else 1
+            if k == _lib.PRIOR_IMPROPER_COV:
+                if n_cov < 2:
+                    # lower Cholesky factor of the inverse-Wishart scale of ImproperCov.rvs (priors.py:118-123)
+                    L = np.eye(3)
+                    L[:ncols, :ncols] = np.linalg.cholesky(np.asarray(self.priors[i]._iw_scale, dtype=np.float64))
+                    for e, (r, q) in enumerate(((0, 0), (1, 0), (1, 1), (2, 0), (2, 1), (2, 2))):
+                        c.iw_chol[n_cov][e] = float(L[r, q])
+                n_cov += 1
+                d += ncols * (ncols + 1) // 2
+            elif k == _lib.PRIOR_EXTERNAL:
+                self.external.append((self.priors[i], d, ncols))
+                d += ncols
+            else:
+                d += 1
+        if d > _lib.MAX_PARAMS:
+            raise NotImplementedError("at most %d parameters" % _lib.MAX_PARAMS)
         c.n_priors = len(descs)
         c.n_params = d
         self.d = d
         self.n_priors = len(descs)
-        # summed log-prior of any particle inside the support (all device priors are flat)
-        # (one add chain in prior order, as build_col_priors does on the library side)
-        self.lp_const = 0.0
-        for (k, _, _, _, lpin) in descs:
-            if k != _lib.PRIOR_IMPROPER_COV:
-                self.lp_const += float(lpin)
+        self.n_cov = n_cov
+        # summed log-prior of any particle inside the support when every prior is flat there (one add
+        # chain in prior order, as build_col_priors does on the library side); None with host-evaluated priors
+        self.lp_const = None
+        if not self.external:
+            self.lp_const = 0.0
+            for (k, _, _, _, lpin) in descs:
+                if k != _lib.PRIOR_IMPROPER_COV:
+                    self.lp_const += float(lpin)
         data = np.asarray(data, dtype=np.float64)
         self._data_dev = dev(data.reshape(-1))
         c.data = self._data_dev.data_ptr()
         self._x_dev = None
+        dev_model = isinstance(model, DeviceModel)
+        fusable = dev_model and not self.external
         if kind == "normal":
+            fusable = fusable and n_cov == 0
             c.loglike_id = _lib.LL_NORMAL
             c.n_data = int(data.reshape(-1).shape[0])
             c.n_snapshots = 1
@@ -311,6 +339,8 @@ class ProblemSpec:
             c.sigma = 0.0 if log_like_args is None else float(np.asarray(log_like_args).reshape(-1)[0])
             c.n_model_params = d - c.sigma_is_param
         elif kind == "multisource":
+            if not (fusable and n_cov == 0):
+                raise NotImplementedError("MultiSourceNormal needs a built-in device model and device priors")
             lens, stds = list(log_like_args[0]), list(log_like_args[1])
             if len(lens) != len(stds) or len(lens) > _lib.MAX_SEGMENTS:
                 raise NotImplementedError("MultiSourceNormal on the device supports up to %d segments" % _lib.MAX_SEGMENTS)
@@ -334,25 +364,39 @@ class ProblemSpec:
         elif kind == "mvnormal":
             if data.ndim != 2:
                 raise ValueError("MVNormal data must be (snapshots, features)")
-            c.loglike_id = _lib.LL_MVNORMAL
-            c.n_snapshots, c.n_data = int(data.shape[0]), int(data.shape[1])
+            S, F = int(data.shape[0]), int(data.shape[1])
             args = list(log_like_args)
-            if len(args) != c.n_data * (c.n_data + 1) // 2:
+            if len(args) != F * (F + 1) // 2:
                 raise ValueError("MVNormal args must hold F(F+1)/2 covariance terms")
-            if len(args) > _lib.MAX_COV_ARGS:
-                raise NotImplementedError("MVNormal on the device supports up to 3 features")
             n_none = args.count(None)
-            j = 0
-            for i, a in enumerate(args):
-                if a is None:
-                    c.cov_param_col[i] = d - n_none + j
-                    j += 1
-                else:
-                    c.cov_param_col[i] = -1
-                    c.cov_fixed[i] = float(a)
             c.n_model_params = d - n_none
+            fusable = fusable and isinstance(model, LinearModel) and F <= 3
+            self.mvn_args, self.mvn_shape = args, (S, F)
+            self._data2_dev = self._data_dev.reshape(S, F)
+            if fusable:
+                c.loglike_id = _lib.LL_MVNORMAL
+                c.n_snapshots, c.n_data = S, F
+                j = 0
+                for i, a in enumerate(args):
+                    if a is None:
+                        c.cov_param_col[i] = d - n_none + j
+                        j += 1
+                    else:
+                        c.cov_param_col[i] = -1
+                        c.cov_fixed[i] = float(a)
+                # snapshot mean + scatter matrix: all the kernels need of the S x F data
+                self._mvn_stats = torch.zeros(_lib.MVN_STATS, dtype=torch.float64, device=rt.device)
+                call("smcb_mvn_scatter", ptr(self._data_dev), S, F, ptr(self._mvn_stats), stream_ptr())
+                c.mvn_stats = self._mvn_stats.data_ptr()
+        elif kind == "torch":
+            if loglike is None or not callable(getattr(loglike, "torch_loglike", None)):
+                raise TypeError("a user log-likelihood needs a torch_loglike(params) method")
+            fusable = False
+            c.n_model_params = d
         else:
             raise NotImplementedError(kind)
+        self.fused = bool(fusable)
+        self.model_fn = None                    # un-fused route: (N, d_model) device tensor -> (N, M) device tensor
         if self.fused:
             c.model_id = model.model_id
             if model.n_model_params != c.n_model_params:
@@ -372,17 +416,28 @@ class ProblemSpec:
                 if model.n_out != c.n_data:
                     raise ValueError("identity model size and data length differ")
         else:
-            from .models import NvrtcModel
-            if not (callable(model) or isinstance(model, NvrtcModel)):
+            if kind != "torch" and not (callable(model) or isinstance(model, (NvrtcModel, DeviceModel))):
                 raise TypeError("model must be a smcpy_b200.models.DeviceModel, NvrtcModel or a torch callable")
             if isinstance(model, NvrtcModel):
-                if model.n_model_params != d - (1 if log_like_args is None else 0):
+                if kind != "normal":
+                    raise NotImplementedError("registered CUDA models support the Normal likelihood only")
+                if model.n_model_params != c.n_model_params:
                     raise ValueError("model takes %d parameters but the priors/likelihood leave %d"
-                                     % (model.n_model_params, d - (1 if log_like_args is None else 0)))
-                if kind == "normal" and model.n_out != int(data.reshape(-1).shape[0]):
+                                     % (model.n_model_params, c.n_model_params))
+                if model.n_out != int(data.reshape(-1).shape[0]):
                     raise ValueError("model output count and data length differ")
+            elif dev_model:
+                if model.n_model_params != c.n_model_params:
+                    raise ValueError("model takes %d parameters but the priors/likelihood leave %d"
+                                     % (model.n_model_params, c.n_model_params))
+                self.model_fn = model.torch_eval
+            else:
+                self.model_fn = model
             if kind != "normal":
-                raise NotImplementedError("torch-callable models support the Normal likelihood only")
+                # the kernels of the un-fused route only see the prior table; the likelihood is a torch callable
+                c.loglike_id = _lib.LL_NORMAL
+                c.n_data = 1
+                c.n_snapshots = 1
             c.model_id = _lib.MODEL_IDENTITY      # unused by the un-fused kernels
         self.c = c
         self.device = rt.device
@@ -648,8 +703,9 @@ def find_phi(st, spec, phi_old, target_ess, lam=1.0):
     inside it.  st.search_info = (passes over the particles, evaluations scipy would have made)."""
     _, world = dist_info()
     s = stream_ptr()
-    lp = None if (st.lq is None and spec is not None) else st.lp
-    lp_const = spec.lp_const if spec is not None else 0.0
+    flat = spec is not None and spec.lp_const is not None and st.lq is None
+    lp = None if flat else st.lp
+    lp_const = spec.lp_const if flat else 0.0
     px = PeerExchange.get() if world > 1 else None
     if world == 1 or (px is not None and not os.environ.get("SMCB_NO_BISECT_XCHG")):
         with _timed("bisect"):
@@ -681,8 +737,9 @@ def ess_margin(st, spec, phi_new, phi_old, target_ess, lam=1.0):
     """AdaptiveSampler.predict_ess_margin (samplers.py:264-276) for one candidate phi."""
     _, world = dist_info()
     s = stream_ptr()
-    lp = None if (st.lq is None and spec is not None) else st.lp
-    lp_const = spec.lp_const if spec is not None else 0.0
+    flat = spec is not None and spec.lp_const is not None and st.lq is None
+    lp = None if flat else st.lp
+    lp_const = spec.lp_const if flat else 0.0
     st.bis.zero_()
     st.bis[6] = float(phi_new)
     part = st.scalars[8:11]

@@ -43,8 +43,17 @@ class Initializer:
             st.set_params_host(arr[lo:hi])
         else:
             rng = kernel.rng
-            call("smcb_sample_priors", C.byref(spec.c), ptr(st.cols), st.n, st.n, rng.seed, rng.next_stream(),
-                 st.id_offset, stream_ptr())
+            stream_id = rng.next_stream()
+            try:
+                call("smcb_sample_priors", C.byref(spec.c), ptr(st.cols), st.n, st.n, rng.seed, stream_id,
+                     st.id_offset, stream_ptr())
+            except NotImplementedError:
+                # priors the device cannot draw (host-evaluated ones, non-integer inverse-Wishart dof): their own
+                # rvs on the host, from a numpy Generator keyed by the Philox seed -- the same on every rank
+                gen = np.random.default_rng([rng.seed & 0xFFFFFFFF, rng.seed >> 32, stream_id])
+                cols = [np.asarray(p.rvs(num_particles, random_state=gen), dtype=np.float64).reshape(num_particles, -1)
+                        for p in spec.priors]
+                st.set_params_host(np.hstack(cols)[lo:hi])
         if not kernel.has_proposal():
             st.lp_const = spec.lp_const      # drawn from the (flat) priors: every particle is inside the support
         engine.eval_incoming(st, spec)

@@ -65,4 +65,7 @@ def loglike_kind(obj_or_cls):
         return "mvnormal"
     if name == "MultiSourceNormal":
         return "multisource"
-    raise NotImplementedError("log-likelihood %s has no device kernel (Normal, MVNormal)" % name)
+    if callable(getattr(obj_or_cls, "torch_loglike", None)):
+        return "torch"                  # user likelihood evaluated as a torch callable on device tensors
+    raise NotImplementedError("log-likelihood %s has neither a device kernel (Normal, MultiSourceNormal, MVNormal) "
+                              "nor a torch_loglike(params) method" % name)

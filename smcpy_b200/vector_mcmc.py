@@ -28,14 +28,29 @@ def _spec_for_priors(priors):
     for i, p in enumerate(priors):
         k, ncols, a, b, lpin = describe_prior(p)
         c.priors[i] = _lib.Prior(k, ncols, a, b, lpin)
-        d += ncols * (ncols + 1) // 2 if k == _lib.PRIOR_IMPROPER_COV else 1
+        d += ncols * (ncols + 1) // 2 if k == _lib.PRIOR_IMPROPER_COV else (ncols if k == _lib.PRIOR_EXTERNAL else 1)
     c.n_priors = len(priors)
     c.n_params = d
     return c, d
 
 
+def host_prior_columns(priors, x):
+    """{prior index: (N,) log-pdf} of the host-evaluated (SMCB_PRIOR_EXTERNAL) priors on host rows x (N, d):
+    each object sees its own `dim` columns as a 2-D block, as vector_mcmc.py:105-109 hands them over."""
+    from .priors import describe_prior, prior_dim
+    out, c0 = {}, 0
+    for i, p in enumerate(priors):
+        k, ncols, _, _, _ = describe_prior(p)
+        dim = ncols * (ncols + 1) // 2 if k == _lib.PRIOR_IMPROPER_COV else (ncols if k == _lib.PRIOR_EXTERNAL else 1)
+        if k == _lib.PRIOR_EXTERNAL:
+            out[i] = np.asarray(p.logpdf(x[:, c0:c0 + dim]), dtype=np.float64).reshape(-1)
+        c0 += dim
+    return out
+
+
 def device_log_priors(priors, x, problem_c=None):
-    """(N, n_priors) un-summed log-priors of host rows x (N, d)  (vector_mcmc.py:98-111)."""
+    """(N, n_priors) un-summed log-priors of host rows x (N, d)  (vector_mcmc.py:98-111): device prior table,
+    plus the host-evaluated columns."""
     x = np.asarray(x, dtype=np.float64)
     if problem_c is None:
         problem_c, d = _spec_for_priors(priors)
@@ -51,7 +66,10 @@ def device_log_priors(priors, x, problem_c=None):
     lp = torch.empty(n, dtype=torch.float64, device=rt.device)
     cols = torch.empty((int(problem_c.n_priors), n), dtype=torch.float64, device=rt.device)
     call("smcb_log_priors", C.byref(problem_c), ptr(soa), n, n, ptr(lp), ptr(cols), stream_ptr())
-    return cols.t().contiguous().cpu().numpy()
+    out = cols.t().contiguous().cpu().numpy()
+    for i, v in host_prior_columns(priors, x).items():
+        out[:, i] = v
+    return out
 
 
 def device_log_likelihood(loglike, inputs):
@@ -67,12 +85,15 @@ def device_log_likelihood(loglike, inputs):
 class B200VectorMCMC:
     def __init__(self, model, data, priors, log_like_args=None, log_like_func=Normal):
         """
-        :param model: a smcpy_b200.models.DeviceModel (fused kernels) or a torch callable
-            mapping a device tensor (N, d_model) to (N, M) (un-fused route)
+        :param model: a smcpy_b200.models.DeviceModel (fused kernels), a models.NvrtcModel, or a torch
+            callable mapping a device tensor (N, d_model) to (N, M) (un-fused route); for
+            ApproxHierarch the conditional-probability model class (hierarch_log_likelihoods.py)
         :param data: 1-D data array (Normal) or (snapshots, features) array (MVNormal)
-        :param priors: scipy.stats.uniform frozen objects, ImproperUniform, ImproperCov
+        :param priors: scipy.stats.uniform frozen objects, ImproperUniform, ImproperCov (device
+            log-pdf); InvWishart, ImproperConstrainedUniform or any object with logpdf (host-evaluated)
         :param log_like_args: likelihood hyper-parameters as in the reference
-        :param log_like_func: Normal or MVNormal (these or the reference's classes)
+        :param log_like_func: Normal, MultiSourceNormal, MVNormal (these or the reference's classes),
+            ApproxHierarch, or a class with a torch_loglike(params) method
         """
         self._eval_model = model
         self._data = data
@@ -100,7 +121,7 @@ class B200VectorMCMC:
     def spec(self):
         if self._spec is None:
             self._spec = engine.ProblemSpec(self._eval_model, self._data, self._priors, self._log_like_args,
-                                            self._kind)
+                                            self._kind, loglike=self._log_like_func)
             self._spec.set_proposal(self._proposal)
         return self._spec
 

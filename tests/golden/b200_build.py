@@ -28,6 +28,10 @@ def make_b200(problem, rng=None, path=None):
             priors.append(sb.ImproperUniform(p[1], p[2]))
         elif p[0] == "improper_cov":
             priors.append(sb.ImproperCov(int(p[1]), dof=5, S=np.eye(int(p[1]))))
+        elif p[0] == "invwishart":
+            priors.append(sb.InvWishart(p[2], np.asarray(p[3], dtype=float)))
+        elif p[0] == "constrained":
+            priors.append(sb.ImproperConstrainedUniform(p[2], bounds=np.asarray(p[3], dtype=float)))
     lk, largs = problem["loglike"]
     cls = {"normal": sb.Normal, "mvnormal": sb.MVNormal, "multisource": sb.MultiSourceNormal}[lk]
     mcmc = sb.B200VectorMCMC(model, problem["data"], priors, largs, cls)

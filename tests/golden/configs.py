@@ -96,6 +96,50 @@ def multisource_problem(data_seed=12):
     }
 
 
+def invwishart_problem(n_snap=50):
+    """C4 with a proper InvWishart(dof=5, scale=I) prior on the covariance terms (smcpy/priors.py:38-90)
+    instead of ImproperCov."""
+    p = mvn_problem(n_snap)
+    p["priors"] = [("uniform", 0.0, 6.0), ("uniform", 0.0, 6.0), ("invwishart", 3, 5, np.eye(3))]
+    return p
+
+
+def sum_below(x):
+    """Constraint of the constrained-prior case: a + b < 5.6 (binds: the posterior sits at a + b ~ 5.52)."""
+    return x[:, 0] + x[:, 1] < 5.6
+
+
+def constrained_problem():
+    """C1 under one 2-column ImproperConstrainedUniform prior (smcpy/priors.py:150-247,
+    examples/priors/run_example_constrained_prior.py)."""
+    p = linear_problem(100)
+    p["priors"] = [("constrained", 2, sum_below, np.array([[-6.0, -6.0], [6.0, 6.0]]))]
+    return p
+
+
+def impcov_normal_problem():
+    """Linear model, Normal likelihood with the std-dev sampled, its prior a 1 x 1 ImproperCov (positive)."""
+    p = linear_problem(60, data_seed=8, unknown_sigma=True)
+    p["priors"] = [("uniform", -6.0, 12.0), ("uniform", -6.0, 12.0), ("improper_cov", 1)]
+    return p
+
+
+def constrained_init_params(n, seed):
+    """ImproperConstrainedUniform.rvs (smcpy/priors.py:199-212): uniform candidates inside the bounds, pruned by
+    the constraint, repeated until n are found."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        cand = rng.uniform([-6.0, -6.0], [6.0, 6.0], (n, 2))
+        out += list(cand[sum_below(cand)])
+    return np.array(out)[:n]
+
+
+def impcov_normal_init_params(n, seed):
+    rng = np.random.default_rng(seed)
+    return np.column_stack([rng.uniform(-6, 6, n), rng.uniform(-6, 6, n), rng.uniform(0.05, 5.0, n)])
+
+
 # name -> (problem builder, sampler kind, sampler kwargs, rng seed)
 CASES = {
     "c1_adaptive": (lambda: linear_problem(100), "adaptive",
@@ -121,7 +165,26 @@ CASES = {
                     dict(n=400, K=5, target_ess=0.8, resampler="standard"), 8),
     "c1_proposal_reqphi": (lambda: proposal_problem([0.2, 0.6]), "adaptive",
                            dict(n=400, K=4, target_ess=0.75, resampler="stratified"), 9),
+    # priors without a device log-pdf (host-evaluated column of the un-fused route)
+    "c4_invwishart": (lambda: invwishart_problem(50), "adaptive",
+                      dict(n=200, K=3, target_ess=0.8, resampler="standard", iw_seed=13), 11),
+    "c1_constrained": (lambda: constrained_problem(), "adaptive",
+                       dict(n=300, K=4, target_ess=0.8, resampler="standard", init="constrained", init_seed=14), 12),
+    "c2_impcov_normal": (lambda: impcov_normal_problem(), "fixed",
+                         dict(n=300, K=4, phi=np.linspace(0, 1, 12) ** 2, ess_threshold=0.7, resampler="standard",
+                              init="impcov_normal", init_seed=15), 13),
 }
+
+
+def init_params_for(kw):
+    """Host-side initial particles of the cases whose priors the oracle / device do not sample."""
+    if "iw_seed" in kw:
+        return mvn_init_params(kw["n"], kw["iw_seed"])
+    if kw.get("init") == "constrained":
+        return constrained_init_params(kw["n"], kw["init_seed"])
+    if kw.get("init") == "impcov_normal":
+        return impcov_normal_init_params(kw["n"], kw["init_seed"])
+    return None
 
 
 def mvn_init_params(n, seed):

@@ -26,6 +26,7 @@ sys.path.insert(0, os.environ.get("SMCPY_REFERENCE", "/root/reference"))
 import smcpy                                                  # noqa: E402
 from smcpy import (AdaptiveSampler, FixedPhiSampler, VectorMCMC, VectorMCMCKernel,  # noqa: E402
                    ImproperUniform, ImproperCov, MVNormal)
+from smcpy.priors import InvWishart, ImproperConstrainedUniform  # noqa: E402
 from smcpy.log_likelihoods import MultiSourceNormal, Normal   # noqa: E402
 from smcpy.paths import GeometricPath                         # noqa: E402
 from smcpy.proposals import MultivarIndependent               # noqa: E402
@@ -58,6 +59,10 @@ def ref_objects(problem):
             priors.append(ImproperUniform(p[1], p[2]))
         elif p[0] == "improper_cov":
             priors.append(ImproperCov(int(p[1]), dof=5, S=np.eye(int(p[1]))))
+        elif p[0] == "invwishart":
+            priors.append(InvWishart(p[2], np.asarray(p[3], float)))
+        elif p[0] == "constrained":
+            priors.append(ImproperConstrainedUniform(p[2], bounds=np.asarray(p[3], float)))
     lk, largs = problem["loglike"]
     ll_cls = {"normal": Normal, "mvnormal": MVNormal, "multisource": MultiSourceNormal}[lk]
     if lk == "multisource":
@@ -133,9 +138,8 @@ def run_case(name):
         dists = [stats.norm(loc, sc) if k == "normal" else stats.uniform(loc, sc) for k, loc, sc in problem["proposal"]]
         path = GeometricPath(proposal=MultivarIndependent(*dists), required_phi=problem.get("required_phi", 1))
     kernel = VectorMCMCKernel(mcmc, param_order=problem["names"], rng=rng, path=path)
-    init = None
-    if "iw_seed" in kw:
-        init = configs.mvn_init_params(kw["n"], kw["iw_seed"])
+    init = configs.init_params_for(kw)
+    if init is not None:
         kernel.sample_from_prior = lambda n: dict(zip(kernel.param_order, init.T))
     res = {"standard": standard, "stratified": stratified}[kw["resampler"]]
     rec = Recorder()
@@ -328,12 +332,32 @@ def metropolis_fixture():
     print("metropolis_chain", chain.shape)
 
 
+def hierarch_fixture():
+    """ApproxHierarch + MVNHierarchModel (hierarch_log_likelihoods.py) on seeded inputs."""
+    from smcpy.hierarch_log_likelihoods import ApproxHierarch, MVNHierarchModel
+    rng = np.random.default_rng(77)
+    R, ns, p, N = 3, 40, 2, 25
+    data = rng.normal(0, 1, (R, ns, p)) + rng.normal(0, 2, (R, 1, p))
+    mlls = rng.normal(-20, 3, R)
+    lpr = rng.normal(-3, 0.5, (R, ns))
+    A = rng.normal(0, 1, (N, p, p))
+    covs = A @ np.transpose(A, (0, 2, 1)) + 0.5 * np.eye(p)
+    i1, i2 = np.triu_indices(p)
+    theta = np.column_stack([rng.normal(0, 2, (N, p)), covs[:, i1, i2]])
+    ll = ApproxHierarch(MVNHierarchModel, data, [mlls, lpr])(theta)
+    np.savez_compressed(os.path.join(HERE, "hierarch.npz"), data=data, mlls=mlls, lpr=lpr, theta=theta, ll=ll)
+    print("hierarch", ll.shape)
+
+
 if __name__ == "__main__":
     print("reference smcpy", smcpy.__version__, "numpy", np.__version__)
     only = sys.argv[1:]
     if not only:
         unit_vectors()
         metropolis_fixture()
+        hierarch_fixture()
+    elif "hierarch" in only:
+        hierarch_fixture()
     for name in configs.CASES:
         if not only or name in only:
             run_case(name)

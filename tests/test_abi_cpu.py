@@ -30,15 +30,36 @@ def test_library_exports_every_declared_symbol():
     assert L.lib.smcb_workspace_bytes(1 << 20, 2) > (1 << 20)
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every struct of include/smcb200.h as gcc lays them out == the ctypes mirrors."""
+    import subprocess
     import smcpy_b200._lib as L
-    assert ctypes.sizeof(L.Prior) == 32
-    assert ctypes.sizeof(L.Path) == 24
-    assert ctypes.sizeof(L.Rng) == 48
-    assert ctypes.sizeof(L.Xchg) == 8 + 8 + 8 * 8 + 8 + 8
-    # 8 ints + sigma + 8 args + 2 ptrs + 6 doubles + 6 ints + priors
-    assert ctypes.sizeof(L.ProposalCol) == 24
-    assert ctypes.sizeof(L.Problem) == 32 + 8 + 64 + 16 + 48 + 24 + 32 * 32 + 8 + 32 * 24 + 4 + 32 + 32 + 4 + 64
+    structs = {"smcb_prior_t": (L.Prior, ["kind", "ncols", "a", "b", "logp_in"]),
+               "smcb_proposal_col_t": (L.ProposalCol, ["kind", "a", "b"]),
+               "smcb_path_t": (L.Path, ["phi", "phi_prev"]),
+               "smcb_rng_t": (L.Rng, ["mode", "seed", "stream", "id_offset", "z", "u"]),
+               "smcb_xchg_t": (L.Xchg, ["world", "rank", "gen", "peer_slots", "global_counts", "ticket"]),
+               "smcb_resample_t": (L.Resample, ["kind", "n_local", "seed", "cdf", "totals", "t_peer", "src", "src_stride",
+                                                "dst_peer", "dst_stride", "idx_out", "n_unique_out"]),
+               "smcb_problem_t": (L.Problem, ["model_id", "n_priors", "sigma", "model_args", "data", "xgrid", "cov_fixed",
+                                              "cov_param_col", "priors", "has_proposal", "proposal", "n_segments",
+                                              "seg_len", "seg_sigma_col", "seg_sigma", "mvn_stats", "iw_chol"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "smcb200.h"', "int main(void) {"]
+    for cname, (_, fields) in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f in fields:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+    lines.append("return 0; }")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, (cls, fields) in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for f in fields:
+            assert int(got["%s.%s" % (cname, f)]) == getattr(cls, f).offset, (cname, f)
+    assert L.MVN_STATS == 12 and L.MAX_RANKS == 8
 
 
 def test_argument_errors_are_reported_without_a_gpu():
@@ -119,5 +140,6 @@ def test_prior_descriptions():
     assert describe_prior(stats.uniform(loc=1.0, scale=2.0))[2:4] == (1.0, 2.0)
     assert describe_prior(sb.ImproperUniform(None, 3))[2:4] == (-np.inf, 3.0)
     assert describe_prior(sb.ImproperCov(3))[:2] == (3, 3)
+    assert describe_prior(stats.norm(0, 1))[:2] == (4, 1)        # any object with logpdf: host-evaluated column
     with pytest.raises(TypeError):
-        describe_prior(stats.norm(0, 1))
+        describe_prior(3.0)

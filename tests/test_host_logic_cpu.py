@@ -151,3 +151,58 @@ def test_native_generator_streams():
     a, b = r.next_stream(), r.next_stream()
     assert b == a + 1 and r.seed == 42
     assert sb.PhiloxRNG(42).next_stream() == a
+
+
+# ---- host-evaluated priors (smcpy/priors.py:38-90,150-247): pure host objects, no GPU needed -------------
+def test_invwishart_prior_host_logpdf_and_rvs():
+    from oracle import smc_oracle as orc
+    scale = np.array([[2.0, 0.3], [0.3, 1.0]])
+    p = sb.InvWishart(4, scale)
+    assert p.dim == 3
+    x = p.rvs(7, random_state=np.random.default_rng(3))
+    assert x.shape == (7, 3)
+    assert p.rvs(1, random_state=np.random.default_rng(3)).shape == (1, 3)
+    lp = p.logpdf(x)
+    assert lp.shape == (7, 1)
+    np.testing.assert_allclose(lp[:, 0], orc.logpdf_invwishart(x, 2, 4, scale), rtol=1e-13)
+    covs = np.array([[[a, b], [b, c]] for a, b, c in x])
+    np.testing.assert_allclose(lp[:, 0], stats.invwishart(4, scale).logpdf(np.transpose(covs, (1, 2, 0))), rtol=1e-13)
+    np.testing.assert_allclose(p.pdf(x), np.exp(lp), rtol=1e-12)
+    # one matrix of the batch not positive definite: the reference's quirk gives the whole batch -inf / 0
+    bad = x.copy()
+    bad[2] = [1.0, 5.0, 1.0]
+    assert np.isneginf(p.logpdf(bad)).all() and (p.pdf(bad) == 0).all()
+
+
+def test_improper_constrained_uniform_prior():
+    bounds = np.array([[-1.0, 0.0], [1.0, 2.0]])
+    cons = lambda x: x[:, 0] < x[:, 1]
+    p = sb.ImproperConstrainedUniform(cons, bounds=bounds)
+    assert p.dim == 2
+    x = np.array([[0.0, 1.0], [0.5, 0.2], [-1.0, 0.0], [0.0, 2.5], [1.0, 2.0], [-1.5, 1.0]])
+    np.testing.assert_array_equal(p.logpdf(x)[:, 0], [0.0, -np.inf, 0.0, -np.inf, 0.0, -np.inf])
+    s = p.rvs(200, random_state=np.random.default_rng(1))
+    assert s.shape == (200, 2) and cons(s).all() and (s >= bounds[0]).all() and (s <= bounds[1]).all()
+    assert sb.ImproperConstrainedUniform(cons, dim=2).dim == 2
+    np.testing.assert_array_equal(sb.ImproperConstrainedUniform(cons, dim=2).logpdf(x)[:, 0],
+                                  [0.0, -np.inf, 0.0, 0.0, 0.0, 0.0])
+    with pytest.raises(ValueError):
+        sb.ImproperConstrainedUniform(cons)
+    with pytest.raises(NotImplementedError):
+        sb.ImproperConstrainedUniform(cons, dim=2).rvs(3)
+    with pytest.raises(TypeError):
+        p.rvs(3, random_state=np.random.RandomState(1))
+    with pytest.raises(ValueError, match="Max rvs tries"):
+        sb.ImproperConstrainedUniform(lambda x: x[:, 0] > 5, bounds=bounds, max_rvs_tries=3).rvs(2, np.random.default_rng(0))
+
+
+def test_prior_table_descriptors():
+    from smcpy_b200 import _lib
+    from smcpy_b200.priors import describe_prior
+    assert describe_prior(stats.uniform(-6, 12))[:4] == (_lib.PRIOR_UNIFORM, 1, -6.0, 12.0)
+    assert describe_prior(sb.ImproperUniform(0, 3))[:4] == (_lib.PRIOR_IMPROPER_UNIFORM, 1, 0.0, 3.0)
+    assert describe_prior(sb.ImproperCov(3, dof=5))[:3] == (_lib.PRIOR_IMPROPER_COV, 3, 5.0)
+    assert describe_prior(sb.InvWishart(5, np.eye(3)))[:2] == (_lib.PRIOR_EXTERNAL, 6)
+    assert describe_prior(stats.norm(0, 1))[:2] == (_lib.PRIOR_EXTERNAL, 1)       # any object with logpdf
+    with pytest.raises(TypeError):
+        describe_prior(object())

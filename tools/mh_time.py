@@ -2,7 +2,6 @@
 import os, sys
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
-import bench
 import smcpy_b200 as sb
 from smcpy_b200 import engine
 from smcpy_b200.initializer import Initializer
