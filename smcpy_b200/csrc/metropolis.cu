@@ -1231,11 +1231,13 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     }
     const int64_t per_tile = (int64_t)TPB * PPT;
     const int64_t n_tiles = (a.n + per_tile - 1) / per_tile;
-    // persistent blocks (stage L / data once, loop over tiles) for the bandwidth-bound identity
-    // model; one tile per block for the FP64-bound models, where the hardware block scheduler
-    // balances the tail better than a static tile loop (SMCB_PERSIST overrides: tuning aid)
     const int persist_env = options().persist;
-    const bool persist = DYN || (persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL));
+    // persistent blocks (stage L / data once, loop over tiles) for the kernels with little work per particle
+    // (identity model, MVNormal through its scatter matrix: C4 0.188 ms persistent against 0.277 ms with one
+    // 128-particle tile per block, and on several GPUs every block also ends with a fence + ticket); one tile
+    // per block for the FP64-bound models with long tiles, where the hardware block scheduler balances the
+    // tail better than a static tile loop (C3: 10.6 ms against 11.2 ms).  SMCB_PERSIST overrides: tuning aid
+    const bool persist = DYN || (persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL || is_mvn(KIND)));
     const int64_t cap = persist ? (int64_t)kNumSMs * blocks_per_sm : n_tiles;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
     if (MODE == 1) {

@@ -69,7 +69,12 @@ class VectorMCMCKernel(KernelBase):
         return self._conv_param_array_to_dict(self._mcmc.sample_from_priors(num_samples))
 
     def sample_from_proposal(self, num_samples):
-        arr = self.path.proposal.rvs(num_samples, random_state=self.rng)
+        rng = self.rng
+        if isinstance(rng, engine.PhiloxRNG):
+            # the proposal object draws on the host (scipy): give it a numpy Generator keyed by the native
+            # generator's seed and next stream -- the same on every rank
+            rng = np.random.default_rng([rng.seed & 0xFFFFFFFF, rng.seed >> 32, rng.next_stream()])
+        arr = self.path.proposal.rvs(num_samples, random_state=rng)
         return self._conv_param_array_to_dict(arr)
 
     def get_log_likelihoods(self, param_dict):

@@ -21,6 +21,18 @@ from .storage import ContextManager, InMemoryStorage
 from .updater import Updater
 
 
+def rank_zero_value(value):
+    """Rank 0's copy of a host scalar on every rank (the reference decorates optimize_step with
+    rank_zero_output_only, smcpy/utils/mpi_utils.py:18-28, so that every MPI rank follows rank 0's decision);
+    the identity without a process group."""
+    if engine.dist_info()[1] == 1:
+        return value
+    import torch.distributed as dist
+    box = [value]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
 class SamplerBase:
     def __init__(self, mcmc_kernel, show_progress_bar=True):
         self._mcmc_kernel = mcmc_kernel
@@ -53,6 +65,13 @@ class SamplerBase:
     def _save_step(self, step):
         self._result.save_step(step)          # every rank keeps (or writes) its own shard
 
+    def _finish(self):
+        """End of sample(): file-backed stores stream steps out asynchronously -- wait for the last write."""
+        flush = getattr(self._result, "flush", None)
+        if flush is not None:
+            flush()
+        return self._result, self._result.estimate_marginal_log_likelihoods()
+
     def _initialize(self, num_particles):
         """samplers.py:87-92.  With a file-backed result store opened on an existing file the run
         resumes from the last stored step: its particles go back to the device (log-priors are
@@ -62,12 +81,24 @@ class SamplerBase:
         if self._result is not None and getattr(self._result, "is_restart", False) and len(self._result) > 0:
             if engine.dist_info()[1] > 1:
                 raise NotImplementedError("restart from a file-backed store is single-GPU")
-            import ctypes as C
-            from ._lib import call, ptr, stream_ptr
             last = self._result[-1]
-            st = last.to_state()
-            call("smcb_log_priors", C.byref(self._mcmc_kernel.spec.c), ptr(st.cols), st.n, st.n, ptr(st.lp),
-                 None, stream_ptr())
+            kernel = self._mcmc_kernel
+            spec = kernel.spec
+            # fresh working set with the layout this problem needs (a proposal log-pdf column when the path has
+            # one); log-priors, log-likelihoods and log q are re-evaluated from the stored parameters
+            st = engine.DeviceState(last.num_particles, last.num_particles, spec.d, with_lq=spec.has_device_proposal)
+            st.cols[:spec.d].copy_(last._cols[:spec.d])
+            st.log_w.copy_(last._log_w)
+            st.w.copy_(last._w)
+            st.total_unnorm_log_weight = last.attrs.get("total_unnorm_log_weight")
+            engine.eval_incoming(st, spec)
+            st.check_flags("restart", allow_oob=True)
+            if not kernel.has_proposal():
+                st.lp_const = spec.lp_const
+            if isinstance(kernel.rng, engine.PhiloxRNG) and "rng_stream" in last.attrs:
+                # continue the counter-based generator where the stored run left it: resumed steps must not
+                # reuse the (seed, stream, particle) tuples of the original run
+                kernel.rng._stream = max(kernel.rng._stream, int(last.attrs["rng_stream"]))
             self._st = st
             self._step = last                      # already stored: not saved again
             self._restart_phi = list(self._result.phi_sequence)
@@ -86,6 +117,8 @@ class SamplerBase:
         ratio = self._mutator.mutate_state(st, num_mcmc_samples)      # reads the deferred checks with its one sync
         attrs = {"total_unnorm_log_weight": st.total_unnorm_log_weight, "phi": self._mcmc_kernel.path.phi,
                  "mutation_ratio": ratio}
+        if isinstance(self._mcmc_kernel.rng, engine.PhiloxRNG):
+            attrs["rng_stream"] = self._mcmc_kernel.rng._stream
         self.step = Particles.from_state(st, self._mcmc_kernel.param_order, attrs)
 
     # progress bar (samplers.py:104-124), rank 0 only
@@ -131,7 +164,7 @@ class FixedPhiSampler(SamplerBase):
                 bar.set_description(f"[ mutation ratio: {self.step.attrs['mutation_ratio']}")
                 bar.update(float(self._phi_sequence[i + 1] - self._phi_sequence[i]))
         self._pbar_close(bar)
-        return self._result, self._result.estimate_marginal_log_likelihoods()
+        return self._finish()
 
 
 class AdaptiveSampler(SamplerBase):
@@ -161,7 +194,7 @@ class AdaptiveSampler(SamplerBase):
         self._pbar_close(bar)
         self.req_phi_index = [i for i, phi in enumerate(self.phi_sequence)
                               if phi in self._mcmc_kernel.path.required_phi_list]
-        return self._result, self._result.estimate_marginal_log_likelihoods()
+        return self._finish()
 
     def _state_of(self, particles):
         if particles is self._step and self._st is not None:
@@ -231,7 +264,9 @@ class FixedTimeSampler(AdaptiveSampler):
 
     def _do_smc_step(self, phi, num_mcmc_samples):
         super()._do_smc_step(phi=phi, num_mcmc_samples=num_mcmc_samples)
-        self._time_history.append(time.time() - self._start_time)
+        # one clock for the whole job: every phi decision below derives from this history, so the ranks of a
+        # multi-GPU run cannot disagree (and then issue mismatched collectives)
+        self._time_history.append(rank_zero_value(time.time() - self._start_time))
         estimated_future_time = self.prev_time_step + self._time_history[-1]
         if self._buffer_phi is None and estimated_future_time >= self.buffer_time:
             self._buffer_phi = phi

@@ -5,8 +5,11 @@ stores (HDF5Storage :79-170, PickleStorage :173-277).
 
 Steps are device snapshots (`Particles`).  InMemoryStorage keeps them in HBM (`retain` bounds how
 many; the reference keeps every step, 17 GB per step at 64M x 32).  The file-backed stores stream
-every step to the host through page-locked memory (engine.host) as it is produced and keep nothing
-on the device; reading a step back (`storage[i]`, iteration, restart) uploads it again.
+every step out ASYNCHRONOUSLY (StepStreamer): save_step() enqueues a device-to-host copy of the
+snapshot's SoA rows into page-locked memory on a dedicated copy stream, ordered after the producing
+kernels by an event, and a writer thread appends the record to the file once the copy has landed --
+the sampler goes on with the next SMC step meanwhile.  Nothing stays on the device; reading a step
+back (`storage[i]`, iteration, restart) drains the queue first and uploads the step again.
 
 On-disk formats:
   * HDF5Storage writes the reference's layout -- one group per step named by its index, attrs `phi`,
@@ -57,6 +60,86 @@ class ContextManager:
         if not s:
             raise TypeError("No context on context stack")
         return s[-1]
+
+
+class StepStreamer:
+    """Asynchronous device -> host -> file pipeline of the file-backed stores.
+    submit(step, sink) returns at once; sink(record) runs on the writer thread, in submission order.
+    The structure-of-arrays layout makes every parameter one contiguous row, so the record's arrays are
+    views of the pinned buffer -- no transposition on the way out."""
+
+    def __init__(self, depth=4):
+        import queue
+        self._q = queue.Queue(maxsize=depth)         # bounds the page-locked memory in flight
+        self._err = None
+        self._thread = None
+        self._stream = None
+
+    def _worker(self):
+        while True:
+            item = self._q.get()
+            try:
+                if item is None:
+                    return
+                done, rec, sink, _keep = item
+                if self._err is None:
+                    if done is not None:
+                        done.synchronize()                # the copy of this step has landed
+                    sink(rec)
+            except BaseException as e:                     # surfaced by the next submit / drain
+                self._err = e
+            finally:
+                self._q.task_done()
+
+    def _start(self):
+        if self._thread is None:
+            self._thread = threading.Thread(target=self._worker, name="smcb-step-writer", daemon=True)
+            self._thread.start()
+
+    def submit(self, step, sink):
+        self._raise()
+        cols = getattr(step, "_cols", None)
+        if cols is None or not getattr(cols, "is_cuda", False):
+            self.drain()
+            sink(_host_record(step))                            # host-side step object: nothing to overlap
+            return
+        self._start()
+        import torch
+        d, n = step._d, step._num_particles
+        if self._stream is None:
+            self._stream = torch.cuda.Stream()
+        ready = torch.cuda.Event()
+        ready.record()                                      # after everything that produced the snapshot
+        buf = torch.empty((d + 2, n), dtype=torch.float64, pin_memory=True)
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(ready)
+            buf[:d + 1].copy_(cols[:d + 1], non_blocking=True)     # parameters + log-likelihood rows
+            buf[d + 1].copy_(step._log_w, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        arr = buf.numpy()
+        rec = {"params": {k: arr[i] for i, k in enumerate(step.param_names)},
+               "log_likes": arr[d].reshape(-1, 1), "log_weights": arr[d + 1].reshape(-1, 1),
+               "attrs": _step_attrs(step)}
+        self._q.put((done, rec, sink, step))                # the snapshot stays referenced until its copy has landed
+
+    def drain(self):
+        if self._thread is not None:
+            self._q.join()
+        self._raise()
+
+    def _raise(self):
+        if self._err is not None:
+            e, self._err = self._err, None
+            raise e
+
+
+def _step_attrs(step):
+    a = {"phi": step.attrs["phi"], "mutation_ratio": step.attrs["mutation_ratio"],
+         "total_unnorm_log_weight": step.total_unnorm_log_weight}
+    if "rng_stream" in step.attrs:          # native generator: stream counter, restored on restart
+        a["rng_stream"] = int(step.attrs["rng_stream"])
+    return a
 
 
 class BaseStorage(ContextManager):
@@ -134,11 +217,10 @@ def _rank_filename(filename):
 
 
 def _host_record(step):
-    """Host copy of one step: what both file formats store."""
+    """Host copy of one step (synchronous): what both file formats store."""
     return {"params": {k: np.array(v) for k, v in step.param_dict.items()},
             "log_likes": np.array(step.log_likes), "log_weights": np.array(step.log_weights),
-            "attrs": {"phi": step.attrs["phi"], "mutation_ratio": step.attrs["mutation_ratio"],
-                      "total_unnorm_log_weight": step.total_unnorm_log_weight}}
+            "attrs": _step_attrs(step)}
 
 
 def _particles_from_record(rec):
@@ -155,8 +237,9 @@ class PickleStorage(BaseStorage):
         _check_mode(mode)
         super().__init__()
         self._filename = _rank_filename(filename)
-        self._offsets = []                   # byte offset of every stored step
+        self._offsets = []                   # byte offset of every stored step (appended by the writer thread)
         self._meta = []                      # (phi, mutation_ratio, total_unnorm_log_weight) per step
+        self._streamer = StepStreamer()
         if mode == "w" and os.path.exists(self._filename):
             os.remove(self._filename)
         if os.path.exists(self._filename):
@@ -187,19 +270,26 @@ class PickleStorage(BaseStorage):
     def _step_totals(self):
         return [m[2] for m in self._meta]
 
-    def __len__(self):
-        return len(self._offsets)
-
     def save_step(self, step):
-        rec = _host_record(step)
+        a = _step_attrs(step)
+        self._meta.append((a["phi"], a["mutation_ratio"], a["total_unnorm_log_weight"]))   # known at once
+        self._streamer.submit(step, self._write)
+
+    def _write(self, rec):
         pos = os.path.getsize(self._filename) if os.path.exists(self._filename) else 0
         with open(self._filename, "ab") as f:
             pickle.dump(rec, f, pickle.HIGHEST_PROTOCOL)
         self._offsets.append(pos)
-        a = rec["attrs"]
-        self._meta.append((a["phi"], a["mutation_ratio"], a["total_unnorm_log_weight"]))
+
+    def flush(self):
+        """Blocks until every submitted step is in the file."""
+        self._streamer.drain()
+
+    def __len__(self):
+        return len(self._meta)
 
     def __getitem__(self, idx):
+        self.flush()
         idx = self._index(idx)
         with open(self._filename, "rb") as f:
             f.seek(self._offsets[idx])
@@ -223,6 +313,7 @@ class HDF5Storage(BaseStorage):
         self._filename = _rank_filename(filename)
         self._mode = mode
         self._len = 0
+        self._streamer = StepStreamer()
         if os.path.exists(self._filename) and mode == "a":
             with self._open("r") as h5:
                 self._len = len(h5.keys())
@@ -231,7 +322,12 @@ class HDF5Storage(BaseStorage):
     def _open(self, mode):
         return self._h5py.File(self._filename, mode, track_order=True)
 
+    def flush(self):
+        """Blocks until every submitted step is in the file."""
+        self._streamer.drain()
+
     def _attr_list(self, name):
+        self.flush()
         with self._open("r") as h5:
             return [h5[str(i)].attrs[name] for i in range(len(h5.keys()))]
 
@@ -250,20 +346,25 @@ class HDF5Storage(BaseStorage):
         return self._len
 
     def save_step(self, step):
-        rec = _host_record(step)
+        self._len += 1
+        self._streamer.submit(step, self._write)
+
+    def _write(self, rec):
         with self._open(self._mode) as h5:
             self._mode = "a"
             grp = h5.create_group(str(len(h5.keys())))
-            for k, v in rec["attrs"].items():
-                grp.attrs[k] = v
+            for k in ("phi", "total_unnorm_log_weight", "mutation_ratio"):     # the reference's three, its order
+                grp.attrs[k] = rec["attrs"][k]
+            if "rng_stream" in rec["attrs"]:
+                grp.attrs["rng_stream"] = rec["attrs"]["rng_stream"]
             grp.create_dataset("log_likes", data=rec["log_likes"])
             grp.create_dataset("log_weights", data=rec["log_weights"])
             pg = grp.create_group("params", track_order=True)
             for k, v in rec["params"].items():
                 pg.create_dataset(k, data=v)
-            self._len = len(h5.keys())
 
     def __getitem__(self, idx):
+        self.flush()
         idx = self._index(idx)
         with self._open("r") as h5:
             grp = h5[str(idx)]

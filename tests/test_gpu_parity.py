@@ -836,6 +836,62 @@ def test_pickle_storage_streams_steps_and_restarts(sb, tmp_path):
     assert mll2[-1] == pytest.approx(mll[-1], abs=0.3)
 
 
+def test_hdf5_storage_async_streaming_and_restart_details(sb, tmp_path, monkeypatch):
+    """f3: HDF5Storage (through the h5py stand-in of tests/h5py_stub.py -- the image has no h5py) receives the
+    device snapshots through the asynchronous copy stream + writer thread and reads back equal to the
+    in-memory run; a restart continues the native generator's stream counter and rebuilds the proposal
+    log-pdf column of a path with a proposal (restart)."""
+    import sys
+    from tests import h5py_stub
+    monkeypatch.setitem(sys.modules, "h5py", h5py_stub.module())
+    problem = configs.proposal_problem([0.2, 0.6])
+
+    def sampler(storage, seed):
+        mcmc, kernel = make_b200(problem, rng=seed)
+        if storage is None:
+            return sb.AdaptiveSampler(kernel, show_progress_bar=False), kernel
+        with storage:
+            return sb.AdaptiveSampler(kernel, show_progress_bar=False), kernel
+    smc, _ = sampler(None, 21)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mem_steps, mem_mll = smc.sample(20000, 3, target_ess=0.8, resample_rng=sb.stratified)
+    fn = tmp_path / "run.h5"
+    smc, kernel = sampler(sb.HDF5Storage(fn, mode="w"), 21)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steps, mll = smc.sample(20000, 3, target_ess=0.8, resample_rng=sb.stratified)
+    assert isinstance(steps, sb.HDF5Storage) and len(steps) == len(mem_steps)
+    np.testing.assert_array_equal(mll, mem_mll)
+    for i in (0, 1, len(steps) - 1):
+        np.testing.assert_array_equal(steps[i].params, mem_steps[i].params)
+        np.testing.assert_array_equal(steps[i].log_likes, mem_steps[i].log_likes)
+        np.testing.assert_array_equal(steps[i].log_weights, mem_steps[i].log_weights)
+    assert steps[-1].param_names == ("a", "b") and steps[-1].attrs["phi"] == 1.0
+    assert steps[-1].attrs["rng_stream"] == kernel.rng._stream
+    # resume from the first three stored steps: a copy of the file cut after group "2"
+    from tests.h5py_stub import File
+    fn2 = tmp_path / "cut.h5"
+    with File(fn, "r") as src, File(fn2, "w") as dst:
+        for k in ("0", "1", "2"):
+            dst._items[k] = src[k]
+    store = sb.HDF5Storage(fn2)
+    assert store.is_restart and len(store) == 3
+    stream_at_2 = store[2].attrs["rng_stream"]
+    smc2, kernel2 = sampler(store, 21)
+    assert kernel2.spec.has_device_proposal
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steps2, mll2 = smc2.sample(20000, 3, target_ess=0.8, resample_rng=sb.stratified)
+    assert smc2._st.with_lq                                       # proposal column rebuilt on restart
+    assert kernel2.rng._stream > stream_at_2                      # the counter went on from the stored value
+    np.testing.assert_array_equal(mll2[:4], mem_mll[:4])
+    assert list(smc2.phi_sequence[:3]) == list(smc.phi_sequence[:3]) and smc2.phi_sequence[-1] == 1.0
+    # same seed, same stream counter, same stored particles: the resumed run IS the original run
+    np.testing.assert_allclose(smc2.phi_sequence, smc.phi_sequence, rtol=1e-12)
+    np.testing.assert_allclose(mll2, mem_mll, rtol=1e-10)
+
+
 def test_full_size_c2_step_properties(sb):
     """One SMC step of the headline workload at its full size (2^20 particles, 1000 data points, 20
     Metropolis steps, native RNG), checked through size-independent properties: normalised weights,

@@ -110,6 +110,51 @@ def test_sharded_resampling_bookkeeping_gloo():
         assert mism <= 1                         # sharded offsets may move an edge by one ulp
 
 
+def _fixed_time_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import time
+    from scipy import stats
+    import smcpy_b200 as sb
+    from smcpy_b200 import samplers
+    mc = sb.B200VectorMCMC(sb.LinearModel(np.arange(3.0)), np.zeros(3), [stats.uniform(0, 1)] * 2, 1.0)
+    kernel = sb.VectorMCMCKernel(mc, ["a", "b"], rng=np.random.default_rng(0))
+    smc = sb.FixedTimeSampler(kernel, time=0.5, show_progress_bar=False)
+    # the device work is replaced by sleeps of different length per rank: local clocks disagree
+    samplers.AdaptiveSampler._do_smc_step = lambda self, phi, num_mcmc_samples: time.sleep(0.03 * (1 + 2 * rank))
+    samplers.AdaptiveSampler.optimize_step = lambda self, particles, phi_old, target_ess=1: min(1.0, phi_old + 0.05)
+    smc._start_time = time.time()
+    phis = [0.0]
+    while phis[-1] < 1 and len(phis) < 100:
+        phi = smc.optimize_step(None, phis[-1], 0.8)
+        smc._do_smc_step(phi, 1)
+        phis.append(phi)
+    assert samplers.rank_zero_value(rank) == 0
+    out.put((rank, phis, list(smc._time_history), smc._buffer_phi))
+    dist.destroy_process_group()
+
+
+def test_fixed_time_sampler_ranks_follow_rank_zero_clock_gloo():
+    """FixedTimeSampler decides phi from wall-clock time; under one process per GPU every rank must
+    take rank 0's decisions (smcpy/smc/samplers.py:304-379 + utils/mpi_utils.py rank_zero_output_only)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fixed_time_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict((r[0], r[1:]) for r in (q.get(timeout=120) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][0] == res[1][0] and res[0][0][-1] == 1        # same phi sequence, ended by the time budget
+    assert res[0][1] == res[1][1] and res[0][2] == res[1][2]    # same time history and buffer phi
+    assert len(res[0][0]) < 21                                  # jumped to 1 before the 0.05 steps got there
+
+
 def _nccl_worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
