@@ -37,18 +37,25 @@ __host__ __device__ constexpr bool is_mvn(int kind) { return kind == K_LINEAR_MV
 //     with t = fl(x-loc) that is exactly 0 <= t <= scale (DESIGN.md "priors"), no division;
 //   ImproperUniform(lo, hi):   a = 0 (t = x exactly), [lo, hi];
 //   columns of a matrix prior: a = 0, [-inf, inf].
+// One record per column (32 B): the d columns a kernel tests are contiguous in the constant bank -- as
+// separate arrays (a[32], lo[32], hi[32]) they were 256 B apart and, with the rest of the 3.7 KB argument
+// block, kept evicting one another from the per-SM constant cache (profiles/r02_kernels.md).
+struct ColPrior {
+    double a, lo, hi, logp;
+};
 struct ColPriors {
-    int8_t prior_of_col[SMCB_MAX_PARAMS];   // -1: column belongs to a matrix prior
-    double a[SMCB_MAX_PARAMS], lo[SMCB_MAX_PARAMS], hi[SMCB_MAX_PARAMS], logp[SMCB_MAX_PARAMS];
+    ColPrior col[SMCB_MAX_PARAMS];
     double logp_total;                      // sum of logp in column order
+    int8_t prior_of_col[SMCB_MAX_PARAMS];   // -1: column belongs to a matrix prior
     int32_t n_external;                     // number of EXTERNAL (host-evaluated) priors
     int32_t n_cov;                          // number of IMPROPER_COV priors (<= 2)
     int32_t cov_c0[2], cov_ncols[2], cov_prior[2];
 };
 
+// Kernel argument block (3.7 KB of constant bank).  What every tile of the hot loop reads comes first and
+// close together (pointers, sizes, path, generator, round keys, the prior records); the problem description,
+// of which a kernel reads a few scalars, goes last.
 struct MhArgs {
-    smcb_problem_t prob;
-    ColPriors cp;
     double* params;
     int64_t stride, n;
     double n_global;
@@ -65,8 +72,10 @@ struct MhArgs {
     double* lp_cols;      // init / priors only (optional)
     double* new_params;   // propose only
     double* new_lp;       // propose only
-    smcb_xchg_t x;        // world <= 1: no cross-GPU exchange
     PhiloxKeys rk;        // Philox round keys of rng.seed
+    ColPriors cp;
+    smcb_xchg_t x;        // world <= 1: no cross-GPU exchange
+    smcb_problem_t prob;
 };
 
 // covariance scale after the first `step` Metropolis steps (vector_mcmc.py:55-60):
@@ -179,8 +188,8 @@ __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th
 #pragma unroll
     for (int c = 0; c < DMAX; ++c) {
         if (EXACT || c < d) {
-            const double t = th[c] - a.cp.a[c];
-            ok = ok && (t >= a.cp.lo[c]) && (t <= a.cp.hi[c]);
+            const double t = th[c] - a.cp.col[c].a;
+            ok = ok && (t >= a.cp.col[c].lo) && (t <= a.cp.col[c].hi);
         }
     }
     double lps = ok ? a.cp.logp_total : kNegInf;
@@ -190,9 +199,9 @@ __device__ __forceinline__ double eval_priors(const MhArgs& a, const double (&th
             double x = 0.0;
 #pragma unroll
             for (int k = 0; k < DMAX; ++k) x = (k == c) ? th[k] : x;
-            const double t = x - a.cp.a[c];
+            const double t = x - a.cp.col[c].a;
             lp_cols_row[(int64_t)a.cp.prior_of_col[c] * col_stride] =
-                (t >= a.cp.lo[c] && t <= a.cp.hi[c]) ? a.cp.logp[c] : kNegInf;
+                (t >= a.cp.col[c].lo && t <= a.cp.col[c].hi) ? a.cp.col[c].logp : kNegInf;
         }
     }
     // matrix priors: packed upper-triangular columns must form a Cholesky-PD matrix.
@@ -1068,9 +1077,9 @@ __global__ void __launch_bounds__(256) sample_priors_kernel(ColPriors cp, IwArgs
         const uint64_t pid = (uint64_t)(id_offset + i);
         for (int c = 0; c < d; c += 2) {
             const uint4 r = rng(pid, (uint32_t)(c >> 1), stream_id);
-            if (cp.prior_of_col[c] >= 0) params[(int64_t)c * stride + i] = cp.a[c] + cp.hi[c] * u01_53(r.x, r.y);
+            if (cp.prior_of_col[c] >= 0) params[(int64_t)c * stride + i] = cp.col[c].a + cp.col[c].hi * u01_53(r.x, r.y);
             if (c + 1 < d && cp.prior_of_col[c + 1] >= 0)
-                params[(int64_t)(c + 1) * stride + i] = cp.a[c + 1] + cp.hi[c + 1] * u01_53(r.z, r.w);
+                params[(int64_t)(c + 1) * stride + i] = cp.col[c + 1].a + cp.col[c + 1].hi * u01_53(r.z, r.w);
         }
         for (int q = 0; q < iw.n_cov; ++q) {
             const int p = iw.ncols[q];
@@ -1148,8 +1157,8 @@ static int build_col_priors(const smcb_problem_t* p, ColPriors* cp) {
     const double inf = __builtin_huge_val();
     for (int c = 0; c < SMCB_MAX_PARAMS; ++c) {
         cp->prior_of_col[c] = -1;
-        cp->lo[c] = -inf;
-        cp->hi[c] = inf;
+        cp->col[c].lo = -inf;
+        cp->col[c].hi = inf;
     }
     int col = 0;
     double total = 0.0;
@@ -1159,15 +1168,15 @@ static int build_col_priors(const smcb_problem_t* p, ColPriors* cp) {
             if (col >= SMCB_MAX_PARAMS) return -1;
             cp->prior_of_col[col] = (int8_t)q;
             if (pr.kind == SMCB_PRIOR_UNIFORM) {
-                cp->a[col] = pr.a;
-                cp->lo[col] = 0.0;
-                cp->hi[col] = pr.b;
+                cp->col[col].a = pr.a;
+                cp->col[col].lo = 0.0;
+                cp->col[col].hi = pr.b;
             } else {
-                cp->a[col] = 0.0;
-                cp->lo[col] = pr.a;
-                cp->hi[col] = pr.b;
+                cp->col[col].a = 0.0;
+                cp->col[col].lo = pr.a;
+                cp->col[col].hi = pr.b;
             }
-            cp->logp[col] = pr.logp_in;
+            cp->col[col].logp = pr.logp_in;
             total += pr.logp_in;
             col += 1;
         } else if (pr.kind == SMCB_PRIOR_IMPROPER_COV) {
@@ -1183,7 +1192,7 @@ static int build_col_priors(const smcb_problem_t* p, ColPriors* cp) {
             if (pr.ncols < 1 || col + pr.ncols > SMCB_MAX_PARAMS) return -1;
             for (int k = 0; k < pr.ncols; ++k) {
                 cp->prior_of_col[col + k] = (int8_t)q;
-                cp->a[col + k] = 0.0;
+                cp->col[col + k].a = 0.0;
             }
             col += pr.ncols;
             cp->n_external += 1;
