@@ -374,6 +374,12 @@ def north_star_gpu(sb, engine, _lib, torch, dist, rank, world, local, peaks):
         b = (16 * C5_D + 48) * n_local
         kern["resample"] = {"avg_ms": ms, "calls": len(prof["resample"]), "alg_bytes_per_particle": 16 * C5_D + 48,
                             "gbps": b / ms / 1e6, "frac_hbm": b / ms / 1e6 / hbm, "share_of_wall": share["resample"]}
+        if pbytes.get("rs_nvlink_rows"):
+            rows = float(np.mean(pbytes["rs_nvlink_rows"]))
+            kern["resample"]["nvlink_rows_per_call"] = rows          # rank 0's rows written into other ranks' buffers
+            kern["resample"]["nvlink_bytes_per_call"] = rows * 8 * (C5_D + 2)
+            kern["resample"]["nvlink_note"] = ("rank 0, from the exchanged rank weight totals: slots whose sorted uniform "
+                                               "falls into this rank's CDF segment minus the slots it holds itself")
     if "cov" in prof:
         ms = float(np.mean(prof["cov"]))
         b = 16 * C5_D * n_local

@@ -3,17 +3,14 @@ Multi-GPU resampling: particles are sharded in contiguous blocks, one process pe
 (replaces the MPI scatter/allgather of model evaluations in
 smcpy/mcmc/parallel_vector_mcmc.py:36-47 by sharding the whole particle loop).
 
-Per resample:
-  1. local inclusive scan of the (globally normalised) weights           [smcb_cdf_scan]
-  2. all-gather of the per-rank weight totals -> segment offsets O_r     [NCCL, G doubles]
-  3. every rank draws the uniforms of its own output slots                [smcb_resample_uniforms]
-     and routes each to the rank whose CDF segment [O_r, O_r+1) holds it  [all-to-all, 8 B/slot]
-  4. the owner searches its local CDF (+ offset) and gathers the rows     [smcb_searchsorted_offset,
-                                                                           smcb_gather]
-  5. rows travel back to the requesting rank                              [all-to-all, 8(d+2) B/slot]
-Stratified / systematic uniforms are already sorted, so step 3 is a split of a contiguous range;
-multinomial uniforms are sorted first (particles are exchangeable, so slot order is immaterial).
-Collectives are NCCL over NVLink; every count that decides a split is exchanged explicitly.
+resample_sharded (default): owner-computes over NVLink peer memory -- local CDF scan, rank totals through
+the peer-memory exchange kernel, then every rank searches its own CDF for the contiguous range of global
+output slots whose sorted uniform falls into its segment and writes the selected rows straight into the
+buffer of the rank that holds the slot.  No routing of requests, no NCCL payload, no host sync.
+_resample_sharded_routed (fallback without symmetric memory, and the round-1 form): uniforms of a rank's own
+slots are routed to the rank whose CDF segment holds them (all-to-all), answered, and the rows travel back.
+The uniforms of every built-in resampler are sorted (stratified / systematic by construction, multinomial by
+exponential spacings), so both forms deal in contiguous ranges.
 """
 
 import os
@@ -146,6 +143,14 @@ def resample_sharded(st, kernel, resample_rng, warn_threshold, defer=False):
     else:
         engine.warn_collapsed(int(n_unique.item()), n_global, warn_threshold)
     ph(None)
+    if engine.PROFILE is not None:
+        # rows this rank writes into OTHER ranks' buffers over NVLink: slots whose uniform falls into this rank's
+        # CDF segment [O_r, O_r+1) minus the slots it holds itself (profiling only: one extra host read)
+        tot = totals[:, 0].cpu().numpy()
+        off = np.concatenate([[0.0], np.cumsum(tot)]) / max(float(tot.sum()), 1e-300)
+        lo_s, hi_s = off[rank] * st.n_global, off[rank + 1] * st.n_global
+        own = max(0.0, min(hi_s, (rank + 1) * n) - max(lo_s, rank * n))
+        engine._note_bytes("rs_nvlink_rows", max(0.0, (hi_s - lo_s) - own))
     return None
 
 
