@@ -385,6 +385,25 @@ def north_star_gpu(sb, engine, _lib, torch, dist, rank, world, local, peaks):
         b = 16 * C5_D * n_local
         kern["covariance"] = {"avg_ms": ms, "calls": len(prof["cov"]), "alg_bytes_per_particle": 16 * C5_D,
                               "gbps": b / ms / 1e6, "frac_hbm": b / ms / 1e6 / hbm, "share_of_wall": share["cov"]}
+    # the same mutation kernel with the strict fp64 proposal (fp64 FMAs for L.z instead of the tf32 tensor-core product)
+    strict = None
+    try:
+        prof_keep, bytes_keep = engine.PROFILE, dict(engine.PROFILE_BYTES)
+        old = _lib.set_option("strict_proposal", 1)
+        try:
+            c5(2, profile=True)
+            ms_strict = float(np.mean([a.elapsed_time(b) for a, b in engine.PROFILE["mh_step"]]))
+            strict = {"kernel": _lib.last_mh_variant(), "avg_ms": ms_strict, "gbps": b_mut / ms_strict / 1e6,
+                      "frac_hbm": b_mut / ms_strict / 1e6 / hbm}
+        finally:
+            _lib.set_option("strict_proposal", old)
+            engine.PROFILE = None
+            engine.PROFILE_BYTES.clear()
+            engine.PROFILE_BYTES.update(bytes_keep)
+        gc.collect()
+    except Exception as e:                                   # pragma: no cover
+        strict = {"error": "%s: %s" % (type(e).__name__, e)}
+    kern["mutation_strict_fp64_proposal"] = strict
     out["c5"] = {"workload": "C5: 32-dim Gaussian target, AdaptiveSampler to phi=1, 2^%d particles per GPU x %d GPU(s) = %d, "
                              "K=%d, target_ess=0.8, standard resampling, native Philox generator"
                              % (C5_LOG2N, world, n_global, C5_K),

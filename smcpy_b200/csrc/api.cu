@@ -42,6 +42,7 @@ Options& options() {
         v.bisect_plain = env_int("SMCB_BISECT_PLAIN", 0);
         v.spring_ppt = env_int("SMCB_SPRING_PPT", -1);
         v.no_mvn3 = env_int("SMCB_NO_MVN3", 0);
+        v.no_pref = env_int("SMCB_NO_PREF", 0);
         v.xchg_timeout_s = env_int("SMCB_XCHG_TIMEOUT_S", 0);
         v.no_fused_resample = env_int("SMCB_NO_FUSED_RESAMPLE", 0);
         return v;
@@ -68,6 +69,7 @@ static const OptEntry kOptTable[] = {
     {"spring_ppt", &Options::spring_ppt},   {"xchg_timeout_s", &Options::xchg_timeout_s},
     {"no_fused_resample", &Options::no_fused_resample},
     {"no_mvn3", &Options::no_mvn3},
+    {"no_pref", &Options::no_pref},
 };
 
 }  // namespace smcb

@@ -43,6 +43,7 @@ struct Options {
     int bisect_plain;      // 1: evaluate every scipy midpoint (no monotone bracketing)
     int spring_ppt;        // -1 auto; 1/2 particles per thread in the RK4 kernel
     int no_mvn3;           // 1: never take the static-layout MVNormal kernel (K_LINEAR_MVN3)
+    int no_pref;           // 1: never take the cp.async-prefetching variant of it
     int xchg_timeout_s;    // peer-exchange time-out inside kernels (seconds; 0 = default 30)
     int no_fused_resample; // 1: separate uniforms / search / count / gather kernels (native mode)
 };
@@ -411,6 +412,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// per-thread asynchronous 8-byte copy global -> shared (LDGSTS): each thread prefetches ITS OWN next-tile values
+// into thread-private shared slots, so no block barrier is needed -- cp_async_wait_all() makes them visible to
+// the issuing thread
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace smcb

@@ -563,8 +563,12 @@ __device__ __forceinline__ double ll_multisource(const MhArgs& a, const double (
 //       MULTI: MultiSourceNormal likelihood (segment table in the problem).
 //       STRICT (with TMA): the increment sqrt(s) L z is accumulated with fp64 FMAs instead of the tf32
 //       tensor-core product (option "strict_proposal"); same normals, same Philox counters.
+//       PREF (persistent static tiles, PPT = 1, MODE 1): every thread prefetches its own d + 2 values of the
+//       block's NEXT tile into thread-private shared slots with cp.async (LDGSTS) while it computes the
+//       current tile -- hides the column-load latency of the narrow bandwidth-bound kernels (C4) without a
+//       block barrier.
 template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
-          bool DYN = false, bool MULTI = false, bool STRICT = false>
+          bool DYN = false, bool MULTI = false, bool STRICT = false, bool PREF = false>
 __global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT, TMA, KIND))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -632,6 +636,22 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         __syncthreads();
         if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) tma_issue(blockIdx.x);
     }
+    // PREF stage: (d + 2) x TPB doubles after the data staging area, slot [c][threadIdx.x] is private to the thread
+    double* pstage = sdata + 64;
+    auto pref_issue = [&](int64_t tile) {
+        int64_t i = tile * per_tile + threadIdx.x;
+        if (i >= a.n) i = 0;                                   // ragged end: any valid row (the result is not used)
+        const double* pc = a.params + i;
+#pragma unroll
+        for (int c = 0; c < DMAX; ++c) {
+            if (EXACT || c < d) cp_async8(pstage + c * TPB + threadIdx.x, pc);
+            pc += a.stride;
+        }
+        cp_async8(pstage + DMAX * TPB + threadIdx.x, a.ll + i);
+        cp_async8(pstage + (DMAX + 1) * TPB + threadIdx.x, a.lp + i);
+        cp_async_commit();
+    };
+    if (PREF && (int64_t)blockIdx.x < n_tiles) pref_issue(blockIdx.x);
     __shared__ long long sh_tile;
     for (int64_t tile = blockIdx.x;; tile += gridDim.x) {
         if (DYN) {
@@ -774,6 +794,16 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                     }
                 }
             }
+        } else if constexpr (PREF) {
+            const int64_t i = tile * per_tile + threadIdx.x;
+            valid[0] = i < a.n;
+            idx[0] = valid[0] ? i : 0;
+            cp_async_wait_all();                               // this thread's prefetched values have landed
+#pragma unroll
+            for (int c = 0; c < DMAX; ++c) th[0][c] = (EXACT || c < d) ? pstage[c * TPB + threadIdx.x] : 0.0;
+            ll_old[0] = pstage[DMAX * TPB + threadIdx.x];
+            lp_old[0] = pstage[(DMAX + 1) * TPB + threadIdx.x];
+            if (tile + gridDim.x < n_tiles) pref_issue(tile + gridDim.x);     // slots are free: values are in registers
         } else {
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
@@ -1216,15 +1246,17 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
 }
 
 template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
-          bool DYN = false, bool MULTI = false, bool STRICT = false>
+          bool DYN = false, bool MULTI = false, bool STRICT = false, bool PREF = false>
 static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
+    static_assert(!PREF || (PPT == 1 && MODE == 1 && !TMA && !DYN && !PROP), "PREF: persistent static tiles, one particle per thread");
     const size_t smem = mh_smem_bytes(&a.prob) + (size_t)DMAX * DMAX * sizeof(double) +
                         (TMA ? (size_t)(64 + (DMAX + 2) * TPB) * sizeof(double) +
-                                   (size_t)(TPB / 32) * 16 * (DMAX + 4) * sizeof(float) : 0);
+                                   (size_t)(TPB / 32) * 16 * (DMAX + 4) * sizeof(float) : 0) +
+                        (PREF ? (size_t)(64 + (DMAX + 2) * TPB) * sizeof(double) : 0);
     if (TMA) {
         static bool attr = false;
         if (!attr) {
-            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT>,
+            cudaFuncSetAttribute(mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT, PREF>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr = true;
         }
@@ -1233,7 +1265,7 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT>, TPB,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT, PREF>, TPB,
                                                           smem) != cudaSuccess || nb < 1)
             nb = 1;
         blocks_per_sm = nb;
@@ -1246,19 +1278,19 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
     // 128-particle tile per block, and on several GPUs every block also ends with a fence + ticket); one tile
     // per block for the FP64-bound models with long tiles, where the hardware block scheduler balances the
     // tail better than a static tile loop (C3: 10.6 ms against 11.2 ms).  SMCB_PERSIST overrides: tuning aid
-    const bool persist = DYN || (persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL || is_mvn(KIND)));
+    const bool persist = PREF || DYN || (persist_env >= 0 ? (persist_env != 0) : (KIND == K_IDENTITY_NORMAL || is_mvn(KIND)));
     const int64_t cap = persist ? (int64_t)kNumSMs * blocks_per_sm : n_tiles;
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
     if (MODE == 1) {
         char txt[200];
         snprintf(txt, sizeof(txt),
-                 "mh_kernel<kind=%d,dmax=%d,tpb=%d,ppt=%d,exact=%d,tma=%d,prop=%d,dyn=%d,multi=%d,strict=%d> grid=%u "
+                 "mh_kernel<kind=%d,dmax=%d,tpb=%d,ppt=%d,exact=%d,tma=%d,prop=%d,dyn=%d,multi=%d,strict=%d,pref=%d> grid=%u "
                  "rng=%d n=%lld",
-                 KIND, DMAX, TPB, PPT, (int)EXACT, (int)TMA, (int)PROP, (int)DYN, (int)MULTI, (int)STRICT, grid,
+                 KIND, DMAX, TPB, PPT, (int)EXACT, (int)TMA, (int)PROP, (int)DYN, (int)MULTI, (int)STRICT, (int)PREF, grid,
                  (int)a.rng.mode, (long long)a.n);
         note_mh_variant(txt);
     }
-    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT><<<grid, TPB, smem, s>>>(a);
+    mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT, PREF><<<grid, TPB, smem, s>>>(a);
     return check_launch("mh_kernel");
 }
 
@@ -1280,6 +1312,11 @@ static int launch_cfg(const MhArgs& a, cudaStream_t s) {
                         return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true, true, false, false, false, true>(a, s);
                     return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true, true>(a, s);
                 }
+            }
+            if constexpr (KIND == K_LINEAR_MVN3 && MODE == 1 && PPT == 1) {
+                // narrow bandwidth-bound kernel: per-thread cp.async prefetch of the next tile (option no_pref: off)
+                if (!options().no_pref && a.n >= (int64_t)kNumSMs * 8 * TPB)
+                    return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true, false, false, false, false, false, true>(a, s);
             }
             return launch_cfg2<KIND, DMAX, MODE, TPB, PPT, true>(a, s);
         }

@@ -65,7 +65,15 @@ class Particles:
         self = cls.__new__(cls)
         f = (lambda t: t.clone()) if clone else (lambda t: t)
         self._adopt(f(st.cols), f(st.log_w), f(st.w), st.d, names, st.n_global, st.id_offset)
+        self._is_view = not clone
         self.attrs = dict(attrs or {})
+        return self
+
+    def detach(self):
+        """Turns a zero-copy view of a live working set (from_state(clone=False)) into an owning snapshot."""
+        if getattr(self, "_is_view", False):
+            self._cols, self._log_w, self._w = self._cols.clone(), self._log_w.clone(), self._w.clone()
+            self._is_view = False
         return self
 
     def to_state(self):

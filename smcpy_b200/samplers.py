@@ -70,6 +70,8 @@ class SamplerBase:
         flush = getattr(self._result, "flush", None)
         if flush is not None:
             flush()
+        if self._step is not None:
+            self._step.detach()
         return self._result, self._result.estimate_marginal_log_likelihoods()
 
     def _initialize(self, num_particles):
@@ -119,7 +121,10 @@ class SamplerBase:
                  "mutation_ratio": ratio}
         if isinstance(self._mcmc_kernel.rng, engine.PhiloxRNG):
             attrs["rng_stream"] = self._mcmc_kernel.rng._stream
-        self.step = Particles.from_state(st, self._mcmc_kernel.param_order, attrs)
+        # a store that only ever shows the latest step gets a view of the working set (no per-step snapshot copy);
+        # the view of the final step is turned into an owning snapshot by _finish()
+        snap = getattr(self._result, "wants_snapshots", True)
+        self.step = Particles.from_state(st, self._mcmc_kernel.param_order, attrs, clone=snap)
 
     # progress bar (samplers.py:104-124), rank 0 only
     def _pbar_open(self, initial):

@@ -143,6 +143,10 @@ def _step_attrs(step):
 
 
 class BaseStorage(ContextManager):
+    # False: the store never hands out a step other than the most recent one, so the samplers may give it zero-copy
+    # views of the live working set instead of a device-to-device snapshot per SMC step
+    wants_snapshots = True
+
     def __init__(self):
         self.is_restart = False
 
@@ -173,6 +177,8 @@ class InMemoryStorage(BaseStorage):
         self._mut_ratio_sequence = []
         self._totals = []
         self._retain = retain
+        # retain=1: only the latest step is ever visible; at C5 scale a snapshot is 2.3 GB read + written per step
+        self.wants_snapshots = retain != 1
 
     @property
     def phi_sequence(self):

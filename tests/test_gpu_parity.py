@@ -836,6 +836,36 @@ def test_pickle_storage_streams_steps_and_restarts(sb, tmp_path):
     assert mll2[-1] == pytest.approx(mll[-1], abs=0.3)
 
 
+@pytest.mark.parametrize("kind", ["adaptive", "fixed"])
+def test_retain_one_storage_views_equal_full_storage(sb, kind):
+    """InMemoryStorage(retain=1) hands the samplers zero-copy views of the working set instead of a snapshot per
+    SMC step (what bench.py times); the run and its final step must equal the run that keeps every step --
+    incl. fixed-phi steps that do not resample and therefore mutate the viewed buffers in place."""
+    problem = configs.linear_problem(100)
+
+    def run(storage):
+        mcmc, kernel = make_b200(problem, rng=17)
+        cls = sb.AdaptiveSampler if kind == "adaptive" else sb.FixedPhiSampler
+        smc = cls(kernel, show_progress_bar=False)
+        smc._result = storage
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if kind == "adaptive":
+                return smc.sample(5000, 4, target_ess=0.8)
+            return smc.sample(5000, 4, np.linspace(0, 1, 14) ** 2, 0.6, resample_rng=sb.stratified)
+    full, mll_full = run(sb.InMemoryStorage())
+    one, mll_one = run(sb.InMemoryStorage(retain=1))
+    assert len(one) == 1 and len(full) == len(mll_full) - 1
+    np.testing.assert_array_equal(mll_one, mll_full)
+    assert list(one.phi_sequence) == list(full.phi_sequence)
+    a, b = one[-1], full[-1]
+    assert not a._is_view and a._cols.data_ptr() != b._cols.data_ptr()
+    np.testing.assert_array_equal(a.params, b.params)
+    np.testing.assert_array_equal(a.log_likes, b.log_likes)
+    np.testing.assert_array_equal(a.log_weights, b.log_weights)
+    assert a.attrs == b.attrs
+
+
 def test_hdf5_storage_async_streaming_and_restart_details(sb, tmp_path, monkeypatch):
     """f3: HDF5Storage (through the h5py stand-in of tests/h5py_stub.py -- the image has no h5py) receives the
     device snapshots through the asynchronous copy stream + writer thread and reads back equal to the
@@ -1049,6 +1079,47 @@ def test_c4_mvn_instantiations_replay_vs_oracle(sb, opts, want):
         for k, old in saved:
             _lib.set_option(k, old)
     np.testing.assert_allclose(ll, orc.log_likelihood(problem, theta), rtol=RTOL)
+
+
+def test_c4_prefetching_kernel_equals_plain_kernel_bit_for_bit(sb):
+    """The cp.async-prefetching variant of the static-layout MVNormal kernel (what config C4 launches at its
+    size) against the plain variant that test_c4_mvn_instantiations_replay_vs_oracle pins to the oracle: same
+    replayed normals / uniforms, ragged last tile, particles at and outside the prior bounds -- every output
+    bit-equal, and native-RNG runs equal too."""
+    from smcpy_b200 import _lib, engine
+    problem = configs.mvn_problem(50)
+    g = golden("c4_mvn")
+    n = (1 << 18) + 77
+    rng0 = np.random.default_rng(12)
+    theta = g["params_last"][rng0.integers(0, g["params_last"].shape[0], n)] + rng0.normal(0, 2e-3, (n, 8))
+    theta[:3, 0] = [5.9999, 0.0001, 3.0]                       # next to the uniform(0, 6) bounds
+    cov = orc.weighted_cov(theta, np.full(n, 1.0 / n)) * 0.4
+    out = {}
+    for no_pref in (0, 1):
+        mc, kernel = make_b200(problem, rng=np.random.default_rng(33))
+        kernel.path.phi = 0.7
+        with _lib.option("no_pref", no_pref):
+            out[no_pref] = mc.smc_metropolis(theta, 3, cov)
+            v = _lib.last_mh_variant()
+        assert ("kind=4,dmax=8,tpb=128,ppt=1,exact=1" in v) and (("pref=%d" % (1 - no_pref)) in v) and "rng=1" in v, v
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    assert 0.05 < np.mean(np.any(out[0][0] != theta, axis=1)) < 0.999
+    # native generator, sampler-level state: the two variants leave identical particles
+    res = {}
+    for no_pref in (0, 1):
+        mc, kernel = make_b200(problem, rng=5)
+        st = engine.DeviceState(n, n, 8)
+        st.set_params_host(theta)
+        engine.eval_incoming(st, mc.spec)
+        st.cov.copy_(engine.dev(cov))
+        engine.cholesky(st)
+        with _lib.option("no_pref", no_pref):
+            ratio = engine.mutate(st, mc.spec, 2, engine.make_path(0.7, 0.7, 1.0), engine.PhiloxRNG(9))
+        res[no_pref] = (st.params_host(), st.ll.cpu().numpy().copy(), ratio)
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2]
 
 
 @pytest.mark.parametrize("ppt", [1, 2])
