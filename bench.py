@@ -369,6 +369,13 @@ def north_star_gpu(sb, engine, _lib, torch, dist, rank, world, local, peaks):
                            "alg_bytes_per_particle": float(by.mean() / n_local),
                            "gbps": float(by.sum() / ms.sum() / 1e6), "frac_hbm": float(by.sum() / ms.sum() / 1e6 / hbm),
                            "share_of_wall": share[name]}
+            if name == "reweight":
+                # SURVEY 8(d) counted 48 B/particle for this step (two passes over ll / log_w, log_w and w written);
+                # the fused launch reads ll once and writes nothing when the step resamples
+                kern[label]["survey_contract_bytes_per_particle"] = 48
+                kern[label]["gbps_at_survey_contract"] = float(48.0 * n_local / ms.mean() / 1e6)
+                kern[label]["note"] = ("one cooperative launch; DRAM traffic = the algorithmic bytes (ncu, profiles/r02_kernels.md); "
+                                       "at 67 MB the launch + grid barrier is as long as the stream")
     if "resample" in prof:
         ms = float(np.mean(prof["resample"]))
         b = (16 * C5_D + 48) * n_local
@@ -646,8 +653,8 @@ def run_gpu(args):
                 # FP64 instructions issued (fma, sub, fma per data point) / FMA issue peak
                 "issue_frac": (3.0 * M_DATA * N_PER_GPU / (mh_ms * 1e-3)) / (fp64_peak * 1e12 / 2.0),
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (ncu --set full capture,
-                # profiles/r01_mh_kernels.md: 33.63 MB; the 2^20-particle state is L2 resident)
-                "traffic": 33.63e6, "traffic_source": "profiles/r01_mh_kernels.md (ncu, C2 PPT=4 capture)",
+                # profiles/r02_kernels.md: 33.62 MB read + 0.02 MB written; the 2^20-particle state is L2 resident)
+                "traffic": 33.64e6, "traffic_source": "profiles/r02_kernels.md (ncu --set full, tools/mh_only.py c2)",
                 "avg_launch_ms": mh_ms, "launches_timed": int(mh.size),
                 "timing": "CUDA events on the launch stream around every launch, in one extra pass of the same workload "
                           "right after the timed region (900 event pairs inside it would perturb the headline)",

@@ -1081,6 +1081,36 @@ def test_c4_mvn_instantiations_replay_vs_oracle(sb, opts, want):
     np.testing.assert_allclose(ll, orc.log_likelihood(problem, theta), rtol=RTOL)
 
 
+@pytest.mark.parametrize("model, m, n", [("linear", 2500, 700), ("linear", 1025, 1), ("spring", 1500, 257),
+                                         ("linear", 1, 33), ("spring", 2, 5)])
+def test_metropolis_edge_sizes_replay_vs_oracle(sb, model, m, n):
+    """Edge sizes of the fused Metropolis kernels against the oracle under replay: data vectors longer than the
+    1024-point shared-memory chunk (re-staged chunk by chunk, several chunks and a ragged last one), a single
+    data point, one particle, particle counts that are not a multiple of the tile: 1e-10."""
+    rng0 = np.random.default_rng(m + n)
+    if model == "linear":
+        problem = configs.linear_problem(m, data_seed=21) if m > 1 else configs.linear_problem(2, data_seed=21)
+        if m == 1:
+            problem["model"] = ("linear", problem["model"][1][:1])
+            problem["data"] = problem["data"][:1]
+        theta = np.column_stack([rng0.normal(2.0, 0.2, n), rng0.normal(3.5, 0.3, n)])
+        cov = np.diag([0.01, 0.02])
+    else:
+        problem = configs.spring_problem(m, 2)
+        theta = np.column_stack([rng0.normal(1.67, 0.05, n), rng0.normal(4.62, 0.1, n), rng0.normal(0.5, 0.03, n)])
+        cov = np.diag([0.002, 0.006, 0.0008])
+    K, phi = 3, 0.15
+    accepts = []
+    o_theta, o_ll = orc.smc_metropolis(problem, theta, K, cov, phi, np.random.default_rng(3), trace=accepts)
+    mc, kernel = make_b200(problem, rng=np.random.default_rng(3))
+    kernel.path.phi = phi
+    g_theta, g_ll = mc.smc_metropolis(theta, K, cov)
+    assert g_theta.shape == (n, theta.shape[1]) and g_ll.shape == (n, 1)
+    np.testing.assert_allclose(g_theta, o_theta, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(g_ll, o_ll, rtol=RTOL)
+    np.testing.assert_allclose(mc.evaluate_log_likelihood(theta), orc.log_likelihood(problem, theta), rtol=RTOL)
+
+
 def test_c4_prefetching_kernel_equals_plain_kernel_bit_for_bit(sb):
     """The cp.async-prefetching variant of the static-layout MVNormal kernel (what config C4 launches at its
     size) against the plain variant that test_c4_mvn_instantiations_replay_vs_oracle pins to the oracle: same
