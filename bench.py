@@ -639,7 +639,11 @@ def run_gpu(args):
     d = 2
     alg_bytes = (16 * d + 32) * N_PER_GPU                       # 16d+32 B per particle-step
     ach = alg_bytes / (mh_ms * 1e-3) / 1e9
-    flops_per_unit = 5.0 * M_DATA + 4 * d * d                   # fma + sub + fma per data point
+    # FP64 work per particle-step.  The kernel accumulates the residuals about the data means (two FMAs per data
+    # point: 4 flop); SURVEY 8(d) counts the direct form (fma, sub, fma: 5 flop per point).  The roofline fraction
+    # is computed on the flops the kernel EXECUTES; the rate on the survey's count is given beside it.
+    flops_per_unit = 4.0 * M_DATA + 4 * d * d + 6
+    flops_survey = 5.0 * M_DATA + 4 * d * d
     fp64_ach = flops_per_unit * N_PER_GPU / (mh_ms * 1e-3) / 1e12
     probes = fp64_probes(_lib, torch)
     fp64_peak = max(probes.values())
@@ -650,11 +654,15 @@ def run_gpu(args):
                                "(%.2f TFLOP/s); MEASURED_PEAKS.json has no FP64 figure"
                                % (probes["smcb_fp64_probe"], probes["smcb_dmma_probe"]),
                 "flops_per_particle_step": flops_per_unit,
-                # FP64 instructions issued (fma, sub, fma per data point) / FMA issue peak
-                "issue_frac": (3.0 * M_DATA * N_PER_GPU / (mh_ms * 1e-3)) / (fp64_peak * 1e12 / 2.0),
+                "flops_note": "executed: residuals accumulated about the data means, sum (a u_j - v_j)^2 + M (a xbar + b - ybar)^2, "
+                              "two FMAs per data point; the direct form of SURVEY 8(d) is 5 flop per point",
+                "survey_flops_per_particle_step": flops_survey,
+                "tflops_at_survey_count": flops_survey * N_PER_GPU / (mh_ms * 1e-3) / 1e12,
+                # FP64 instructions issued (two FMAs per data point) / FMA issue peak
+                "issue_frac": (2.0 * M_DATA * N_PER_GPU / (mh_ms * 1e-3)) / (fp64_peak * 1e12 / 2.0),
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (ncu --set full capture,
-                # profiles/r02_kernels.md: 33.62 MB read + 0.02 MB written; the 2^20-particle state is L2 resident)
-                "traffic": 33.64e6, "traffic_source": "profiles/r02_kernels.md (ncu --set full, tools/mh_only.py c2)",
+                # profiles/r02_kernels.md: 33.62 MB read + 0.16 MB written; the 2^20-particle state is L2 resident)
+                "traffic": 33.78e6, "traffic_source": "profiles/r02_kernels.md (ncu --set full, tools/mh_only.py c2)",
                 "avg_launch_ms": mh_ms, "launches_timed": int(mh.size),
                 "timing": "CUDA events on the launch stream around every launch, in one extra pass of the same workload "
                           "right after the timed region (900 event pairs inside it would perturb the headline)",

@@ -50,7 +50,7 @@ class Problem(C.Structure):
                 ("proposal", ProposalCol * MAX_PARAMS), ("n_segments", C.c_int32),
                 ("seg_len", C.c_int32 * MAX_SEGMENTS), ("seg_sigma_col", C.c_int32 * MAX_SEGMENTS),
                 ("pad2", C.c_int32), ("seg_sigma", C.c_double * MAX_SEGMENTS), ("mvn_stats", C.c_void_p),
-                ("iw_chol", (C.c_double * 6) * 2)]
+                ("iw_chol", (C.c_double * 6) * 2), ("lin_centered", C.c_void_p)]
 
 
 class Path(C.Structure):
@@ -91,6 +91,7 @@ SIGNATURES = {
     "smcb_soa_to_aos": [_P, _P, _I64, _I32, _I64, _P],
     "smcb_fp64_probe": [_P, _I32, _I32, _P],
     "smcb_mvn_scatter": [_P, _I32, _I32, _P, _P],
+    "smcb_linear_center": [_P, _P, _I32, _P, _P],
     "smcb_dmma_probe": [_P, _I32, _I32, _P],
     "smcb_fill_f64": [_P, _I64, _D, _P],
     "smcb_reweight": [_I64, _P, _P, _P, _P, _I64, _PP(Path), _P, _P, _P, _P, _P],

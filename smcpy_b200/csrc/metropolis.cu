@@ -269,12 +269,18 @@ __device__ __forceinline__ double normal_ll(double ssq, double sigma, int m) {
     return term1 + term2;
 }
 
-template <int KIND>
+template <int KIND, bool CENTERED = false>
 __device__ __forceinline__ void stage_data(const MhArgs& a, double* sdata, int base, int cnt) {
     if (KIND == K_LINEAR_NORMAL) {
         double2* sxy = reinterpret_cast<double2*>(sdata);
-        for (int j = threadIdx.x; j < cnt; j += blockDim.x)
-            sxy[j] = make_double2(a.prob.xgrid[base + j], a.prob.data[base + j]);
+        if (CENTERED) {
+            // (x_j - xbar, -(y_j - ybar)) pairs prepared once per problem by smcb_linear_center
+            const double2* cen = reinterpret_cast<const double2*>(a.prob.lin_centered + 2);
+            for (int j = threadIdx.x; j < cnt; j += blockDim.x) sxy[j] = cen[base + j];
+        } else {
+            for (int j = threadIdx.x; j < cnt; j += blockDim.x)
+                sxy[j] = make_double2(a.prob.xgrid[base + j], a.prob.data[base + j]);
+        }
     } else if (is_mvn(KIND)) {
         // [0..2] mean of the snapshots, [3..11] their scatter matrix (3 x 3, zero padded), [12..14] X
         const int F = a.prob.n_data;
@@ -291,12 +297,19 @@ __device__ __forceinline__ void stage_data(const MhArgs& a, double* sdata, int b
 }
 
 // Linear model + Normal likelihood for PPT particles per thread: every staged data point
-// (one broadcast LDS.128) feeds 3*PPT FP64 instructions, which keeps the shared-memory pipe
+// (one broadcast LDS.128) feeds 2*PPT FP64 instructions, which keeps the shared-memory pipe
 // off the critical path (profiles/r01_mh_kernels.md).
+// The residuals are accumulated about the data means: with u_j = x_j - xbar, v_j = y_j - ybar (sum u = sum v = 0)
+//     sum_j (a x_j + b - y_j)^2 = sum_j (a u_j - v_j)^2 + M (a xbar + b - ybar)^2,
+// the cross term vanishing identically.  The model is still evaluated at every data point and the squared
+// residuals are still reduced over the whole vector, but the intercept is applied once instead of M times:
+// two FP64 instructions per point (fma, fma) instead of three (fma, sub, fma), and no cancellation between
+// b and y_j.  Within a few ulp of the reference's direct form (smcpy/log_likelihoods.py:42-49); pinned at
+// 1e-10 by the replay tests.
 template <int DMAX, int PPT>
 __device__ __forceinline__ void ll_linear_normal(const MhArgs& a, const double (&th)[PPT][DMAX], bool run_any,
                                                  bool resident, double* sdata, double (&ll)[PPT]) {
-    const double2* sxy = reinterpret_cast<const double2*>(sdata);
+    const double2* sxy = reinterpret_cast<const double2*>(sdata);      // (u_j, -v_j)
     const int m = a.prob.n_data;
     double s0[PPT], s1[PPT];
 #pragma unroll
@@ -305,7 +318,7 @@ __device__ __forceinline__ void ll_linear_normal(const MhArgs& a, const double (
         const int cnt = (m - base < kChunk) ? (m - base) : kChunk;
         if (!resident) {
             __syncthreads();
-            stage_data<K_LINEAR_NORMAL>(a, sdata, base, cnt);
+            stage_data<K_LINEAR_NORMAL, true>(a, sdata, base, cnt);
             __syncthreads();
         }
         if (run_any) {
@@ -315,8 +328,8 @@ __device__ __forceinline__ void ll_linear_normal(const MhArgs& a, const double (
                 const double2 p0 = sxy[j], p1 = sxy[j + 1];
 #pragma unroll
                 for (int p = 0; p < PPT; ++p) {
-                    const double d0 = fma(th[p][0], p0.x, th[p][1]) - p0.y;
-                    const double d1 = fma(th[p][0], p1.x, th[p][1]) - p1.y;
+                    const double d0 = fma(th[p][0], p0.x, p0.y);
+                    const double d1 = fma(th[p][0], p1.x, p1.y);
                     s0[p] = fma(d0, d0, s0[p]);
                     s1[p] = fma(d1, d1, s1[p]);
                 }
@@ -325,16 +338,18 @@ __device__ __forceinline__ void ll_linear_normal(const MhArgs& a, const double (
                 const double2 q = sxy[j];
 #pragma unroll
                 for (int p = 0; p < PPT; ++p) {
-                    const double dd = fma(th[p][0], q.x, th[p][1]) - q.y;
+                    const double dd = fma(th[p][0], q.x, q.y);
                     s0[p] = fma(dd, dd, s0[p]);
                 }
             }
         }
     }
+    const double xbar = a.prob.lin_centered[0], ybar = a.prob.lin_centered[1];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
         const double sigma = a.prob.sigma_is_param ? th[p][DMAX > 2 ? 2 : 0] : a.prob.sigma;
-        ll[p] = normal_ll(s0[p] + s1[p], sigma, m);
+        const double c = fma(th[p][0], xbar, th[p][1]) - ybar;
+        ll[p] = normal_ll(fma((double)m * c, c, s0[p] + s1[p]), sigma, m);
     }
 }
 
@@ -606,7 +621,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             sh_scale = (a.x.world > 1) ? cov_scale_sqrt_xchg(a.x, a.step, a.n_global)
                                        : cov_scale_sqrt(a.accept_counts, a.step, a.n_global);
     }
-    if ((MODE == 0 || MODE == 1) && resident) stage_data<KIND>(a, sdata, 0, a.prob.n_data);
+    if ((MODE == 0 || MODE == 1) && resident) stage_data<KIND, !MULTI>(a, sdata, 0, a.prob.n_data);
     __syncthreads();
     const double sc = (MODE == 1 || MODE == 2) ? sh_scale : 0.0;
 
@@ -1157,6 +1172,37 @@ __global__ void __launch_bounds__(256) sample_priors_kernel(ColPriors cp, IwArgs
     }
 }
 
+// centred data of the linear model + Normal likelihood: out[0] = xbar, out[1] = ybar (fixed-order tree sums),
+// out[2 + 2 j] = x_j - xbar, out[3 + 2 j] = -(y_j - ybar)
+__global__ void __launch_bounds__(256) linear_center_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                            int m, double* out) {
+    __shared__ double sx[256], sy[256];
+    double ax = 0.0, ay = 0.0;
+    for (int j = threadIdx.x; j < m; j += 256) {
+        ax += x[j];
+        ay += y[j];
+    }
+    sx[threadIdx.x] = ax;
+    sy[threadIdx.x] = ay;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sx[threadIdx.x] += sx[threadIdx.x + o];
+            sy[threadIdx.x] += sy[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    const double xbar = sx[0] / (double)m, ybar = sy[0] / (double)m;
+    if (threadIdx.x == 0) {
+        out[0] = xbar;
+        out[1] = ybar;
+    }
+    for (int j = threadIdx.x; j < m; j += 256) {
+        out[2 + 2 * j] = x[j] - xbar;
+        out[3 + 2 * j] = -(y[j] - ybar);
+    }
+}
+
 // snapshot mean and scatter matrix of the MVNormal data: one thread per output entry, sequential sums
 // over the snapshots (deterministic; S is small)
 __global__ void mvn_scatter_kernel(const double* __restrict__ data, int S, int F, double* out) {
@@ -1450,6 +1496,7 @@ static int validate_problem(const smcb_problem_t* p, ColPriors* cp) {
         const int extra = p->sigma_is_param ? 1 : 0;
         if (p->n_model_params + extra != p->n_params) { set_error("Normal: n_model_params + sigma != n_params"); return SMCB_ERR_ARG; }
         if (p->model_id == SMCB_MODEL_LINEAR && (!p->xgrid || p->n_model_params != 2)) { set_error("linear model needs xgrid and 2 params"); return SMCB_ERR_ARG; }
+        if (p->model_id == SMCB_MODEL_LINEAR && p->loglike_id == SMCB_LL_NORMAL && !p->lin_centered) { set_error("linear model + Normal: lin_centered is NULL (fill it with smcb_linear_center)"); return SMCB_ERR_ARG; }
         if (p->model_id == SMCB_MODEL_SPRING_MASS && (p->n_model_params != 2 || p->model_args[3] < 1)) { set_error("spring-mass model needs 2 params and nsub >= 1"); return SMCB_ERR_ARG; }
         if (p->model_id == SMCB_MODEL_IDENTITY && p->n_model_params != p->n_data) { set_error("identity model needs n_data == n_model_params"); return SMCB_ERR_ARG; }
         if (p->model_id == SMCB_MODEL_IDENTITY && p->sigma_is_param) { set_error("identity model: fused kernels need a fixed sigma"); return SMCB_ERR_UNSUPPORTED; }
@@ -1486,6 +1533,15 @@ static int validate_problem(const smcb_problem_t* p, ColPriors* cp) {
 }  // namespace smcb
 
 using namespace smcb;
+
+extern "C" int smcb_linear_center(const double* x, const double* y, int32_t m, double* out, void* stream) {
+    if (!x || !y || !out || m < 1) {
+        set_error("smcb_linear_center: bad argument");
+        return SMCB_ERR_ARG;
+    }
+    linear_center_kernel<<<1, 256, 0, as_stream(stream)>>>(x, y, m, out);
+    return check_launch("linear_center_kernel");
+}
 
 extern "C" int smcb_mvn_scatter(const double* data, int32_t n_snapshots, int32_t n_features, double* stats_out,
                                 void* stream) {

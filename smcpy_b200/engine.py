@@ -407,6 +407,12 @@ class ProblemSpec:
                     raise ValueError("linear model grid and data length differ")
                 self._x_dev = dev(model.x)
                 c.xgrid = self._x_dev.data_ptr()
+                if kind == "normal":
+                    # data centred about its means: what the linear + Normal kernels stage (smcb_linear_center)
+                    self._lin_centered = torch.empty(2 + 2 * c.n_data, dtype=torch.float64, device=rt.device)
+                    call("smcb_linear_center", ptr(self._x_dev), ptr(self._data_dev), c.n_data, ptr(self._lin_centered),
+                         stream_ptr())
+                    c.lin_centered = self._lin_centered.data_ptr()
             elif model.model_id == _lib.MODEL_SPRING_MASS:
                 if model.n_out != c.n_data:
                     raise ValueError("spring-mass output count and data length differ")

@@ -72,10 +72,8 @@ class Updater:
     def update(self, particles):
         st = particles.to_state()
         if not particles._lp_valid:
-            import ctypes as C
-            from ._lib import call, ptr, stream_ptr
-            call("smcb_log_priors", C.byref(self._mcmc_kernel.spec.c), ptr(st.cols), st.n, st.n, ptr(st.lp),
-                 None, stream_ptr())
+            from .callable_route import log_priors_into         # device prior table + host-evaluated priors
+            log_priors_into(st, self._mcmc_kernel.spec, st.params, st.lp)
         self.update_state(st)
         attrs = {"total_unnorm_log_weight": st.total_unnorm_log_weight}
         return Particles.from_state(st, particles.param_names, attrs, clone=False)

@@ -43,7 +43,7 @@ def test_struct_layout_matches_header(tmp_path):
                                                 "dst_peer", "dst_stride", "idx_out", "n_unique_out"]),
                "smcb_problem_t": (L.Problem, ["model_id", "n_priors", "sigma", "model_args", "data", "xgrid", "cov_fixed",
                                               "cov_param_col", "priors", "has_proposal", "proposal", "n_segments",
-                                              "seg_len", "seg_sigma_col", "seg_sigma", "mvn_stats", "iw_chol"])}
+                                              "seg_len", "seg_sigma_col", "seg_sigma", "mvn_stats", "iw_chol", "lin_centered"])}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "smcb200.h"', "int main(void) {"]
     for cname, (_, fields) in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
