@@ -126,6 +126,31 @@ __device__ __forceinline__ double cov_scale_sqrt_xchg(const smcb_xchg_t& x, int 
     return sqrt(s);
 }
 
+// The same scale computed by the whole block: thread k classifies step k (the accept-count loads of all
+// previous steps are in flight together instead of one dependent load after another on thread 0: up to 19 x 0.6 us
+// at the 20th step of a mutate call), the two class counts are reduced with barrier counts, and every thread
+// applies them.  s = 2^up / 5^down with one rounding per division: multiplying by 2 is exact, so the order of the
+// operations does not matter and the result is bit-identical to the sequential rule above.
+// Must be called by every thread of the block.
+template <int TPB>
+__device__ __forceinline__ double block_cov_scale_sqrt(const MhArgs& a) {
+    int up = 0, down = 0;
+    for (int base = 0; base < a.step; base += TPB) {
+        const int k = base + (int)threadIdx.x;
+        bool u = false, dn = false;
+        if (k < a.step) {
+            const double acc = (a.x.world > 1) ? xchg_global_count(a.x, k, k == a.step - 1) : (double)a.accept_counts[k];
+            dn = acc < a.n_global * 0.3;
+            u = acc > a.n_global * 0.7;
+        }
+        up += __syncthreads_count(u);
+        down += __syncthreads_count(dn);
+    }
+    double s = 1.0;
+    for (int i = 0; i < down && s > 0.0; ++i) s = s * 1 / 5;
+    return sqrt(scalbn(s, up));
+}
+
 // ---- priors -----------------------------------------------------------------------------------
 __device__ __noinline__ double gen_uniform53(uint32_t k0, uint32_t k1, uint64_t pid, uint32_t call, uint32_t stream) {
     const uint4 r = philox_s(k0, k1, pid, call, stream);
@@ -275,8 +300,16 @@ __device__ __forceinline__ void stage_data(const MhArgs& a, double* sdata, int b
         double2* sxy = reinterpret_cast<double2*>(sdata);
         if (CENTERED) {
             // (x_j - xbar, -(y_j - ybar)) pairs prepared once per problem by smcb_linear_center
-            const double2* cen = reinterpret_cast<const double2*>(a.prob.lin_centered + 2);
-            for (int j = threadIdx.x; j < cnt; j += blockDim.x) sxy[j] = cen[base + j];
+            const double2* cen = reinterpret_cast<const double2*>(a.prob.lin_centered + 2) + base;
+            const int bd = blockDim.x;
+            for (int j = threadIdx.x; j < cnt; j += 4 * bd) {       // four independent loads in flight per thread
+                double2 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = (j + k * bd < cnt) ? cen[j + k * bd] : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (j + k * bd < cnt) sxy[j + k * bd] = v[k];
+            }
         } else {
             for (int j = threadIdx.x; j < cnt; j += blockDim.x)
                 sxy[j] = make_double2(a.prob.xgrid[base + j], a.prob.data[base + j]);
@@ -500,6 +533,9 @@ __device__ __forceinline__ double ll_linear_mvn(const MhArgs& a, const double (&
 
 // register budget per thread -> minimum resident blocks per SM (keeps ptxas from trading
 // occupancy for unrolling: profiles/r01_mh_kernels.md)
+#ifndef SMCB_PPT4_REGS
+#define SMCB_PPT4_REGS 84
+#endif
 __host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt, bool tma = false, int kind = -1) {
 #ifdef SMCB_TMA_REGS
     const int tma_regs = SMCB_TMA_REGS;
@@ -509,7 +545,7 @@ __host__ __device__ constexpr int mh_min_blocks(int dmax, int tpb, int ppt, bool
     // MVNormal (3 x 3 factorisation + solves) and two interleaved RK4 chains need ~80 registers to stay
     // out of local memory; both are FP64-bound, so 6 blocks of 128 threads per SM are plenty
     const bool wide = (is_mvn(kind) && dmax >= 8) || (kind == K_SPRING_NORMAL && ppt >= 2);
-    const int regs = dmax >= 32 ? (tma ? tma_regs : 128) : (dmax >= 16 ? 96 : (wide ? 80 : (ppt >= 4 ? 84 : 64)));
+    const int regs = dmax >= 32 ? (tma ? tma_regs : 128) : (dmax >= 16 ? 96 : (wide ? 80 : (ppt >= 4 ? SMCB_PPT4_REGS : 64)));
     return 65536 / (tpb * regs) > 0 ? 65536 / (tpb * regs) : 1;
 }
 
@@ -587,7 +623,6 @@ template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA =
 __global__ void __launch_bounds__(TPB, mh_min_blocks(DMAX, TPB, PPT, TMA, KIND))
 mh_kernel(const __grid_constant__ MhArgs a) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double sh_scale;
     __shared__ __align__(8) uint64_t mbar, mbar_empty;
     const int d = EXACT ? DMAX : a.prob.n_params;
     // Cholesky factor transposed and zero-padded to DMAX: sLt[j * DMAX + r] = L[r][j], so column j
@@ -617,13 +652,11 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                 sB[e] = (r < d && j <= r) ? (float)a.chol[r * d + j] : 0.0f;
             }
         }
-        if (threadIdx.x == 0)
-            sh_scale = (a.x.world > 1) ? cov_scale_sqrt_xchg(a.x, a.step, a.n_global)
-                                       : cov_scale_sqrt(a.accept_counts, a.step, a.n_global);
     }
     if ((MODE == 0 || MODE == 1) && resident) stage_data<KIND, !MULTI>(a, sdata, 0, a.prob.n_data);
+    double sc = 0.0;
+    if (MODE == 1 || MODE == 2) sc = block_cov_scale_sqrt<TPB>(a);
     __syncthreads();
-    const double sc = (MODE == 1 || MODE == 2) ? sh_scale : 0.0;
 
     const int64_t per_tile = (int64_t)TPB * PPT;
     const int64_t n_tiles = (a.n + per_tile - 1) / per_tile;
@@ -667,6 +700,8 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         cp_async_commit();
     };
     if (PREF && (int64_t)blockIdx.x < n_tiles) pref_issue(blockIdx.x);
+    // (fetching the next tile at the START of the current one, to hide the atomic's latency, was measured 15 %
+    // slower for C2 and is not done)
     __shared__ long long sh_tile;
     for (int64_t tile = blockIdx.x;; tile += gridDim.x) {
         if (DYN) {

@@ -19,6 +19,8 @@ elif cfg == "c4":
     problem = configs.mvn_problem(50); n = 1 << 22
 if len(sys.argv) > 2:
     n = 1 << int(sys.argv[2])
+if os.environ.get("SMCB_N"):
+    n = int(os.environ["SMCB_N"])
 mcmc, kernel = make_b200(problem, rng=3)
 if cfg == "c4":
     init = configs.mvn_init_params(4096, 1)
