@@ -1681,6 +1681,25 @@ extern "C" int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* 
     return dispatch<1>(a, as_stream(stream));
 }
 
+extern "C" int smcb_mh_steps(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride,
+                             int64_t n, int64_t n_global, double* ll, double* lp, double* lq, uint8_t* moved,
+                             const double* chol, int64_t* accept_counts, int32_t first_step, int32_t n_steps,
+                             const smcb_rng_t* rng, int32_t* flags, const smcb_xchg_t* x, void* stream) {
+    SMCB_REQUIRE(rng && n_steps >= 0 && first_step >= 0 && first_step + n_steps <= SMCB_MAX_MCMC_STEPS, "bad step range");
+    SMCB_REQUIRE(rng->mode == 0, "smcb_mh_steps: native generator only (replay tapes are per step)");
+    smcb_rng_t r = *rng;
+    for (int32_t k = 0; k < n_steps; ++k) {
+        r.stream = rng->stream + (uint64_t)k;
+        const int rc = (x && x->world > 1)
+                           ? smcb_mh_step_xchg(prob, path, params, stride, n, n_global, ll, lp, lq, moved, chol, accept_counts,
+                                               first_step + k, &r, flags, x, stream)
+                           : smcb_mh_step(prob, path, params, stride, n, n_global, ll, lp, lq, moved, chol, accept_counts,
+                                          first_step + k, &r, flags, stream);
+        if (rc) return rc;
+    }
+    return SMCB_OK;
+}
+
 extern "C" int smcb_mh_propose(const smcb_problem_t* prob, const double* params, int64_t stride, int64_t n,
                                int64_t n_global, const double* chol, const int64_t* accept_counts, int32_t step,
                                const smcb_rng_t* rng, double* new_params, double* new_lp, void* stream) {

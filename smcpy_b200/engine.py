@@ -1034,7 +1034,18 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False, lazy_chol=Fal
     lq = ptr(st.lq) if (spec.fused and spec.has_device_proposal) else None
     xchg = PeerExchange.get() if (world > 1 and spec.fused) else None
     xs = xchg.next_gen() if xchg is not None else None
-    for k in range(num_samples):
+    if spec.fused and not host_rng and PROFILE is None and num_samples > 0:
+        # native generator: the K launches are enqueued by ONE library call (smcb_mh_steps); per-step calls are kept
+        # for the replay tapes and for per-launch timing
+        r.mode, r.seed, r.stream = 0, rng.seed, rng._stream + 1
+        rng._stream += num_samples
+        call("smcb_mh_steps", C.byref(spec.c), C.byref(path), ptr(st.cols), st.n, st.n, st.n_global,
+             ptr(st.ll), ptr(st.lp), lq, ptr(st.moved), ptr(st.chol), ptr(st.accept_counts), 0, num_samples,
+             C.byref(r), ptr(st.flags), C.byref(xs) if xs is not None else None, s, launches=num_samples)
+        num_steps_left = 0
+    else:
+        num_steps_left = num_samples
+    for k in range(num_steps_left):
         if host_rng:
             z = dev(rng.normal(0, 1, (st.n, st.d)))
             u = dev(rng.uniform(0, 1, (st.n, 1)).reshape(-1))
