@@ -359,28 +359,45 @@ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
     const uint64_t x = ((uint64_t)hi << 32) | lo;
     return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
-// two standard normals from two 32-bit words: Box-Muller in fp32 with the hardware
-// approximations (lg2 / sin / cos MUFU).  Proposals only need a symmetric, well-distributed z
-// (the Metropolis ratio does not involve the proposal density) -- see DESIGN.md "RNG".
+// two standard normals from two 32-bit words: Box-Muller in fp32 on the special-function unit
+// (MUFU.LG2 / SQRT / SIN / COS through the .approx.ftz PTX forms: the library wrappers __log2f, rsqrtf,
+// __frsqrt_rn add denormal scaling and Newton refinement -- 34 SASS instructions per pair, 13 here; the
+// arguments are never denormal).  Proposals only need a symmetric, well-distributed z (the Metropolis
+// ratio does not involve the proposal density) -- see DESIGN.md "RNG".
+__device__ __forceinline__ float mufu_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_sin(float x) {
+    float y;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_cos(float x) {
+    float y;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void normal_pair_f(uint32_t w0, uint32_t w1, float& z0, float& z1) {
-    const float u1 = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
+    const float v = (float)(w0 >> 8) + 0.5f;                       // 2^24 u1, u1 in (0, 1]: 24 bits
     const float th = ((float)(int32_t)w1) * (3.14159265358979f / 2147483648.0f);   // [-pi, pi)
-    const float x = -1.38629436111989f * __log2f(u1);       // -2 ln(u1) > 0
-    const float r = x * __frsqrt_rn(fmaxf(x, 1e-30f));      // u1 can round to 1.0f: x = 0 must give r = 0, not 0 * inf
-    float s, c;
-    __sincosf(th, &s, &c);
-    z0 = r * c;
-    z1 = r * s;
+    // -2 ln u1 = 2 ln 2 (24 - lg2 v); v can round to 2^24 and the approximation can overshoot: clamp at 0
+    const float x = fmaxf(fmaf(mufu_lg2(v), -1.38629436111989f, 24.0f * 1.38629436111989f), 0.0f);
+    const float r = mufu_sqrt(x);
+    z0 = r * mufu_cos(th);
+    z1 = r * mufu_sin(th);
 }
 __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, double& z0, double& z1) {
-    const float u1 = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
-    const float th = ((float)(int32_t)w1) * (3.14159265358979f / 2147483648.0f);   // [-pi, pi)
-    const float x = -2.0f * __logf(u1);       // >= 0 (u1 can round to 1.0f)
-    const float r = x * rsqrtf(fmaxf(x, 1e-30f));   // x = 0 gives r = 0, not 0 * inf
-    float s, c;
-    __sincosf(th, &s, &c);
-    z0 = (double)(r * c);
-    z1 = (double)(r * s);
+    float a, b;
+    normal_pair_f(w0, w1, a, b);
+    z0 = (double)a;
+    z1 = (double)b;
 }
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a): 1-D cp.async.bulk global -> shared ----------------
