@@ -156,17 +156,22 @@ typedef struct smcb_rng {
 } smcb_rng_t;
 
 /* cross-GPU accept-count exchange fused into the Metropolis kernel (multi-GPU only).  Each rank
- * owns a symmetric `slots` buffer of SMCB_MAX_MCMC_STEPS x SMCB_MAX_RANKS uint64 mapped by
- * every peer.  The last block of step k stores (gen << 32 | local count) into slot [k][rank] of
- * EVERY rank over NVLink; the prologue of step k+1 waits until all `world` slots of step k carry
- * `gen` and sums them -- no separate collective launch.  `gen` increases with every mutate call. */
+ * owns a symmetric `slots` buffer of smcb_mh_xchg_slot_words() uint64 (two tables of SMCB_MAX_MCMC_STEPS x
+ * SMCB_MAX_RANKS words: FINAL counts, then EARLY counts) mapped by every peer.  The last block of step k
+ * stores (gen << 32 | local count) into final slot [k][rank] of EVERY rank over NVLink; the dynamic-tile
+ * kernels also store a running count into early slot [k][rank] once all but 15 % / world of N are counted.
+ * The prologue of step k+1 reads the `world` slots of step k in its own memory and applies the
+ * covariance-scale rule (vector_mcmc.py:55-60) as soon as the (bounds on the) global count leave one
+ * answer -- no separate collective launch, and usually no wait for the slowest rank's kernel to end.
+ * `gen` increases with every mutate call. */
 #define SMCB_MAX_RANKS 8
 typedef struct smcb_xchg {
     int32_t world, rank;
     uint64_t gen;
     uint64_t* peer_slots[SMCB_MAX_RANKS];   /* device pointers to each rank's slots buffer */
-    int64_t* global_counts;                 /* device, SMCB_MAX_MCMC_STEPS: summed counts (local cache) */
-    uint32_t* ticket;                       /* device, zero-initialised block ticket */
+    int64_t* global_counts;                 /* device, SMCB_MAX_MCMC_STEPS: per step a count with the scale decision of the
+                                             * global count (the global count itself when every final slot had arrived) */
+    uint32_t* ticket;                       /* device, 2 zero-initialised words: block ticket, counted particles */
 } smcb_xchg_t;
 
 /* ---- library --------------------------------------------------------------------- */
@@ -450,7 +455,8 @@ int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path, double* pa
                  const double* chol, int64_t* accept_counts, int32_t step, const smcb_rng_t* rng,
                  int32_t* flags, void* stream);
 /* same step with the cross-GPU accept-count exchange fused in (x->world > 1); accept_counts
- * then holds the LOCAL counts, x->global_counts the global ones. */
+ * then holds the LOCAL counts, x->global_counts decision-equivalent global ones (see smcb_xchg_t). */
+int smcb_mh_xchg_slot_words(void);
 int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride,
                       int64_t n, int64_t n_global, double* ll, double* lp, double* lq, uint8_t* moved,
                       const double* chol, int64_t* accept_counts, int32_t step, const smcb_rng_t* rng,

@@ -140,6 +140,7 @@ SIGNATURES = {
     "smcb_reweight_fused": [_I64, _P, _P, _D, _P, _P, _I64, _PP(Path), _D, _P, _P, _P, _P, _PP(Xchg), _P],
     "smcb_ess_search": [_I64, _P, _P, _P, _D, _D, _D, _D, _I64, _D, _P, _P, _PP(Xchg), _P],
     "smcb_xchg_slot_words": [],
+    "smcb_mh_xchg_slot_words": [],
     "smcb_test_search_host": [_P, _I64, _D, _D, _D, _I32, _P, _P, _I32],
     "smcb_resample_exponential_sums": [_I64, _I64, _I64, _U64, _U64, _P, _P, _P, _P],
     "smcb_cdf_scan_weights": [_I64, _P, _P, _D, _P, _P, _I64, _PP(Path), _P, _P, _P, _P, _P],
@@ -200,7 +201,7 @@ class _LazyLib:
 lib = _LazyLib()
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
 LAUNCHES = {"smcb_reweight": 2, "smcb_cdf_scan": 2, "smcb_cdf_scan_weights": 2, "smcb_resample_exponential_sums": 2,
-            "smcb_resample_fused": 3, "smcb_xchg_slot_words": 0, "smcb_xchg_big_slot_words": 0, "smcb_xchg_max_vals": 0, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
+            "smcb_resample_fused": 3, "smcb_xchg_slot_words": 0, "smcb_mh_xchg_slot_words": 0, "smcb_xchg_big_slot_words": 0, "smcb_xchg_max_vals": 0, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
             "smcb_weighted_sums1": 2, "smcb_weighted_moments_shifted": 3, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0,
             "smcb_ess_bisect_xchg_slot_words": 0}
 launch_count = 0

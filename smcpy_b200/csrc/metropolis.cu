@@ -99,33 +99,84 @@ __device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p
 __device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// global accept count of step j: local cache if already summed, else wait for every rank's slot
-__device__ __forceinline__ double xchg_global_count(const smcb_xchg_t& x, int j, bool latest) {
+// Slot buffer of a rank (symmetric memory, smcb_mh_xchg_slot_words() words): FINAL counts [step][rank], then
+// EARLY counts [step][rank].  A word is (generation << 32 | count).
+//   final: the rank's accept count of the step, stored by the last block of its launch;
+//   early: a LOWER BOUND of it, stored (dynamic-tile kernels) as soon as all but `slack` of the rank's particles
+//          are counted, so count <= final <= count + slack.
+// The covariance-scale rule (vector_mcmc.py:55-60) only asks whether the GLOBAL count is below 0.3 N, above 0.7 N
+// or in between.  With every rank's count known to within its slack that question usually has ONE answer long
+// before the slowest rank finishes the step (C2: ~45 % acceptance, decided at 85 % progress), so the next step
+// does not wait for the peers' kernels to end plus an NVLink round trip: the ranks run the K steps of a mutation
+// free of each other and meet again at the next reweight.  When the bounds straddle a threshold the reader keeps
+// polling until the finals arrive -- the decision is always the one the exact count gives.
+constexpr unsigned long long kCountMask = 0xffffffffull;
+__device__ __forceinline__ unsigned long long xchg_early_slack(double n_global, int world) {
+    return (unsigned long long)(0.15 * n_global / (double)world);
+}
+// a count with the same scale decision as the global accept count of step j (the exact count whenever every
+// rank's final slot had arrived): local cache for earlier steps, else from the peers' slots
+__device__ __forceinline__ double xchg_global_count(const smcb_xchg_t& x, int j, bool latest, double n_global) {
     if (!latest) return (double)x.global_counts[j];
-    const unsigned long long* mine =
+    const unsigned long long* fin =
         reinterpret_cast<const unsigned long long*>(x.peer_slots[x.rank]) + (size_t)j * SMCB_MAX_RANKS;
-    unsigned long long total = 0;
-    for (int r = 0; r < x.world; ++r) {
-        unsigned long long v = ld_sys(mine + r);
-        while ((v >> 32) != x.gen) {
-            __nanosleep(64);
-            v = ld_sys(mine + r);
+    const unsigned long long* early = fin + (size_t)SMCB_MAX_MCMC_STEPS * SMCB_MAX_RANKS;
+    const unsigned long long slack = xchg_early_slack(n_global, x.world);
+    unsigned long long rep = 0;
+    for (;;) {
+        unsigned long long lo = 0, hi = 0;
+        bool ready = true, exact = true;
+        for (int r = 0; r < x.world; ++r) {
+            const unsigned long long v = ld_sys(fin + r);
+            if ((v >> 32) == x.gen) {
+                lo += v & kCountMask;
+                hi += v & kCountMask;
+                continue;
+            }
+            const unsigned long long e = ld_sys(early + r);
+            if ((e >> 32) != x.gen) {
+                ready = false;
+                break;
+            }
+            lo += e & kCountMask;
+            hi += (e & kCountMask) + slack;
+            exact = false;
         }
-        total += v & 0xffffffffull;
+        if (ready) {
+            const double dlo = (double)lo, dhi = (double)hi;
+            if (exact || dlo > n_global * 0.7 || (dlo >= n_global * 0.3 && dhi <= n_global * 0.7)) {
+                rep = lo;
+                break;
+            }
+            if (dhi < n_global * 0.3) {
+                rep = hi;
+                break;
+            }
+        }
+        __nanosleep(64);
     }
-    x.global_counts[j] = (long long)total;     // every block writes the same value
-    return (double)total;
+    x.global_counts[j] = (long long)rep;     // blocks may store different, decision-equivalent values
+    return (double)rep;
 }
-__device__ __forceinline__ double cov_scale_sqrt_xchg(const smcb_xchg_t& x, int step, double n_global) {
-    double s = 1.0;
-    for (int k = 0; k < step; ++k) {
-        const double acc = xchg_global_count(x, k, k == step - 1);
-        if (acc < n_global * 0.3) s = s * 1 / 5;
-        if (acc > n_global * 0.7) s = s * 2;
+// producer side of the early slot (thread 0 of a block, after the block finished a tile of `cnt` particles whose
+// accepted proposals are already added to accept_counts[step]): the block whose tile takes the number of counted
+// particles across n - slack publishes the running count to every peer.
+__device__ __forceinline__ void xchg_tile_done(const smcb_xchg_t& x, unsigned long long* accept_counts, int step,
+                                               long long n, double n_global, unsigned int cnt) {
+    const unsigned long long slack = xchg_early_slack(n_global, x.world);
+    const unsigned long long thr = (unsigned long long)n > slack ? (unsigned long long)n - slack : 0ull;
+    __threadfence();
+    const unsigned long long before = atomicAdd(x.ticket + 1, cnt), after = before + cnt;
+    if (after >= thr && (before < thr || (thr == 0ull && before == 0ull))) {
+        __threadfence();
+        const unsigned long long c = atomicAdd(accept_counts + step, 0ull);
+        const unsigned long long word = (x.gen << 32) | (c & kCountMask);
+        for (int r = 0; r < x.world; ++r)
+            st_sys(reinterpret_cast<unsigned long long*>(x.peer_slots[r]) +
+                       (size_t)(SMCB_MAX_MCMC_STEPS + step) * SMCB_MAX_RANKS + x.rank,
+                   word);
     }
-    return sqrt(s);
 }
-
 // The same scale computed by the whole block: thread k classifies step k (the accept-count loads of all
 // previous steps are in flight together instead of one dependent load after another on thread 0: up to 19 x 0.6 us
 // at the 20th step of a mutate call), the two class counts are reduced with barrier counts, and every thread
@@ -139,7 +190,7 @@ __device__ __forceinline__ double block_cov_scale_sqrt(const MhArgs& a) {
         const int k = base + (int)threadIdx.x;
         bool u = false, dn = false;
         if (k < a.step) {
-            const double acc = (a.x.world > 1) ? xchg_global_count(a.x, k, k == a.step - 1) : (double)a.accept_counts[k];
+            const double acc = (a.x.world > 1) ? xchg_global_count(a.x, k, k == a.step - 1, a.n_global) : (double)a.accept_counts[k];
             dn = acc < a.n_global * 0.3;
             u = acc > a.n_global * 0.7;
         }
@@ -356,7 +407,7 @@ __device__ __forceinline__ void ll_linear_normal(const MhArgs& a, const double (
         }
         if (run_any) {
             int j = 0;
-#pragma unroll 4
+#pragma unroll 8
             for (; j + 2 <= cnt; j += 2) {
                 const double2 p0 = sxy[j], p1 = sxy[j + 1];
 #pragma unroll
@@ -656,6 +707,8 @@ mh_kernel(const __grid_constant__ MhArgs a) {
     if ((MODE == 0 || MODE == 1) && resident) stage_data<KIND, !MULTI>(a, sdata, 0, a.prob.n_data);
     double sc = 0.0;
     if (MODE == 1 || MODE == 2) sc = block_cov_scale_sqrt<TPB>(a);
+    __shared__ long long sh_tile;                  // DYN: the tile the block works on (-1: none yet)
+    if (DYN && threadIdx.x == 0) sh_tile = -1;
     __syncthreads();
 
     const int64_t per_tile = (int64_t)TPB * PPT;
@@ -702,11 +755,25 @@ mh_kernel(const __grid_constant__ MhArgs a) {
     if (PREF && (int64_t)blockIdx.x < n_tiles) pref_issue(blockIdx.x);
     // (fetching the next tile at the START of the current one, to hide the atomic's latency, was measured 15 %
     // slower for C2 and is not done)
-    __shared__ long long sh_tile;
     for (int64_t tile = blockIdx.x;; tile += gridDim.x) {
         if (DYN) {
+            if (MODE == 1 && a.x.world > 1) {
+                // several GPUs: count the finished tile's accepted proposals now (not at the end of the launch),
+                // so that thread 0 can report the tile below and the early slot carries a running count
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
+                if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
+                n_acc = 0;
+            }
             __syncthreads();                       // previous tile fully consumed sh_tile
-            if (threadIdx.x == 0) sh_tile = (long long)atomicAdd(reinterpret_cast<unsigned int*>(a.flags) + 1, 1u);
+            if (threadIdx.x == 0) {
+                if (MODE == 1 && a.x.world > 1 && sh_tile >= 0) {       // sh_tile still names the tile just finished
+                    const int64_t left = a.n - (int64_t)sh_tile * per_tile;
+                    xchg_tile_done(a.x, a.accept_counts, a.step, a.n, a.n_global,
+                                   (unsigned int)(left < per_tile ? left : per_tile));
+                }
+                sh_tile = (long long)atomicAdd(reinterpret_cast<unsigned int*>(a.flags) + 1, 1u);
+            }
             __syncthreads();
             tile = sh_tile;
         }
@@ -717,6 +784,10 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         double ll_old[PPT], lp_old[PPT], lp_new[PPT], ll_new[PPT];
         double lq_old[PPT], lq_new[PPT];
         bool prior_ok[PPT];
+        // linear model, several particles per thread: the current ll / lp are only needed by the acceptance test --
+        // loading them after the pass over the data keeps 4 PPT registers out of the FP64 loop (with them live ptxas
+        // schedules every residual right before its square: a dependent DFMA pair per point)
+        constexpr bool kLateOld = (KIND == K_LINEAR_NORMAL && PPT >= 4 && MODE == 1 && !TMA && !PREF && !PROP);
         if (TMA) {
             // native RNG only.  The proposal increment sqrt(s) L z is a (particles x d) x (d x d) product:
             // tensor cores, tf32 inputs (the mma ignores the low mantissa bits: truncation, exactly
@@ -867,7 +938,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                     pc += a.stride;
                 }
                 ll_old[p] = lp_old[p] = 0.0;
-                if (MODE == 1) {
+                if (MODE == 1 && !kLateOld) {
                     ll_old[p] = a.ll[idx[p]];
                     lp_old[p] = a.lp[idx[p]];
                 }
@@ -972,6 +1043,13 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                 else ll_new[p] = ll_linear_mvn<KIND, DMAX>(a, th[p], run[p], sdata, not_pd[p]);
             }
         }
+        if constexpr (kLateOld) {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                ll_old[p] = a.ll[idx[p]];
+                lp_old[p] = a.lp[idx[p]];
+            }
+        }
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
             if (!run[p]) ll_new[p] = 0.0;       // placeholder (vector_mcmc.py:207)
@@ -1049,7 +1127,10 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                        (size_t)a.step * SMCB_MAX_RANKS + a.x.rank,
                    word);
             __threadfence_system();
-            if (threadIdx.x == 0) *a.x.ticket = 0u;
+            if (threadIdx.x == 0) {
+                a.x.ticket[0] = 0u;
+                a.x.ticket[1] = 0u;                 // counted-particles counter of the early slot
+            }
         }
     }
 }
@@ -1652,6 +1733,8 @@ extern "C" int smcb_mh_step(const smcb_problem_t* prob, const smcb_path_t* path,
     a.flags = flags;
     return dispatch<1>(a, as_stream(stream));
 }
+
+extern "C" int smcb_mh_xchg_slot_words(void) { return 2 * SMCB_MAX_MCMC_STEPS * SMCB_MAX_RANKS; }
 
 extern "C" int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* path, double* params,
                                  int64_t stride, int64_t n, int64_t n_global, double* ll, double* lp, double* lq,

@@ -74,7 +74,7 @@ class PeerExchange:
             for r, p in enumerate(peer_pointers(t, h)):
                 x.peer_slots[r] = p
             return t, h, x
-        self.slots, self.handle, self.x = sym(_lib.MAX_MCMC_STEPS * _lib.MAX_RANKS)
+        self.slots, self.handle, self.x = sym(_lib.lib.smcb_mh_xchg_slot_words())
         self.global_counts = torch.zeros(_lib.MAX_MCMC_STEPS, dtype=torch.int64, device=dv)
         self.ticket = torch.zeros(4, dtype=torch.int32, device=dv)
         self.x.global_counts = self.global_counts.data_ptr()
