@@ -84,20 +84,65 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING a timed region."""
+    """SM clocks / throttle reasons sampled DURING a timed region.
+
+    NVML in-process (pynvml, initialised and queried once BEFORE the region): a poller thread reads clocks, power
+    and the clocks-event-reason mask every 100 ms.  An `nvidia-smi -lms` child process is the fallback only: its
+    start-up (driver enumeration under the management lock) inside a 0.3 s timed region stalled kernel launches
+    of the first process on a fresh box by 10-25 % (same kernels, longer host gaps)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, indices, enabled=True):
         """One poller per job (rank 0), covering every GPU of the job: eight pollers at 10 Hz, one
         per rank, measurably slowed the 8-GPU run through the driver's management lock."""
-        self.rows, self.proc = [], None
-        self.index = ",".join(str(i) for i in indices)
+        self.rows, self.proc, self.nv, self.handles = [], None, None, []
+        self.indices = [int(i) for i in indices]
+        self.index = ",".join(str(i) for i in self.indices)
         self.enabled = enabled
+        self._stop = threading.Event()
+        if not enabled:
+            return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.nv = pynvml
+            self._sample()                       # first queries (lazy driver paths) outside the timed region
+            self.rows = []
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        for h in self.handles:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if mask & b else "Not Active" for _, b in self.BITS])
+
+    def _poll(self):
+        period = 0.1 if len(self.handles) == 1 else 0.2
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self._stop.wait(period)
 
     def start(self):
         if not self.enabled:
+            return
+        self._stop.clear()
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, "--query-gpu=" + self.Q,
@@ -115,13 +160,21 @@ class ClockSampler:
     def stop(self):
         if not self.enabled:
             return None
-        if self.proc is None:
+        if self.nv is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+            try:
+                self._sample()                   # at least one sample right at the end of the region
+            except Exception:
+                pass
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
@@ -135,7 +188,7 @@ class ClockSampler:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None, "samples": len(sm),
-                "gpus": self.index, "reasons": sorted(reasons)}
+                "gpus": self.index, "source": "nvml" if self.nv is not None else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -593,16 +646,22 @@ def run_gpu(args):
     value = units / (ms_per_step * 1e-3)
 
     # ---- timed: end to end through the public API with host buffers ---------------------------
-    for i in range(2):
-        one_pass(300 + i, None, host_out=True)
+    # warm-up with the results HELD like in the timed loop: a pass allocates its page-locked result buffers while
+    # the previous pass's are still referenced, so two sets must exist before the clock starts (the one-time
+    # cudaHostAlloc of the second set, 15-70 ms, otherwise lands in the second timed pass)
+    for i in range(max(2, args.warmup)):
+        p, ll, lw, mll, _ = one_pass(300 + i, None, host_out=True)
     barrier()
     e2e_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     e2e_ev[0].record()
     d2h = 0
+    e2e_pass_ms = []
     for i in range(args.steps):
+        t_pass = time.perf_counter()
         flush.zero_()
         p, ll, lw, mll, _ = one_pass(400 + i, None, host_out=True)
         d2h = p.nbytes + ll.nbytes + lw.nbytes + mll.nbytes
+        e2e_pass_ms.append(round((time.perf_counter() - t_pass) * 1e3, 3))      # host clock: the results are on the host
     e2e_ev[1].record()
     barrier()
     e2e_ms = e2e_ev[0].elapsed_time(e2e_ev[1])
@@ -696,7 +755,8 @@ def run_gpu(args):
                       "stored_steps": "InMemoryStorage(retain=1): only the last step is kept (and copied to the host in e2e)",
                       "precision": PRECISION},
            "clocks": clocks,
-           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "pass_ms_host_clock": e2e_pass_ms},
            "gpu_launches": int(launches),
            "roofline": roofline, "kernels": other,
            "mll_last": mlls[-1]}

@@ -171,7 +171,8 @@ typedef struct smcb_xchg {
     uint64_t* peer_slots[SMCB_MAX_RANKS];   /* device pointers to each rank's slots buffer */
     int64_t* global_counts;                 /* device, SMCB_MAX_MCMC_STEPS: per step a count with the scale decision of the
                                              * global count (the global count itself when every final slot had arrived) */
-    uint32_t* ticket;                       /* device, 2 zero-initialised words: block ticket, counted particles */
+    uint32_t* ticket;                       /* device, 4 zero-initialised words, 8-byte aligned: [0] block ticket,
+                                             * [2..3] progress word (particles counted << 32 | accepted) */
 } smcb_xchg_t;
 
 /* ---- library --------------------------------------------------------------------- */

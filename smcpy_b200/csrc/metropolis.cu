@@ -158,23 +158,30 @@ __device__ __forceinline__ double xchg_global_count(const smcb_xchg_t& x, int j,
     x.global_counts[j] = (long long)rep;     // blocks may store different, decision-equivalent values
     return (double)rep;
 }
-// producer side of the early slot (thread 0 of a block, after the block finished a tile of `cnt` particles whose
-// accepted proposals are already added to accept_counts[step]): the block whose tile takes the number of counted
-// particles across n - slack publishes the running count to every peer.
-__device__ __forceinline__ void xchg_tile_done(const smcb_xchg_t& x, unsigned long long* accept_counts, int step,
-                                               long long n, double n_global, unsigned int cnt) {
+// producer side (dynamic-tile kernels, thread 0 of a block that finished a tile of `cnt` particles of which `acc`
+// were accepted).  One 64-bit atomicAdd per tile on the launch's progress word
+//     (particles counted << 32 | proposals accepted among them)
+// returns a CONSISTENT (counted, accepted) pair, so no fence is needed: the block whose tile takes `counted`
+// across n - slack stores the early slot, the block whose tile completes n stores the final slot (and clears
+// the word for the next launch) -- no end-of-launch ticket round either.
+__device__ __forceinline__ void xchg_tile_done(const smcb_xchg_t& x, int step, long long n, double n_global,
+                                               unsigned int cnt, unsigned int acc) {
+    unsigned long long* prog = reinterpret_cast<unsigned long long*>(x.ticket + 2);
+    const unsigned long long add = ((unsigned long long)cnt << 32) | acc;
+    const unsigned long long before = atomicAdd(prog, add), after = before + add;
+    const unsigned long long d0 = before >> 32, d1 = after >> 32;
     const unsigned long long slack = xchg_early_slack(n_global, x.world);
     const unsigned long long thr = (unsigned long long)n > slack ? (unsigned long long)n - slack : 0ull;
-    __threadfence();
-    const unsigned long long before = atomicAdd(x.ticket + 1, cnt), after = before + cnt;
-    if (after >= thr && (before < thr || (thr == 0ull && before == 0ull))) {
-        __threadfence();
-        const unsigned long long c = atomicAdd(accept_counts + step, 0ull);
-        const unsigned long long word = (x.gen << 32) | (c & kCountMask);
-        for (int r = 0; r < x.world; ++r)
-            st_sys(reinterpret_cast<unsigned long long*>(x.peer_slots[r]) +
-                       (size_t)(SMCB_MAX_MCMC_STEPS + step) * SMCB_MAX_RANKS + x.rank,
-                   word);
+    const bool early = d1 >= thr && (d0 < thr || (thr == 0ull && d0 == 0ull));
+    const bool fin = d1 == (unsigned long long)n;
+    if (early || fin) {
+        const unsigned long long word = (x.gen << 32) | (after & kCountMask);
+        for (int r = 0; r < x.world; ++r) {
+            unsigned long long* base = reinterpret_cast<unsigned long long*>(x.peer_slots[r]) + x.rank;
+            if (early) st_sys(base + (size_t)(SMCB_MAX_MCMC_STEPS + step) * SMCB_MAX_RANKS, word);
+            if (fin) st_sys(base + (size_t)step * SMCB_MAX_RANKS, word);
+        }
+        if (fin) *prog = 0ull;                      // every particle is counted: nobody adds again in this launch
     }
 }
 // The same scale computed by the whole block: thread k classifies step k (the accept-count loads of all
@@ -708,7 +715,11 @@ mh_kernel(const __grid_constant__ MhArgs a) {
     double sc = 0.0;
     if (MODE == 1 || MODE == 2) sc = block_cov_scale_sqrt<TPB>(a);
     __shared__ long long sh_tile;                  // DYN: the tile the block works on (-1: none yet)
-    if (DYN && threadIdx.x == 0) sh_tile = -1;
+    __shared__ unsigned int sh_acc;                // DYN, several GPUs: proposals accepted in that tile
+    if (DYN && threadIdx.x == 0) {
+        sh_tile = -1;
+        sh_acc = 0u;
+    }
     __syncthreads();
 
     const int64_t per_tile = (int64_t)TPB * PPT;
@@ -759,20 +770,25 @@ mh_kernel(const __grid_constant__ MhArgs a) {
         if (DYN) {
             if (MODE == 1 && a.x.world > 1) {
                 // several GPUs: count the finished tile's accepted proposals now (not at the end of the launch),
-                // so that thread 0 can report the tile below and the early slot carries a running count
+                // so that thread 0 can report the tile below with its block total
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
-                if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
+                if ((threadIdx.x & 31) == 0 && n_acc) {
+                    atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
+                    atomicAdd(&sh_acc, (unsigned int)n_acc);
+                }
                 n_acc = 0;
             }
             __syncthreads();                       // previous tile fully consumed sh_tile
             if (threadIdx.x == 0) {
+                // the tile fetch first: the two atomics are independent and travel together
+                const long long next = (long long)atomicAdd(reinterpret_cast<unsigned int*>(a.flags) + 1, 1u);
                 if (MODE == 1 && a.x.world > 1 && sh_tile >= 0) {       // sh_tile still names the tile just finished
                     const int64_t left = a.n - (int64_t)sh_tile * per_tile;
-                    xchg_tile_done(a.x, a.accept_counts, a.step, a.n, a.n_global,
-                                   (unsigned int)(left < per_tile ? left : per_tile));
+                    xchg_tile_done(a.x, a.step, a.n, a.n_global, (unsigned int)(left < per_tile ? left : per_tile), sh_acc);
+                    sh_acc = 0u;
                 }
-                sh_tile = (long long)atomicAdd(reinterpret_cast<unsigned int*>(a.flags) + 1, 1u);
+                sh_tile = next;
             }
             __syncthreads();
             tile = sh_tile;
@@ -1112,7 +1128,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
     if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(a.accept_counts + a.step, (unsigned long long)n_acc);
-    if (a.x.world > 1) {
+    if (a.x.world > 1 && !DYN) {                    // (dynamic-tile kernels: xchg_tile_done stores the final slot)
         // the last block of the grid publishes this rank's count to every peer (P2P stores)
         __shared__ bool is_last;
         __threadfence();
@@ -1127,10 +1143,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
                        (size_t)a.step * SMCB_MAX_RANKS + a.x.rank,
                    word);
             __threadfence_system();
-            if (threadIdx.x == 0) {
-                a.x.ticket[0] = 0u;
-                a.x.ticket[1] = 0u;                 // counted-particles counter of the early slot
-            }
+            if (threadIdx.x == 0) a.x.ticket[0] = 0u;
         }
     }
 }
