@@ -72,7 +72,8 @@ enum {
     SMCB_FLAG_MODEL_NAN = 2,   /* NaN in model output (log_likelihoods.py:14-15) */
     SMCB_FLAG_COV_NOT_PD = 4,  /* MVNormal covariance not PD where the likelihood needed it */
     SMCB_FLAG_CHOL_FAIL = 8,   /* proposal covariance not PD (vector_mcmc.py:224-236) */
-    SMCB_FLAG_COV_RESHIFT = 16 /* one-pass covariance: the shift was too far from the mean, redo in two passes */
+    SMCB_FLAG_COV_RESHIFT = 16, /* one-pass covariance: the shift was too far from the mean, redo in two passes */
+    SMCB_FLAG_XCHG_TIMEOUT = 32 /* smcb_mh_step_xchg: a peer's accept count never arrived (option xchg_timeout_s) */
 };
 /* resampling uniforms (smcpy/resampler_rngs.py:4-9; systematic is an extension) */
 enum { SMCB_RESAMPLE_STANDARD = 0, SMCB_RESAMPLE_STRATIFIED = 1, SMCB_RESAMPLE_SYSTEMATIC = 2 };

@@ -23,7 +23,7 @@ MODEL_LINEAR, MODEL_SPRING_MASS, MODEL_IDENTITY = 1, 2, 3
 LL_NORMAL, LL_MVNORMAL, LL_MULTISOURCE = 1, 2, 3
 MAX_SEGMENTS = 8
 PRIOR_UNIFORM, PRIOR_IMPROPER_UNIFORM, PRIOR_IMPROPER_COV, PRIOR_EXTERNAL = 1, 2, 3, 4
-FLAG_PRIOR_OOB, FLAG_MODEL_NAN, FLAG_COV_NOT_PD, FLAG_CHOL_FAIL, FLAG_COV_RESHIFT = 1, 2, 4, 8, 16
+FLAG_PRIOR_OOB, FLAG_MODEL_NAN, FLAG_COV_NOT_PD, FLAG_CHOL_FAIL, FLAG_COV_RESHIFT, FLAG_XCHG_TIMEOUT = 1, 2, 4, 8, 16, 32
 RESAMPLE_STANDARD, RESAMPLE_STRATIFIED, RESAMPLE_SYSTEMATIC = 0, 1, 2
 SCAN_SEQUENTIAL, SCAN_LOOKBACK = 0, 1
 

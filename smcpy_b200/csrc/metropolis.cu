@@ -75,6 +75,7 @@ struct MhArgs {
     PhiloxKeys rk;        // Philox round keys of rng.seed
     ColPriors cp;
     smcb_xchg_t x;        // world <= 1: no cross-GPU exchange
+    unsigned long long xchg_timeout_ns;
     smcb_problem_t prob;
 };
 
@@ -116,13 +117,16 @@ __device__ __forceinline__ unsigned long long xchg_early_slack(double n_global, 
 }
 // a count with the same scale decision as the global accept count of step j (the exact count whenever every
 // rank's final slot had arrived): local cache for earlier steps, else from the peers' slots
-__device__ __forceinline__ double xchg_global_count(const smcb_xchg_t& x, int j, bool latest, double n_global) {
+__device__ __forceinline__ double xchg_global_count(const smcb_xchg_t& x, int j, bool latest, double n_global,
+                                                    unsigned long long timeout_ns, int32_t* flags) {
     if (!latest) return (double)x.global_counts[j];
     const unsigned long long* fin =
         reinterpret_cast<const unsigned long long*>(x.peer_slots[x.rank]) + (size_t)j * SMCB_MAX_RANKS;
     const unsigned long long* early = fin + (size_t)SMCB_MAX_MCMC_STEPS * SMCB_MAX_RANKS;
     const unsigned long long slack = xchg_early_slack(n_global, x.world);
     unsigned long long rep = 0;
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
     for (;;) {
         unsigned long long lo = 0, hi = 0;
         bool ready = true, exact = true;
@@ -154,6 +158,18 @@ __device__ __forceinline__ double xchg_global_count(const smcb_xchg_t& x, int j,
             }
         }
         __nanosleep(64);
+        // a peer that never answers (died, or never launched the step): give up after the exchange time-out, flag it
+        // (the host raises on every rank) and carry on with what is known -- the result is discarded anyway
+        if ((++spins & 1023u) == 0u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeout_ns) {
+                atomicOr(flags, SMCB_FLAG_XCHG_TIMEOUT);
+                rep = lo;
+                break;
+            }
+        }
     }
     x.global_counts[j] = (long long)rep;     // blocks may store different, decision-equivalent values
     return (double)rep;
@@ -197,7 +213,8 @@ __device__ __forceinline__ double block_cov_scale_sqrt(const MhArgs& a) {
         const int k = base + (int)threadIdx.x;
         bool u = false, dn = false;
         if (k < a.step) {
-            const double acc = (a.x.world > 1) ? xchg_global_count(a.x, k, k == a.step - 1, a.n_global) : (double)a.accept_counts[k];
+            const double acc = (a.x.world > 1) ? xchg_global_count(a.x, k, k == a.step - 1, a.n_global, a.xchg_timeout_ns, a.flags)
+                                               : (double)a.accept_counts[k];
             dn = acc < a.n_global * 0.3;
             u = acc > a.n_global * 0.7;
         }
@@ -1774,6 +1791,10 @@ extern "C" int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* 
     a.moved = moved;
     a.flags = flags;
     a.x = *x;
+    {
+        const int tmo_s = options().xchg_timeout_s;
+        a.xchg_timeout_ns = (unsigned long long)(tmo_s > 0 ? tmo_s : 30) * 1000000000ull;
+    }
     return dispatch<1>(a, as_stream(stream));
 }
 

@@ -598,6 +598,8 @@ class DeviceState:
         if f & _lib.FLAG_COV_NOT_PD:
             raise ValueError("MVNormal covariance is not positive definite for a particle with "
                              "finite prior (%s); add an ImproperCov prior" % where)
+        if f & _lib.FLAG_XCHG_TIMEOUT:
+            raise RuntimeError("a peer GPU never published its accept count (%s): the Metropolis exchange timed out" % where)
         return f
 
 
@@ -1075,12 +1077,12 @@ def mutate(st, spec, num_samples, path, rng, check_incoming=False, lazy_chol=Fal
     items, st.deferred = st.deferred, []
     extra = [t.reshape(1).to(torch.float64) for t, _ in items]
     if world > 1:
-        bits = (st.flags[0].to(torch.int64) >> torch.arange(5, device=st.cols.device)) & 1
+        bits = (st.flags[0].to(torch.int64) >> torch.arange(6, device=st.cols.device)) & 1
         pack = torch.cat([st.counts[1:2].to(torch.float64), bits.to(torch.float64)] + extra)
         _all_reduce_sum(pack)
         packed = pack.cpu().numpy()                          # the step's host sync
-        flags = int(sum((1 << b) for b in range(5) if packed[1 + b] > 0))
-        rest = packed[6:]
+        flags = int(sum((1 << b) for b in range(6) if packed[1 + b] > 0))
+        rest = packed[7:]
     else:
         packed = torch.cat([st.counts[1:2].to(torch.float64), st.flags[0:1].to(torch.float64)] + extra).cpu().numpy()
         flags = int(packed[1])
