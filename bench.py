@@ -29,6 +29,7 @@ One bench "step" = one complete sample() pass = 19 SMC steps x 20 Metropolis ste
 """
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -606,6 +607,11 @@ def run_gpu(args):
     for i in range(args.warmup):
         flush.zero_()
         one_pass(100 + i, spec)
+    # the interpreter's cyclic collector: a full (generation-2) collection walks every object torch / numpy / scipy
+    # created at import -- 15-25 ms on this box, landing at random inside one timed pass (seen as one 78 ms pass among
+    # 64 ms ones).  Everything alive after warm-up is moved to the permanent generation; collection itself stays on.
+    gc.collect()
+    gc.freeze()
 
     # ---- timed: device-resident ------------------------------------------------------------
     sampler_clk = ClockSampler(range(world) if world > 1 else [local], enabled=(rank == 0))
@@ -622,7 +628,8 @@ def run_gpu(args):
         mlls.append(float(mll[-1]))
     barrier()
     clocks = sampler_clk.stop()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
     launches = _lib.launch_count
     mh_variant = _lib.last_mh_variant()
     # separate, untimed pass with per-kernel CUDA events (creating ~900 events inside the timed
@@ -745,7 +752,8 @@ def run_gpu(args):
         other["cov"] = {"avg_ms": float(np.mean(prof["cov"])), "alg_bytes_per_particle": 16 * d}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "step_ms_rank0": [round(x, 3) for x in step_ms],
+           "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": WORKLOAD,
                       "particles_per_gpu": N_PER_GPU, "num_mcmc_samples": K_MCMC, "data_points": M_DATA,
