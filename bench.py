@@ -100,6 +100,7 @@ class ClockSampler:
         """One poller per job (rank 0), covering every GPU of the job: eight pollers at 10 Hz, one
         per rank, measurably slowed the 8-GPU run through the driver's management lock."""
         self.rows, self.proc, self.nv, self.handles = [], None, None, []
+        self.max_mhz, self.sample_ms = {}, []
         self.indices = [int(i) for i in indices]
         self.index = ",".join(str(i) for i in self.indices)
         self.enabled = enabled
@@ -112,21 +113,25 @@ class ClockSampler:
             self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
             self.nv = pynvml
             self._sample()                       # first queries (lazy driver paths) outside the timed region
-            self.rows = []
+            self.rows, self.sample_ms = [], []
         except Exception:
             self.nv = None
 
     def _sample(self):
         nv = self.nv
-        for h in self.handles:
+        t0 = time.perf_counter()
+        for i, h in enumerate(self.handles):
             sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            if i not in self.max_mhz:            # a constant of the board: asked once (before the timed region)
+                self.max_mhz[i] = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            mx = self.max_mhz[i]
             pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
             try:
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
             except Exception:
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if mask & b else "Not Active" for _, b in self.BITS])
+        self.sample_ms.append(round((time.perf_counter() - t0) * 1e3, 3))
 
     def _poll(self):
         period = 0.1 if len(self.handles) == 1 else 0.2
@@ -189,7 +194,8 @@ class ClockSampler:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None, "samples": len(sm),
-                "gpus": self.index, "source": "nvml" if self.nv is not None else "nvidia-smi", "reasons": sorted(reasons)}
+                "gpus": self.index, "source": "nvml" if self.nv is not None else "nvidia-smi", "reasons": sorted(reasons),
+                "sample_call_ms": self.sample_ms[:16]}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -466,8 +466,11 @@ int smcb_mh_step_xchg(const smcb_problem_t* prob, const smcb_path_t* path, doubl
 /* `n_steps` consecutive fused Metropolis steps (first_step .. first_step + n_steps - 1 of the mutate call, generator
  * streams rng->stream .. rng->stream + n_steps - 1) enqueued by ONE call: the K-step loop of
  * VectorMCMC.smc_metropolis (vector_mcmc.py:52-60) without a host round trip per step -- what makes the small
- * configurations (C1: 500 particles) launch-bound is the per-step binding overhead, not the kernels.  Native
- * generator only; x != NULL && x->world > 1 selects the multi-GPU form. */
+ * configurations (C1: 500 particles) launch-bound is the per-step binding overhead, not the kernels.  The launches
+ * of steps after the first are chained by programmatic dependent launch (the next grid is scheduled while the
+ * previous one drains and stages the constant problem data before its griddepcontrol.wait; option "no_pdl" = 1
+ * serialises them plainly; results are bit-identical).  Native generator only; x != NULL && x->world > 1 selects
+ * the multi-GPU form. */
 int smcb_mh_steps(const smcb_problem_t* prob, const smcb_path_t* path, double* params, int64_t stride, int64_t n,
                   int64_t n_global, double* ll, double* lp, double* lq, uint8_t* moved, const double* chol,
                   int64_t* accept_counts, int32_t first_step, int32_t n_steps, const smcb_rng_t* rng, int32_t* flags,

@@ -45,6 +45,7 @@ Options& options() {
         v.no_pref = env_int("SMCB_NO_PREF", 0);
         v.xchg_timeout_s = env_int("SMCB_XCHG_TIMEOUT_S", 0);
         v.no_fused_resample = env_int("SMCB_NO_FUSED_RESAMPLE", 0);
+        v.no_pdl = env_int("SMCB_NO_PDL", 0);
         return v;
     }();
     return o;
@@ -70,6 +71,7 @@ static const OptEntry kOptTable[] = {
     {"no_fused_resample", &Options::no_fused_resample},
     {"no_mvn3", &Options::no_mvn3},
     {"no_pref", &Options::no_pref},
+    {"no_pdl", &Options::no_pdl},
 };
 
 }  // namespace smcb

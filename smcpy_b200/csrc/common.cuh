@@ -46,6 +46,7 @@ struct Options {
     int no_pref;           // 1: never take the cp.async-prefetching variant of it
     int xchg_timeout_s;    // peer-exchange time-out inside kernels (seconds; 0 = default 30)
     int no_fused_resample; // 1: separate uniforms / search / count / gather kernels (native mode)
+    int no_pdl;            // 1: smcb_mh_steps does not chain its launches by programmatic dependent launch
 };
 Options& options();
 void note_mh_variant(const char* text);

@@ -706,6 +706,16 @@ mh_kernel(const __grid_constant__ MhArgs a) {
     double* sdata = smem + DMAX * DMAX;      // 16-byte aligned data staging area
 
     const bool resident = (KIND == K_IDENTITY_NORMAL) || is_mvn(KIND) || (a.prob.n_data <= kChunk);
+    if (MODE == 1) {
+        // Programmatic dependent launch (smcb_mh_steps chains its K launches with it): let the next step's grid be
+        // scheduled as this one's blocks retire, and stage the problem data -- constant for the whole run, written
+        // by nothing on the stream -- BEFORE waiting for the previous step's grid to complete and flush.  The next
+        // launch's latency, block start-up and data staging then overlap the previous step's tail.  Both
+        // instructions are no-ops in a launch without the attribute.
+        asm volatile("griddepcontrol.launch_dependents;");
+        if (resident) stage_data<KIND, !MULTI>(a, sdata, 0, a.prob.n_data);
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     if (MODE == 1 || MODE == 2) {
         for (int e = threadIdx.x; e < DMAX * DMAX; e += TPB) {
             const int j = e / DMAX, r = e - j * DMAX;
@@ -728,7 +738,7 @@ mh_kernel(const __grid_constant__ MhArgs a) {
             }
         }
     }
-    if ((MODE == 0 || MODE == 1) && resident) stage_data<KIND, !MULTI>(a, sdata, 0, a.prob.n_data);
+    if (MODE == 0 && resident) stage_data<KIND, !MULTI>(a, sdata, 0, a.prob.n_data);
     double sc = 0.0;
     if (MODE == 1 || MODE == 2) sc = block_cov_scale_sqrt<TPB>(a);
     __shared__ long long sh_tile;                  // DYN: the tile the block works on (-1: none yet)
@@ -1437,6 +1447,9 @@ static size_t mh_smem_bytes(const smcb_problem_t* p) {
     return data + 16;      // + DMAX*DMAX doubles for the Cholesky factor, added per instantiation
 }
 
+// set by smcb_mh_steps around the launches of steps k >= 1 (the calling thread's launches only)
+static thread_local bool tl_pdl_launch = false;
+
 template <int KIND, int DMAX, int MODE, int TPB, int PPT, bool EXACT, bool TMA = false, bool PROP = false,
           bool DYN = false, bool MULTI = false, bool STRICT = false, bool PREF = false>
 static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
@@ -1481,6 +1494,27 @@ static int launch_cfg2(const MhArgs& a, cudaStream_t s) {
                  KIND, DMAX, TPB, PPT, (int)EXACT, (int)TMA, (int)PROP, (int)DYN, (int)MULTI, (int)STRICT, (int)PREF, grid,
                  (int)a.rng.mode, (long long)a.n);
         note_mh_variant(txt);
+    }
+    if (MODE == 1 && tl_pdl_launch) {
+        // step k >= 1 of smcb_mh_steps: programmatic stream serialisation against the previous step's launch
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TPB);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const cudaError_t e =
+            cudaLaunchKernelEx(&cfg, mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT, PREF>, a);
+        if (e != cudaSuccess) {
+            set_error("mh_kernel (dependent launch): %s", cudaGetErrorString(e));
+            return SMCB_ERR_CUDA;
+        }
+        return SMCB_OK;
     }
     mh_kernel<KIND, DMAX, MODE, TPB, PPT, EXACT, TMA, PROP, DYN, MULTI, STRICT, PREF><<<grid, TPB, smem, s>>>(a);
     return check_launch("mh_kernel");
@@ -1805,13 +1839,18 @@ extern "C" int smcb_mh_steps(const smcb_problem_t* prob, const smcb_path_t* path
     SMCB_REQUIRE(rng && n_steps >= 0 && first_step >= 0 && first_step + n_steps <= SMCB_MAX_MCMC_STEPS, "bad step range");
     SMCB_REQUIRE(rng->mode == 0, "smcb_mh_steps: native generator only (replay tapes are per step)");
     smcb_rng_t r = *rng;
+    const bool pdl = !options().no_pdl;
     for (int32_t k = 0; k < n_steps; ++k) {
         r.stream = rng->stream + (uint64_t)k;
+        // steps after the first follow a launch of the same kernel: chained by programmatic dependent launch
+        // (the first step follows the resampling / covariance / Cholesky kernels, which know nothing of it)
+        tl_pdl_launch = pdl && k > 0;
         const int rc = (x && x->world > 1)
                            ? smcb_mh_step_xchg(prob, path, params, stride, n, n_global, ll, lp, lq, moved, chol, accept_counts,
                                                first_step + k, &r, flags, x, stream)
                            : smcb_mh_step(prob, path, params, stride, n, n_global, ll, lp, lq, moved, chol, accept_counts,
                                           first_step + k, &r, flags, stream);
+        tl_pdl_launch = false;
         if (rc) return rc;
     }
     return SMCB_OK;

@@ -1499,3 +1499,39 @@ def test_standalone_metropolis_chain_vs_oracle(sb):
     np.testing.assert_allclose(g_chain, o_chain, rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(g_chain, golden("metropolis_chain")["chain"], rtol=1e-9, atol=1e-11)   # reference run
     assert np.any(g_chain[:, :, -1] != theta)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case, n, K", [("c2_dyn", 1 << 20, 6), ("c1_small", 500, 10), ("c5_tma", 1 << 18, 5), ("c3_spring", 1 << 16, 3)])
+def test_dependent_launch_chain_equals_plain_chain(sb, case, n, K):
+    """smcb_mh_steps chains the launches of steps k >= 1 by programmatic dependent launch (the next step's grid is
+    scheduled while the previous one drains and stages the constant problem data before griddepcontrol.wait).  The
+    chained run must leave exactly the state of the plainly serialised run (option no_pdl): particles, ll, lp,
+    accept counts, mutation ratio -- bit for bit, for the dynamic-tile C2 kernel, a launch-bound small run, the
+    TMA-staged wide kernel and the one-tile-per-block spring-mass kernel (vector_mcmc.py:46-62)."""
+    from smcpy_b200 import _lib, engine
+    from smcpy_b200.initializer import Initializer
+    problem = {"c2_dyn": lambda: configs.linear_problem(1000, sigma=0.5, data_seed=0),
+               "c1_small": lambda: configs.linear_problem(100),
+               "c5_tma": lambda: configs.gauss_problem(32),
+               "c3_spring": lambda: configs.spring_problem(500, 4)}[case]()
+    res = {}
+    for no_pdl in (0, 1):
+        mc, kernel = make_b200(problem, rng=11)
+        st = Initializer(kernel).initialize_state(n)
+        engine.covariance(st)
+        st.cov.mul_(0.02)
+        engine.cholesky(st)
+        with _lib.option("no_pdl", no_pdl):
+            ratio = engine.mutate(st, mc.spec, K, engine.make_path(0.4, 0.4, 1.0), kernel.rng)
+            v = _lib.last_mh_variant()
+        res[no_pdl] = (st.params_host(), st.ll.cpu().numpy().copy(), st.lp.cpu().numpy().copy(),
+                       st.accept_counts[:K].cpu().numpy().copy(), ratio, v)
+    if case == "c2_dyn":
+        assert "dyn=1" in res[0][5], res[0][5]
+    if case == "c5_tma":
+        assert "tma=1" in res[0][5], res[0][5]
+    for a, b in zip(res[0][:4], res[1][:4]):
+        np.testing.assert_array_equal(a, b)
+    assert res[0][4] == res[1][4] and 0.0 < res[0][4] <= 1.0
+    assert res[0][3].min() > 0
