@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kMomThreads) wsums2_kernel(const double* __res
 constexpr int kWP = 128;            // particles per tile
 constexpr int kWLd = 132;           // row length: == 4 (mod 16) doubles -> conflict-free fragment loads
 constexpr int kDmmaWarps = 8;
+constexpr int kWStages = 3;        // one-pass moments: TMA stages per CTA (3 x 34 KB x 2 CTAs per SM at d = 32)
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -250,8 +251,9 @@ wsums2_dmma_kernel(const double* __restrict__ params, int64_t pstride, const dou
 // the finalisation flags SMCB_FLAG_COV_RESHIFT otherwise and the caller falls back to the two passes.
 // Halves the HBM traffic of the covariance (one read of the particles instead of two).
 // Tiles go from TMA straight into rows padded to kWLd (conflict-free fragment loads); centring and
-// weighting happen in registers at fragment-load time, so there is no staging pass and the two
-// stages of raw tiles double-buffer the loads against the DMMAs.
+// weighting happen in registers at fragment-load time, so there is no staging pass; a ring of kWStages
+// raw tiles per CTA keeps the loads ahead of the DMMAs (with two stages the refill, issued only when all
+// eight warps have left a tile, did not cover the HBM latency: 45 % of the warp time at the tile barrier).
 template <int NB8>
 __global__ void __launch_bounds__(kDmmaWarps * 32, 2)
 wmoments_dmma_kernel(const double* __restrict__ params, int64_t pstride, const double* __restrict__ w, int64_t n,
@@ -261,7 +263,7 @@ wmoments_dmma_kernel(const double* __restrict__ params, int64_t pstride, const d
     constexpr int kStage = (DP + 1) * kWLd;
     constexpr int kOut = NBU8 * 64 + DP + 1;
     extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ __align__(8) uint64_t mbar[kWStages];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int frow = lane >> 2, fk = lane & 3;   // fragment row / k index of this lane
 
@@ -287,23 +289,22 @@ wmoments_dmma_kernel(const double* __restrict__ params, int64_t pstride, const d
         tma_load_1d(raw + DP * kWLd, w + base, bytes, &mbar[stage]);
     };
     if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+#pragma unroll
+        for (int st = 0; st < kWStages; ++st) mbar_init(&mbar[st], 1);
     }
     __syncthreads();
     if (tid == 0) {
-        if ((int64_t)blockIdx.x < n_tiles) issue(0, blockIdx.x);
-        if ((int64_t)blockIdx.x + gridDim.x < n_tiles) issue(1, (int64_t)blockIdx.x + gridDim.x);
+#pragma unroll
+        for (int st = 0; st < kWStages; ++st)
+            if ((int64_t)blockIdx.x + (int64_t)st * gridDim.x < n_tiles) issue(st, (int64_t)blockIdx.x + (int64_t)st * gridDim.x);
     }
-    uint32_t phase0 = 0, phase1 = 0;
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
+    int stage = 0;
+    uint32_t phase = 0;                          // parity of the current trip round the stage ring
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const double* raw = smem + stage * kStage;
         const int64_t base = tile * kWP;
         const int cnt = (int)((n - base < kWP) ? (n - base) : kWP);
-        if (stage == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1u; }
-        else { mbar_wait(&mbar[1], phase1); phase1 ^= 1u; }
+        mbar_wait(&mbar[stage], phase);
 #pragma unroll
         for (int ks = 0; ks < kWP / 4 / kDmmaWarps; ++ks) {
             const int p0 = (wid + ks * kDmmaWarps) * 4 + fk;
@@ -328,8 +329,13 @@ wmoments_dmma_kernel(const double* __restrict__ params, int64_t pstride, const d
                 }
         }
         __syncthreads();                          // every warp is done with this stage
-        if (tid == 0 && tile + 2 * (int64_t)gridDim.x < n_tiles) issue(stage, tile + 2 * (int64_t)gridDim.x);
+        if (tid == 0 && tile + kWStages * (int64_t)gridDim.x < n_tiles) issue(stage, tile + kWStages * (int64_t)gridDim.x);
+        if (++stage == kWStages) {
+            stage = 0;
+            phase ^= 1u;
+        }
     }
+    __syncthreads();
     // lanes -> warp: the four k-lanes of a fragment row hold different particles
 #pragma unroll
     for (int I = 0; I < NB8; ++I) {
@@ -589,7 +595,7 @@ extern "C" int smcb_weighted_moments_shifted(const double* params, int64_t strid
     }
     const int nb8 = (d + 7) / 8, nbu8 = nb8 * (nb8 + 1) / 2, dp = nb8 * 8;
     const int k_out = nbu8 * 64 + dp + 1;
-    size_t smem_w = (size_t)2 * (dp + 1) * kWLd * sizeof(double);
+    size_t smem_w = (size_t)kWStages * (dp + 1) * kWLd * sizeof(double);
     const size_t red = (size_t)kDmmaWarps * k_out * sizeof(double);
     if (red > smem_w) smem_w = red;
     const int grid = kNumSMs * 2;
