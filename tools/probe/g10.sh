@@ -1,0 +1,2 @@
+O=gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3 > $O/g10_n8.json 2> $O/g10_n8.err
