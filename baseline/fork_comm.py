@@ -163,11 +163,21 @@ def c2_fixed_run(x, data, n, K, phi, ess_threshold, seed, ranks):
 def _adaptive(comm, build, n, K, target, seed):
     import smcpy
     from smcpy.resampler_rngs import standard
-    model, data, priors, std, names = build()
+    built = build()
+    model, data, priors, std, names = built[:5]
+    # optional sixth item: the name of a reference log-likelihood class (default Normal); priors given as
+    # ("improper_cov", n) are built from the reference's own prior classes here
+    extra = {}
+    if len(built) > 5:
+        from smcpy import log_likelihoods
+        extra["log_like_func"] = getattr(log_likelihoods, built[5])
+    from smcpy.priors import ImproperCov
+    priors = [ImproperCov(p[1], dof=5, S=np.eye(p[1])) if isinstance(p, tuple) and p[0] == "improper_cov" else p
+              for p in priors]
     if type(comm).__name__ == "ForkComm":
-        mcmc = smcpy.ParallelVectorMCMC(model, data, priors, comm, std)
+        mcmc = smcpy.ParallelVectorMCMC(model, data, priors, comm, std, **extra)
     else:
-        mcmc = smcpy.VectorMCMC(model, data, priors, std)
+        mcmc = smcpy.VectorMCMC(model, data, priors, std, **extra)
     kernel = smcpy.VectorMCMCKernel(mcmc, param_order=names, rng=np.random.default_rng(seed))
     smc = smcpy.AdaptiveSampler(kernel, show_progress_bar=False)
     t0 = time.perf_counter()
@@ -178,5 +188,6 @@ def _adaptive(comm, build, n, K, target, seed):
 
 
 def adaptive_run(build, n, K, target, seed, ranks):
-    """AdaptiveSampler.sample to phi = 1 -> (seconds, mll, SMC steps); build() -> (model, data, priors, std, names)."""
+    """AdaptiveSampler.sample to phi = 1 -> (seconds, mll, SMC steps); build() -> (model, data, priors, std, names
+    [, name of the reference log-likelihood class])."""
     return run_spmd(_adaptive, ranks, build, int(n), int(K), float(target), int(seed))

@@ -218,6 +218,35 @@ def _c1_build():
     return (lambda th: th[:, 0:1] * x[None, :] + th[:, 1:2]), data, [stats.uniform(-6.0, 12.0)] * 2, 0.5, ("a", "b")
 
 
+def _c3_build():
+    """C3 as the reference runs it (examples/spring_mass): LSODA odeint per particle in a Python loop, unknown noise
+    std as the third parameter; data from the closed-form trajectory (g/K)(1 - cos(sqrt(K) t)) + N(0, 0.5)."""
+    from scipy import stats
+    from scipy.integrate import odeint
+    t = np.linspace(0.0, 5.0, 500)
+    K, g = 1.67, 4.62
+    data = (g / K) * (1.0 - np.cos(np.sqrt(K) * t)) + np.random.default_rng(3).normal(0.0, 0.5, t.size)
+
+    def model(th):
+        out = np.empty((th.shape[0], t.size))
+        for i, (k, gg) in enumerate(th[:, :2]):
+            out[i] = odeint(lambda y, tt: [y[1], -k * y[0] + gg], [0.0, 0.0], t)[:, 0]
+        return out
+    return model, data, [stats.uniform(0.0, 10.0)] * 3, None, ("K", "g", "std")
+
+
+def _c4_build():
+    """C4: a X + b over three features, 50 snapshots, MVNormal likelihood with all six covariance terms sampled,
+    uniform(0, 6) x 2 + ImproperCov(3, dof=5, S=I) priors (examples/likelihood_functions/multivariate_normal_example)."""
+    from scipy import stats
+    X = np.arange(3, dtype=float)
+    true_cov = np.array([[0.5, 0.25, 0.005], [0.25, 0.25, 0.04], [0.005, 0.04, 1.0]])
+    data = np.tile(2.0 * X + 3.5, (50, 1)) + np.random.RandomState(200).multivariate_normal([0, 0, 0], true_cov, 50)
+    model = lambda th: th[:, 0:1] * X[None, :] + th[:, 1:2]
+    return (model, data, [stats.uniform(0.0, 6.0), stats.uniform(0.0, 6.0), ("improper_cov", 3)], [None] * 6,
+            ("a", "b") + tuple("cov%d" % i for i in range(6)), "MVNormal")
+
+
 def ref_c2_pass(fc, n, ranks, seed=1):
     x, data = linear_data(M_DATA)
     dt, mll = fc.c2_fixed_run(x, data, n, K_MCMC, PHI, ESS_THRESHOLD, seed, ranks)
@@ -230,7 +259,18 @@ def ref_north_star(fc, ranks, c5_n=2048):
     c1 = sorted(fc.adaptive_run(_c1_build, 500, 10, 0.8, 1 + i, 1)[0] for i in range(3))
     _, mll1, steps1 = fc.adaptive_run(_c1_build, 500, 10, 0.8, 1, 1)
     dt5, mll5, steps5 = fc.adaptive_run(_c5_build, c5_n, C5_K, 0.8, 1, ranks)
-    return {"c1": {"workload": "C1: README linear example, AdaptiveSampler, N=500, K=10, M=100 (full configuration)",
+    dt3, mll3, steps3 = fc.adaptive_run(_c3_build, 100, 5, 0.8, 1, 1)
+    dt4, mll4, steps4 = fc.adaptive_run(_c4_build, 256, 20, 0.8, 1, 1)
+    extra = {"c3": {"workload": "C3 at a CPU-feasible size: spring-mass model (LSODA odeint per particle, as the reference's "
+                                "example), AdaptiveSampler, N=100, K=5, 500 observations, unknown noise std",
+                    "particles": 100, "wall_s_to_phi1": dt3, "smc_steps": steps3, "mll": mll3, "ranks": 1,
+                    "steps_per_s": 100 * 5 * steps3 / dt3, "unit": UNIT},
+             "c4": {"workload": "C4 at a CPU-feasible size: MVNormal likelihood with unknown 3x3 covariance (50 snapshots), "
+                                "AdaptiveSampler, N=256, K=20",
+                    "particles": 256, "wall_s_to_phi1": dt4, "smc_steps": steps4, "mll": mll4, "ranks": 1,
+                    "steps_per_s": 256 * 20 * steps4 / dt4, "unit": UNIT}}
+    return {**extra,
+            "c1": {"workload": "C1: README linear example, AdaptiveSampler, N=500, K=10, M=100 (full configuration)",
                    "wall_s_to_phi1": c1[1], "wall_s_runs": c1, "smc_steps": steps1, "mll": mll1, "ranks": 1},
             "c5": {"workload": "C5 at a CPU-feasible size: 32-dim Gaussian target, AdaptiveSampler, N=%d, K=%d" % (c5_n, C5_K),
                    "particles": c5_n, "wall_s_to_phi1": dt5, "smc_steps": steps5, "mll": mll5,
