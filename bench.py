@@ -396,7 +396,8 @@ def _profile_table(engine, wall_ms):
 
 
 def north_star_gpu(sb, engine, _lib, torch, dist, rank, world, local, peaks):
-    """C5 to phi = 1 at 2^23 particles per GPU (sharded over all GPUs of the job) and C1 at N = 500."""
+    """C5 to phi = 1 at 2^23 particles per GPU (sharded over all GPUs of the job), C1 at N = 500, and C3 / C4 as
+    configured (2^22 particles per GPU)."""
     from scipy import stats
     out = {}
     n_local = 1 << C5_LOG2N
@@ -549,6 +550,60 @@ def north_star_gpu(sb, engine, _lib, torch, dist, rank, world, local, peaks):
                  "wall_s_to_phi1": w1[len(w1) // 2], "wall_s_runs": w1, "smc_steps": r1[0][1], "mll": r1[0][2],
                  "mll_analytic": -77.357884, "launches_per_run": launches,
                  "note": "launch/ctypes-latency bound at this size; host perf_counter around sample()"}
+
+    # C3 / C4 as configured (BASELINE.json configs[2], configs[3]): 2^22 particles per GPU, sharded over the job's GPUs;
+    # one warm-up run, one timed run each (CUDA events around sample(), max over ranks); tools/run_config.py is the
+    # long form with per-kernel times
+    def configured(label, build, names, K, truth):
+        def run(seed):
+            mcmc = build()
+            kernel = sb.VectorMCMCKernel(mcmc, param_order=names, rng=seed)
+            smc = sb.AdaptiveSampler(kernel, show_progress_bar=False)
+            smc._result = sb.InMemoryStorage(retain=1)
+            barrier()
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                steps, mll = smc.sample(n_cfg, K, target_ess=0.8, resample_rng=sb.standard)
+            ev[1].record()
+            barrier()
+            tt = torch.tensor([ev[0].elapsed_time(ev[1]) * 1e-3], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            last = steps[-1]
+            return (float(tt.item()), len(smc.phi_sequence) - 1, float(mll[-1]), last.compute_mean(package=False).tolist(),
+                    last.compute_std_dev(package=False).tolist())
+        n_cfg = (1 << 22) * world
+        run(1)
+        gc.collect()
+        clk = ClockSampler(range(world) if world > 1 else [local], enabled=(rank == 0))
+        clk.start()
+        w, ns_, mll_, mean_, std_ = run(2)
+        clocks_ = clk.stop()
+        gc.collect()
+        return {"workload": label % (world, n_cfg), "particles": n_cfg, "n_gpus": world, "wall_s_to_phi1": w, "smc_steps": ns_,
+                "steps_per_s": n_cfg * K * ns_ / w, "unit": UNIT, "mll": mll_, "posterior_mean": dict(zip(names, mean_)),
+                "posterior_std": dict(zip(names, std_)), "truth": truth, "kernel": _lib.last_mh_variant(), "clocks": clocks_}
+
+    m3 = 500
+    dt3 = 5.0 / (m3 - 1)
+    t3 = np.arange(m3) * dt3
+    data3 = noisy((4.62 / 1.67) * (1.0 - np.cos(np.sqrt(1.67) * t3)), 0.5, 3)[0]
+    out["c3"] = configured(
+        "C3: spring-mass ODE (RK4 device kernel, 4 sub-steps per output), AdaptiveSampler, 2^22 particles per GPU x %d GPU(s) = %d, "
+        "3 params (K, g, noise std), 500 observations, K=5",
+        lambda: sb.B200VectorMCMC(sb.SpringMassModel(dt3, m3, 4, 0.0, 0.0), data3, [stats.uniform(0.0, 10.0)] * 3, None),
+        ["K", "g", "std"], 5, {"K": 1.67, "g": 4.62, "std": 0.5})
+    X4 = np.arange(3, dtype=float)
+    cov4 = np.array([[0.5, 0.25, 0.005], [0.25, 0.25, 0.04], [0.005, 0.04, 1.0]])
+    data4 = np.tile(2.0 * X4 + 3.5, (50, 1)) + np.random.RandomState(200).multivariate_normal([0, 0, 0], cov4, 50)
+    out["c4"] = configured(
+        "C4: MVNormal likelihood with unknown 3x3 covariance (50 snapshots x 3 features), AdaptiveSampler, 2^22 particles per GPU x "
+        "%d GPU(s) = %d, 8 params, K=20",
+        lambda: sb.B200VectorMCMC(sb.LinearModel(X4), data4, [stats.uniform(0.0, 6.0), stats.uniform(0.0, 6.0),
+                                                               sb.ImproperCov(3, dof=5, S=np.eye(3))], [None] * 6, sb.MVNormal),
+        ["a", "b"] + ["cov%d" % i for i in range(6)], 20, {"a": 2.0, "b": 3.5, "cov": cov4[np.triu_indices(3)].tolist()})
     return out
 
 
