@@ -187,7 +187,8 @@ size_t smcb_workspace_bytes(int64_t n, int32_t d);
  * "linear_cfg", "persist", "no_dmma", "cov_two_pass", "no_coop", "coop_tpb", "coop_bps",
  * "bisect_plain", "spring_ppt" (-1 auto, 1 / 2 interleaved RK4 chains per thread), "no_mvn3" (generic MVNormal
  * kernel instead of the static 3-feature layout), "no_pref" (that kernel without its cp.async prefetch), "no_fused_resample", "xchg_timeout_s", "no_pdl" (smcb_mh_steps without
- * programmatic dependent launches).  smcb_get_option returns INT64_MIN for an unknown name. */
+ * programmatic dependent launches), "spring_form" (spring-mass kernels: 1 = RK4 propagator of the linear ODE, the default;
+ * 0 = the RK4 stages evaluated at every sub-step).  smcb_get_option returns INT64_MIN for an unknown name. */
 int smcb_set_option(const char* name, int64_t value);
 int64_t smcb_get_option(const char* name);
 /* Text description of the Metropolis kernel instantiation the calling thread launched last

@@ -46,6 +46,7 @@ Options& options() {
         v.xchg_timeout_s = env_int("SMCB_XCHG_TIMEOUT_S", 0);
         v.no_fused_resample = env_int("SMCB_NO_FUSED_RESAMPLE", 0);
         v.no_pdl = env_int("SMCB_NO_PDL", 0);
+        v.spring_form = env_int("SMCB_SPRING_FORM", 1);
         return v;
     }();
     return o;
@@ -72,6 +73,7 @@ static const OptEntry kOptTable[] = {
     {"no_mvn3", &Options::no_mvn3},
     {"no_pref", &Options::no_pref},
     {"no_pdl", &Options::no_pdl},
+    {"spring_form", &Options::spring_form},
 };
 
 }  // namespace smcb

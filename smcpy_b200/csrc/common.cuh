@@ -46,6 +46,7 @@ struct Options {
     int no_pref;           // 1: never take the cp.async-prefetching variant of it
     int xchg_timeout_s;    // peer-exchange time-out inside kernels (seconds; 0 = default 30)
     int no_fused_resample; // 1: separate uniforms / search / count / gather kernels (native mode)
+    int spring_form;       // spring-mass kernels: 1 (default) RK4 propagator of the linear ODE, 0 RK4 stages at every sub-step
     int no_pdl;            // 1: smcb_mh_steps does not chain its launches by programmatic dependent launch
 };
 Options& options();

@@ -1152,11 +1152,20 @@ def test_c4_prefetching_kernel_equals_plain_kernel_bit_for_bit(sb):
     assert res[0][2] == res[1][2]
 
 
+@pytest.mark.parametrize("form", [1, 0])
 @pytest.mark.parametrize("ppt", [1, 2])
-def test_c3_spring_instantiations_replay_vs_oracle(sb, ppt):
+def test_c3_spring_instantiations_replay_vs_oracle(sb, ppt, form):
     """Spring-mass RK4 kernel with one and with two interleaved chains per thread (the variant the
-    dispatcher takes at config C3's size) against the oracle's smc_metropolis driven by the NumPy RK4
-    model with the same step schedule, replayed normals/uniforms: 1e-10; the two variants agree bit for bit."""
+    dispatcher takes at config C3's size), in both forms -- the RK4 propagator of the linear ODE (default, what is
+    timed) and the RK4 stages evaluated at every sub-step -- against the oracle's smc_metropolis driven by the NumPy
+    RK4 model (stages) with the same step schedule, replayed normals/uniforms: 1e-10; the two chain counts agree
+    bit for bit."""
+    from smcpy_b200 import _lib
+    with _lib.option("spring_form", form):
+        _c3_spring_case(ppt, form)
+
+
+def _c3_spring_case(ppt, form):
     from smcpy_b200 import _lib
     problem = configs.spring_problem(500, 4)
     n, K, phi = 4099, 2, 0.2                                  # odd: the last tile is ragged
@@ -1174,6 +1183,7 @@ def test_c3_spring_instantiations_replay_vs_oracle(sb, ppt):
             out[q] = mc.smc_metropolis(theta, K, cov)
             v = _lib.last_mh_variant()
         assert ("kind=1,dmax=4,tpb=128,ppt=%d," % q) in v and "rng=1" in v, v
+        assert ("rk4=propagator" if form == 1 else "rk4=stages") in v, v
     g_theta, g_ll = out[ppt]
     np.testing.assert_allclose(g_theta, o_theta, rtol=RTOL, atol=1e-12)
     np.testing.assert_allclose(g_ll, o_ll, rtol=RTOL)
@@ -1535,3 +1545,35 @@ def test_dependent_launch_chain_equals_plain_chain(sb, case, n, K):
         np.testing.assert_array_equal(a, b)
     assert res[0][4] == res[1][4] and 0.0 < res[0][4] <= 1.0
     assert res[0][3].min() > 0
+
+
+def test_spring_rk4_propagator_equals_staged_rk4(sb):
+    """The two forms of the spring-mass kernel on the same particles over the whole prior box (K, g in (0, 10): up to
+    2.5 oscillations over the 500 observations, 4 sub-steps each): the log-likelihoods agree to 1e-11 relative -- the
+    propagator composes the same RK4 steps, the difference is rounding -- and a native-generator mutate() from the
+    same seed accepts the same proposals but for the handful whose ratio sits within that rounding of its uniform."""
+    from smcpy_b200 import _lib, engine
+    problem = configs.spring_problem(500, 4)
+    n = 1 << 16
+    rng0 = np.random.default_rng(4)
+    theta = np.column_stack([rng0.uniform(0.01, 9.99, n), rng0.uniform(0.01, 9.99, n), rng0.uniform(0.05, 9.9, n)])
+    theta[:2] = [[1.67, 4.62, 0.5], [9.99, 9.99, 0.3]]
+    res = {}
+    for form in (0, 1):
+        with _lib.option("spring_form", form):
+            mc, kernel = make_b200(problem, rng=7)
+            ll = mc.evaluate_log_likelihood(theta).reshape(-1)
+            st = engine.DeviceState(n, n, 3)
+            st.set_params_host(theta)
+            engine.eval_incoming(st, mc.spec)
+            engine.covariance(st)
+            st.cov.mul_(0.001)
+            engine.cholesky(st)
+            ratio = engine.mutate(st, mc.spec, 3, engine.make_path(0.3, 0.3, 1.0), engine.PhiloxRNG(5))
+            res[form] = (ll, st.params_host(), st.ll.cpu().numpy().copy(), ratio, _lib.last_mh_variant())
+    assert "rk4=stages" in res[0][4] and "rk4=propagator" in res[1][4]
+    np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-11)
+    same = np.all(res[0][1] == res[1][1], axis=1)
+    assert same.mean() > 0.999, same.mean()
+    np.testing.assert_allclose(res[1][2][same], res[0][2][same], rtol=1e-11)
+    assert abs(res[0][3] - res[1][3]) < 1e-3 and 0.05 < res[0][3] < 1.0

@@ -112,6 +112,13 @@ if rank == 0:
                         "gbps": (16 * d + 32) * n_local / mh / 1e6, "frac_hbm": (16 * d + 32) * n_local / mh / 1e6 / peaks["hbm_gbs"]}}
     if cfg == "c3":
         probes = bench.fp64_probes(_lib, torch)
+        if "rk4=propagator" in r0["variant"]:
+            # RK4 propagator of the linear ODE: 4 FMAs per observation (the nsub sub-steps composed once per particle
+            # and step) + the residual (sub, fma) -- the staged form runs 18 FP64 instructions per sub-step
+            flops_unit = 11.0 * M + 40.0 * nsub
+            out["mutation"]["rk4_form"] = "propagator"
+        else:
+            out["mutation"]["rk4_form"] = "stages"
         out["mutation"]["fp64_tflops"] = flops_unit * n_local / mh / 1e9
         out["mutation"]["fp64_peak_tflops"] = max(probes.values())
         out["mutation"]["fp64_frac"] = out["mutation"]["fp64_tflops"] / max(probes.values())
