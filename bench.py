@@ -591,7 +591,8 @@ def north_star_gpu(sb, engine, _lib, torch, dist, rank, world, local, peaks):
     t3 = np.arange(m3) * dt3
     data3 = noisy((4.62 / 1.67) * (1.0 - np.cos(np.sqrt(1.67) * t3)), 0.5, 3)[0]
     out["c3"] = configured(
-        "C3: spring-mass ODE (RK4 device kernel, 4 sub-steps per output), AdaptiveSampler, 2^22 particles per GPU x %d GPU(s) = %d, "
+        "C3: spring-mass ODE (RK4 device kernel, 4 sub-steps per output; the `kernel` field names the form: the RK4 propagator of "
+        "the linear ODE by default, the stages at every sub-step with option spring_form=0), AdaptiveSampler, 2^22 particles per GPU x %d GPU(s) = %d, "
         "3 params (K, g, noise std), 500 observations, K=5",
         lambda: sb.B200VectorMCMC(sb.SpringMassModel(dt3, m3, 4, 0.0, 0.0), data3, [stats.uniform(0.0, 10.0)] * 3, None),
         ["K", "g", "std"], 5, {"K": 1.67, "g": 4.62, "std": 0.5})
