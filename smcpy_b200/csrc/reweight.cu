@@ -319,12 +319,17 @@ __device__ __noinline__ bool xchg_allgather(const smcb_xchg_t& x, int round, con
         st_sys_u64(reinterpret_cast<unsigned long long*>(x.peer_slots[r]) + off + (size_t)kXRec * x.rank + (kXRec - 1), flag);
     const unsigned long long* own = reinterpret_cast<const unsigned long long*>(x.peer_slots[x.rank]) + off;
     const unsigned long long t0 = global_ns();
-    for (int r = 0; r < x.world; ++r) {
-        unsigned int spins = 0;
-        while (ld_sys_u64(own + (size_t)kXRec * r + (kXRec - 1)) != flag) {
-            __nanosleep(40);
-            if ((++spins & 1023u) == 0u && global_ns() - t0 > timeout_ns) return false;
-        }
+    // every rank's flag is requested before the first is looked at: a poll costs one load latency, not `world`
+    for (unsigned int spins = 0;;) {
+        bool all_in = true;
+        unsigned long long f[SMCB_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < SMCB_MAX_RANKS; ++r) f[r] = (r < x.world) ? ld_sys_u64(own + (size_t)kXRec * r + (kXRec - 1)) : flag;
+#pragma unroll
+        for (int r = 0; r < SMCB_MAX_RANKS; ++r) all_in = all_in && (f[r] == flag);
+        if (all_in) break;
+        __nanosleep(40);
+        if ((++spins & 1023u) == 0u && global_ns() - t0 > timeout_ns) return false;
     }
     __threadfence_system();
     for (int r = 0; r < x.world; ++r)
