@@ -402,6 +402,13 @@ int smcb_xchg_allgather(const smcb_xchg_t* x, const double* src, int32_t n_vals,
  * partial sums [sum w, sum w x, sum w (x-m)(x-m)^T] for the multi-GPU all-reduce. */
 int smcb_weighted_cov(const double* params, int64_t stride, const double* w, int64_t n, int32_t d,
                       double* mean_out, double* cov_out, double* sums_out, void* ws, void* stream);
+/* the same for particles sharded over several GPUs, enqueued by one call: both moment sums are all-reduced over
+ * the ranks through smcb_xchg_allgather on generations x->gen and x->gen + 1 (the caller advances its counter by
+ * two); xchg_scratch: device, max(1 + d, d * d) doubles; *status |= 1 on time-out.  Replaces np.cov over the
+ * gathered particles of the reference's parallel path (particles.py:189-198). */
+int smcb_weighted_cov_xchg(const double* params, int64_t stride, const double* w, int64_t n, int32_t d,
+                           double* mean_out, double* cov_out, double* sums_out, void* ws, const smcb_xchg_t* x,
+                           double* xchg_scratch, int32_t* status, void* stream);
 int smcb_weighted_sums1(const double* params, int64_t stride, const double* w, int64_t n, int32_t d,
                         double* sums_out /*1+d*/, void* ws, void* stream);
 int smcb_mean_from_sums(const double* sums /*1+d*/, int32_t d, double* mean_out, void* stream);

@@ -115,6 +115,7 @@ SIGNATURES = {
     "smcb_gather_p2p": [_P, _I64, _P, _I64, _I32, _I32, _P, _P, C.POINTER(C.c_void_p), _I64, _P],
     "smcb_count_unique": [_P, _I64, _I64, _P, _P, _P],
     "smcb_weighted_cov": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P, _P],
+    "smcb_weighted_cov_xchg": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P, _PP(Xchg), _P, _P, _P],
     "smcb_weighted_sums1": [_P, _I64, _P, _I64, _I32, _P, _P, _P],
     "smcb_mean_from_sums": [_P, _I32, _P, _P],
     "smcb_weighted_sums2": [_P, _I64, _P, _I64, _I32, _P, _P, _P, _P],
@@ -201,7 +202,7 @@ class _LazyLib:
 lib = _LazyLib()
 # kernels launched per C-ABI call (bench.py reports the sum as gpu_launches)
 LAUNCHES = {"smcb_reweight": 2, "smcb_cdf_scan": 2, "smcb_cdf_scan_weights": 2, "smcb_resample_exponential_sums": 2,
-            "smcb_resample_fused": 3, "smcb_xchg_slot_words": 0, "smcb_mh_xchg_slot_words": 0, "smcb_xchg_big_slot_words": 0, "smcb_xchg_max_vals": 0, "smcb_count_unique": 2, "smcb_weighted_cov": 7,
+            "smcb_resample_fused": 3, "smcb_xchg_slot_words": 0, "smcb_mh_xchg_slot_words": 0, "smcb_xchg_big_slot_words": 0, "smcb_xchg_max_vals": 0, "smcb_count_unique": 2, "smcb_weighted_cov": 7, "smcb_weighted_cov_xchg": 9,
             "smcb_weighted_sums1": 2, "smcb_weighted_moments_shifted": 3, "smcb_weighted_sums2": 3, "smcb_ess_bisect_max_iters": 0,
             "smcb_ess_bisect_xchg_slot_words": 0}
 launch_count = 0

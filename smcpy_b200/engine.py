@@ -937,6 +937,16 @@ def covariance(st, two_pass=False):
         with _timed("cov"):
             call("smcb_weighted_cov", ptr(st.params), stride, ptr(st.w), st.n, d, ptr(st.mean), ptr(st.cov),
                  ptr(st.sums), ptr(st.ws), s)
+    elif (PeerExchange.get() is not None and d * d <= PeerExchange.get().max_vals):
+        # sharded: the two passes and their two all-reduces over NVLink peer memory, enqueued by one library call
+        px = PeerExchange.get()
+        if getattr(px, "cov_scratch", None) is None:
+            px.cov_scratch = torch.empty(_lib.MAX_PARAMS * _lib.MAX_PARAMS + 1, dtype=torch.float64, device=st.cols.device)
+        px.big_gen += 2
+        px.xg.gen = px.big_gen - 1
+        with _timed("cov"):
+            call("smcb_weighted_cov_xchg", ptr(st.params), stride, ptr(st.w), st.n, d, ptr(st.mean), ptr(st.cov),
+                 ptr(st.sums), ptr(st.ws), C.byref(px.xg), ptr(px.cov_scratch), ptr(px.status), s)
     else:
         with _timed("cov"):
             call("smcb_weighted_sums1", ptr(st.params), stride, ptr(st.w), st.n, d, ptr(st.sums), ptr(st.ws), s)
