@@ -143,3 +143,20 @@ def test_prior_descriptions():
     assert describe_prior(stats.norm(0, 1))[:2] == (4, 1)        # any object with logpdf: host-evaluated column
     with pytest.raises(TypeError):
         describe_prior(3.0)
+
+
+def test_every_documented_runtime_option_exists():
+    """The option names the header documents for smcb_set_option / smcb_get_option are the ones the library knows
+    (an unknown name answers INT64_MIN), and a scoped change is undone."""
+    import smcpy_b200._lib as L
+    text = open(os.path.join(ROOT, "include", "smcb200.h")).read()
+    doc = text[text.index("/* Runtime options"):text.index("int smcb_set_option")]
+    names = re.findall(r'"([a-z0-9_]+)"', doc)
+    assert len(names) >= 17 and "no_pdl" in names and "spring_form" in names, names
+    for n in names:
+        assert L.lib.smcb_get_option(n.encode()) != -(1 << 63), n
+    assert L.lib.smcb_get_option(b"no_such_option") == -(1 << 63)
+    before = L.lib.smcb_get_option(b"spring_form")
+    with L.option("spring_form", 0):
+        assert L.lib.smcb_get_option(b"spring_form") == 0
+    assert L.lib.smcb_get_option(b"spring_form") == before == 1
