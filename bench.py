@@ -105,6 +105,7 @@ class ClockSampler:
         self.index = ",".join(str(i) for i in self.indices)
         self.enabled = enabled
         self._stop = threading.Event()
+        self._ready = threading.Event()
         if not enabled:
             return
         try:
@@ -135,6 +136,16 @@ class ClockSampler:
 
     def _poll(self):
         period = 0.1 if len(self.handles) == 1 else 0.2
+        # the poller is started just BEFORE the barrier that opens the timed region: its first query in a new thread
+        # (1 ms, thread start-up and NVML's per-thread set-up) cost the first timed pass 2 ms when it ran inside it.
+        # That first sample is dropped; every recorded sample is taken during the timed region.
+        try:
+            self._sample()
+        except Exception:
+            pass
+        self.rows, self.sample_ms = [], []
+        self._ready.set()
+        self._stop.wait(period)
         while not self._stop.is_set():
             try:
                 self._sample()
@@ -147,8 +158,10 @@ class ClockSampler:
             return
         self._stop.clear()
         if self.nv is not None:
+            self._ready.clear()
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
+            self._ready.wait(timeout=2)              # the dropped first query is over before the caller goes on
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, "--query-gpu=" + self.Q,
@@ -731,8 +744,8 @@ def run_gpu(args):
 
     # ---- timed: device-resident ------------------------------------------------------------
     sampler_clk = ClockSampler(range(world) if world > 1 else [local], enabled=(rank == 0))
-    barrier()
     sampler_clk.start()
+    barrier()
     _lib.launch_count = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     mlls = []
